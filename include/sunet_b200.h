@@ -1,0 +1,97 @@
+/* sunet_b200.h - C ABI of the B200-native SUNet forward path.
+ *
+ * The reference (mehrdad78/SUNet_TF) is pure PyTorch and has no FFI; the "plugin API" of its forward path is the
+ * nn.Module surface of model/SUNet_detail.py.  Each entry point below replaces the forward of one of those modules
+ * (file:line cited per function).  sunet_tf_b200/modules.py binds them with ctypes and re-exposes the reference's
+ * class names / constructor signatures / state_dict keys.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a cudaStream_t passed as void*.
+ *   - return value: 0 OK, <0 argument/shape/alignment error, >0 cudaError_t.  sunet_last_error() returns the
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - tensors are fp32, contiguous, resident on the current CUDA device, laid out exactly as the reference module
+ *     receives / returns them.  All calls are asynchronous on `stream`.
+ *   - parameters are handed over ONCE at pre-pack time by state_dict key (un-folded, as the reference stores them);
+ *     the library keeps its own fp16 / folded device copies.  Handles are immutable afterwards and may be used from
+ *     one host thread per GPU.
+ *   - whole-model calls never allocate: the caller passes a workspace of sunet_workspace_bytes().  Per-module calls
+ *     take scratch from the stream-ordered allocator (cudaMallocAsync) - they exist for drop-in use and parity
+ *     tests at module granularity, not for throughput.
+ */
+#ifndef SUNET_B200_H
+#define SUNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sunet_handle_s* sunet_handle_t;
+
+int sunet_abi_version(void);
+const char* sunet_last_error(void);
+
+/* Pre-pack the parameters of one module.  `kind` selects the module, `iargs`/`fargs` its constructor arguments,
+ * (names[i], ptrs[i], numels[i]) its fp32 device parameters by state_dict key (relative to the module).
+ *
+ *  kind                iargs                                   fargs        replaces (model/SUNet_detail.py)
+ *  "swin_block"        dim, H, W, num_heads, shift_size        qk_scale     SwinTransformerBlock :157-264
+ *  "window_attention"  dim, num_heads                          qk_scale     WindowAttention      :59-138
+ *  "mlp"               in, hidden, out                         -            Mlp                  :8-24
+ *  "patch_merging"     dim, H, W                               -            PatchMerging         :285-322
+ *  "upsample"          in_channels, factor(2|4), H, W          -            UpSample             :335-386
+ *  "patch_embed"       in_chans, embed_dim, patch, has_norm    -            PatchEmbed           :518-556
+ *  "sunet"             img_size, patch, in_chans, out_chans,   qk_scale     SUNet                :566-755
+ *                      embed_dim, window, depth0..3, heads0..3
+ * qk_scale <= 0 means head_dim ** -0.5 (the reference's `qk_scale or head_dim ** -0.5`, :80).
+ */
+int sunet_prepack(const char* kind, const int64_t* iargs, int n_iargs, const double* fargs, int n_fargs,
+                  const char* const* names, const void* const* ptrs, const int64_t* numels, int n_params, void* stream,
+                  sunet_handle_t* out);
+int sunet_destroy(sunet_handle_t h);
+
+/* SwinTransformerBlock.forward (:227-264): x (B, H*W, C) -> out (B, H*W, C). */
+int sunet_swin_block_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream);
+/* WindowAttention.forward (:107-138): x (num_windows_total, 64, C); mask (mask_nw, 64, 64) fp32 or NULL. */
+int sunet_window_attention_fwd(sunet_handle_t h, const float* x, int64_t num_windows, const float* mask, int mask_nw,
+                               float* out, void* stream);
+/* Mlp.forward (:18-24): x (rows, in) -> out (rows, out). */
+int sunet_mlp_fwd(sunet_handle_t h, const float* x, int64_t rows, float* out, void* stream);
+/* PatchMerging.forward (:301-322): x (B, H*W, C) -> out (B, H*W/4, 2C). */
+int sunet_patch_merging_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream);
+/* UpSample.forward (:365-386): x (B, H*W, C) -> factor 2: (B, 4*H*W, C/2); factor 4: (B, 4H, 4W, C). */
+int sunet_upsample_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream);
+/* PatchEmbed.forward (:548-556): x NCHW (B, in_chans, Himg, Wimg) -> out (B, Himg/p*Wimg/p, embed_dim). */
+int sunet_patch_embed_fwd(sunet_handle_t h, const float* x, int batch, int himg, int wimg, float* out, void* stream);
+
+/* SUNet.forward (:748-755) incl. the 1->3 channel repeat of SUNet_model.forward (model/SUNet.py:26-30):
+ * x NCHW (B, in_chans in {1,3}, img, img) fp32 -> out NCHW (B, out_chans, img, img) fp32.
+ * Batches larger than `max_chunk` images are processed in chunks of max_chunk inside the call (same workspace). */
+size_t sunet_workspace_bytes(sunet_handle_t h, int batch, int max_chunk);
+int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* number of kernels one sunet_forward of `batch` images launches (for bench.py's gpu_launches) */
+int64_t sunet_forward_launches(sunet_handle_t h, int batch, int max_chunk);
+
+/* Any-resolution tile pipeline (demo_any_resolution.py:35-52, :125-139), device side.
+ * sunet_tiles_extract: img NCHW (1, C, h, w) -> tiles (n*n, C, k, k) cut from the zero-padded centred canvas of side X.
+ * sunet_tiles_fold:    tiles (count, C, k, k) covering tile indices [first, first+count) are accumulated into
+ *                      acc (C, X, X) fp32 (must be zeroed by the caller before the first call);
+ * sunet_tiles_finish:  out (1, C, h, w) = clamp(acc / cover_count, 0, 1) cropped to the image region. */
+int sunet_tiles_extract(const float* img, int chans, int h, int w, int kernel, int stride, float* tiles, int first, int count,
+                        void* stream);
+int sunet_tiles_fold(const float* tiles, int chans, int h, int w, int kernel, int stride, int first, int count, float* acc,
+                     void* stream);
+int sunet_tiles_finish(const float* acc, int chans, int h, int w, int kernel, int stride, float* out, void* stream);
+
+/* bring-up / microbenchmarks */
+int sunet_selftest_umma(void* stream);
+/* C[M,N] (fp16) = A[M,K] (fp16) * W[N,K]^T (fp16) + bias; used by tests to pin the tcgen05 GEMM in isolation */
+int sunet_gemm_f16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUNET_B200_H */

@@ -1,0 +1,521 @@
+// Bandwidth-bound kernels: casts, LayerNorm, PatchMerging gather, folded PatchEmbed conv, Dual up-sample combine,
+// folded tail stencil, and the one-off weight pre-pack / fold helpers.  All loads/stores are 8- or 16-byte vectors,
+// consecutive lanes touch consecutive addresses.
+#include "elementwise.cuh"
+#include "error.h"
+
+namespace sunet {
+
+static inline unsigned blocks_for(int64_t n, int per_block) { return static_cast<unsigned>((n + per_block - 1) / per_block); }
+
+// ------------------------------------------------------------------------------------------------ casts
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(in + i + 4));
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+    o2[0] = __floats2half2_rn(a.x, a.y); o2[1] = __floats2half2_rn(a.z, a.w);
+    o2[2] = __floats2half2_rn(b.x, b.y); o2[3] = __floats2half2_rn(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __float2half_rn(in[j]);
+  }
+}
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+    *reinterpret_cast<float4*>(out + i) = make_float4(a.x, a.y, b.x, b.y);
+    *reinterpret_cast<float4*>(out + i + 4) = make_float4(c.x, c.y, d.x, d.y);
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __half2float(in[j]);
+  }
+}
+int cast_f32_to_f16(const float* in, __half* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "cast: 16-byte alignment required");
+  cast_f32_f16_kernel<<<blocks_for((n + 7) / 8, 256), 256, 0, s>>>(in, out, n);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+int cast_f16_to_f32(const __half* in, float* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "cast: 16-byte alignment required");
+  cast_f16_f32_kernel<<<blocks_for((n + 7) / 8, 256), 256, 0, s>>>(in, out, n);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// LPR lanes cooperate on one row; each lane owns up to MAXV 16-byte vectors (8 fp16).  MERGE: the logical row of 4C
+// channels is the 2x2 gather of PatchMerging.
+template <int LPR, int MAXV, bool MERGE>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ in, int64_t ld_in, __half* __restrict__ out,
+                                                        int64_t ld_out, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t M, int C, int H, int W, int Csrc) {
+  const int sub = threadIdx.x % LPR;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+  const bool active = row < M;
+  const int nvec = C >> 3;
+  const __half* src_row = nullptr;
+  int64_t mb = 0, mh = 0, mw = 0;
+  if (active) {
+    if (MERGE) {
+      const int W2 = W >> 1, H2 = H >> 1;
+      mw = row % W2; mh = (row / W2) % H2; mb = row / (static_cast<int64_t>(W2) * H2);
+    } else {
+      src_row = in + row * ld_in;
+    }
+  }
+  float x[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = sub + i * LPR;
+    if (active && v < nvec) {
+      const __half* p;
+      if (MERGE) {
+        const int col = v << 3;
+        const int q = col / Csrc, off = col - q * Csrc;   // segment order TL, BL, TR, BR (SUNet_detail.py:312-316)
+        const int64_t y = 2 * mh + (q & 1), xx = 2 * mw + (q >> 1);
+        p = in + ((mb * H + y) * W + xx) * Csrc + off;
+      } else {
+        p = src_row + (v << 3);
+      }
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        x[i][2 * j] = f.x; x[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = sub + i * LPR;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = x[i][j] - mean; sq += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + 1e-5f);
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = sub + i * LPR;
+    if (v < nvec) {
+      const int col = v << 3;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o2[j] = __floats2half2_rn((x[i][2 * j] - mean) * rstd * g[2 * j] + b[2 * j], (x[i][2 * j + 1] - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
+      *reinterpret_cast<uint4*>(out + row * ld_out + col) = o;
+    }
+  }
+}
+
+template <bool MERGE>
+static int launch_ln(const __half* in, int64_t ld_in, __half* out, int64_t ld_out, const float* gamma, const float* beta, int64_t M,
+                     int C, int H, int W, int Csrc, cudaStream_t s) {
+  if (C % 8 != 0 || C > 32 * 8 * 8) return fail(SUNET_E_SHAPE, "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
+  if ((ld_in % 8) || (ld_out % 8) || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
+    return fail(SUNET_E_ALIGN, "layernorm: 16-byte aligned rows / affine vectors required");
+  const int nvec = C / 8;
+  if (nvec <= 16) {
+    layernorm_kernel<16, 1, MERGE><<<blocks_for(M * 16, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+  } else if (nvec <= 32) {
+    layernorm_kernel<32, 1, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+  } else if (nvec <= 64) {
+    layernorm_kernel<32, 2, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+  } else if (nvec <= 128) {
+    layernorm_kernel<32, 4, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+  } else {
+    layernorm_kernel<32, 8, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+  }
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+int layernorm_f16(const __half* in, int64_t ld_in, __half* out, int64_t ld_out, const float* gamma, const float* beta, int64_t M,
+                  int C, cudaStream_t s) {
+  if (M <= 0) return 0;
+  return launch_ln<false>(in, ld_in, out, ld_out, gamma, beta, M, C, 0, 0, C, s);
+}
+
+int merge_gather_ln_f16(const __half* in, __half* out, const float* gamma, const float* beta, int B, int H, int W, int C,
+                        cudaStream_t s) {
+  if ((H & 1) || (W & 1)) return fail(SUNET_E_SHAPE, "patch merging: grid %dx%d must be even", H, W);
+  if (C % 8) return fail(SUNET_E_SHAPE, "patch merging: C=%d must be a multiple of 8", C);
+  const int64_t M = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+  return launch_ln<true>(in, 0, out, 4 * C, gamma, beta, M, 4 * C, H, W, C, s);
+}
+
+// ------------------------------------------------------------------------------------------------ folded PatchEmbed
+// CTA = 8x8 tokens; warp = one token row (8 tokens); lane = EPL output channels {lane, lane+32, ...}.
+// Per tap: EPL conflict-free weight reads + 8 broadcast input reads feed 8*EPL FMAs.
+template <int EPL>
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, int img_chans, int Himg, int Wimg,
+                                                          const float* __restrict__ wfold, const float* __restrict__ bfold,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          __half* __restrict__ out) {
+  constexpr int E = EPL * 32;
+  constexpr int PITCH = 35;
+  extern __shared__ float sm[];
+  float* s_in = sm;                      // [3][34][PITCH]
+  float* s_w = sm + 3 * 34 * PITCH;      // [108][E]
+  const int GW = Wimg >> 2, GH = Himg >> 2;
+  const int tiles_x = GW >> 3, tiles_y = GH >> 3;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int trem = blockIdx.x % (tiles_x * tiles_y);
+  const int ty0 = (trem / tiles_x) * 8, tx0 = (trem % tiles_x) * 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 108 * E; i += 256) s_w[i] = __ldg(wfold + i);
+  const int y_base = 4 * ty0 - 1, x_base = 4 * tx0 - 1;
+  for (int i = tid; i < 3 * 34 * 34; i += 256) {
+    const int c = i / (34 * 34), r = (i / 34) % 34, col = i % 34;
+    const int y = y_base + r, x = x_base + col;
+    float v = 0.f;
+    if (y >= 0 && y < Himg && x >= 0 && x < Wimg) {
+      const int cs = img_chans == 1 ? 0 : c;   // grey input is repeated to 3 channels (model/SUNet.py:27-28)
+      v = __ldg(img + ((static_cast<int64_t>(b) * img_chans + cs) * Himg + y) * Wimg + x);
+    }
+    s_in[(c * 34 + r) * PITCH + col] = v;
+  }
+  __syncthreads();
+  float acc[8][EPL];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[t][e] = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    for (int u = 0; u < 6; ++u) {
+      const float* in_row = s_in + (c * 34 + 4 * warp + u) * PITCH;
+#pragma unroll
+      for (int v = 0; v < 6; ++v) {
+        const float* wk = s_w + (c * 36 + u * 6 + v) * E + lane;
+        float w[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) w[e] = wk[32 * e];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float xv = in_row[4 * t + v];
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[t][e] = fmaf(xv, w[e], acc[t][e]);
+        }
+      }
+    }
+  }
+  float bia[EPL], gam[EPL], bet[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    bia[e] = __ldg(bfold + lane + 32 * e);
+    gam[e] = __ldg(gamma + lane + 32 * e);
+    bet[e] = __ldg(beta + lane + 32 * e);
+  }
+  const int64_t tok_row0 = (static_cast<int64_t>(b) * GH + ty0 + warp) * GW + tx0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { acc[t][e] += bia[e]; sum += acc[t][e]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / E;
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { const float d = acc[t][e] - mean; sq += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / E + 1e-5f);
+    __half* orow = out + (tok_row0 + t) * E;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) orow[lane + 32 * e] = __float2half_rn((acc[t][e] - mean) * rstd * gam[e] + bet[e]);
+  }
+}
+
+int patch_embed_fused(const float* img, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
+                      const float* gamma, const float* beta, int E, __half* out, cudaStream_t s) {
+  if (img_chans != 1 && img_chans != 3) return fail(SUNET_E_SHAPE, "patch embed: input must have 1 or 3 channels, got %d", img_chans);
+  if (Himg % 32 || Wimg % 32) return fail(SUNET_E_SHAPE, "patch embed: image %dx%d must be a multiple of 32", Himg, Wimg);
+  if (E % 32 || E > 128) return fail(SUNET_E_SHAPE, "patch embed: embed_dim %d must be a multiple of 32 and <= 128", E);
+  const unsigned grid = static_cast<unsigned>(B) * (Himg / 32) * (Wimg / 32);
+  const int smem = (3 * 34 * 35 + 108 * E) * 4;
+#define PE_LAUNCH(EPL)                                                                                          \
+  {                                                                                                             \
+    SUNET_CUDA(cudaFuncSetAttribute(patch_embed_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    patch_embed_kernel<EPL><<<grid, 256, smem, s>>>(img, img_chans, Himg, Wimg, wfold, bfold, gamma, beta, out);   \
+  }
+  switch (E / 32) {
+    case 1: PE_LAUNCH(1); break;
+    case 2: PE_LAUNCH(2); break;
+    case 3: PE_LAUNCH(3); break;
+    default: PE_LAUNCH(4); break;
+  }
+#undef PE_LAUNCH
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void im2col_patch_kernel(const float* __restrict__ img, int Cin, int Himg, int Wimg, int P, __half* __restrict__ out,
+                                    int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int K = Cin * P * P;
+  const int64_t m = i / K;
+  const int k = static_cast<int>(i - m * K);
+  const int c = k / (P * P), ky = (k / P) % P, kx = k % P;
+  const int GW = Wimg / P, GH = Himg / P;
+  const int px = static_cast<int>(m % GW), py = static_cast<int>((m / GW) % GH);
+  const int64_t b = m / (static_cast<int64_t>(GW) * GH);
+  out[i] = __float2half_rn(__ldg(img + ((b * Cin + c) * Himg + py * P + ky) * Wimg + px * P + kx));
+}
+int im2col_patch(const float* img, int B, int Cin, int Himg, int Wimg, int P, __half* out, cudaStream_t s) {
+  if (Himg % P || Wimg % P) return fail(SUNET_E_SHAPE, "im2col: image %dx%d not divisible by patch %d", Himg, Wimg, P);
+  const int64_t total = static_cast<int64_t>(B) * (Himg / P) * (Wimg / P) * Cin * P * P;
+  im2col_patch_kernel<<<blocks_for(total, 256), 256, 0, s>>>(img, Cin, Himg, Wimg, P, out, total);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Dual up-sample
+// align_corners=False taps along one axis (nn.Upsample, SUNet_detail.py:351/:362)
+__device__ __forceinline__ void bilinear_tap(int d, int r, int n, int& i0, int& i1, float& lam) {
+  const float src = fmaxf((d + 0.5f) / r - 0.5f, 0.f);
+  i0 = static_cast<int>(src);
+  i1 = min(i0 + 1, n - 1);
+  lam = src - i0;
+}
+
+__global__ void __launch_bounds__(256) upsample_combine_kernel(const __half* __restrict__ Yp, const __half* __restrict__ Z,
+                                                               void* __restrict__ out, int out_f32, int H, int W, int Co, int r,
+                                                               int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int nv = Co >> 3;
+  const int v = static_cast<int>(i % nv);
+  const int64_t pix = i / nv;
+  const int OW = W * r, OH = H * r;
+  const int X = static_cast<int>(pix % OW), Y = static_cast<int>((pix / OW) % OH);
+  const int64_t b = pix / (static_cast<int64_t>(OW) * OH);
+  const int h = Y / r, ii = Y % r, w = X / r, jj = X % r;
+  const uint4 yp = __ldg(reinterpret_cast<const uint4*>(Yp + (((b * H + h) * W + w) * (r * r) + ii * r + jj) * Co + (v << 3)));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_tap(Y, r, H, y0, y1, ly);
+  bilinear_tap(X, r, W, x0, x1, lx);
+  const __half* zb = Z + b * H * W * Co + (v << 3);
+  const uint4 z00 = __ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(y0) * W + x0) * Co));
+  const uint4 z01 = __ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(y0) * W + x1) * Co));
+  const uint4 z10 = __ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(y1) * W + x0) * Co));
+  const uint4 z11 = __ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(y1) * W + x1) * Co));
+  const __half2 *p = reinterpret_cast<const __half2*>(&yp), *a = reinterpret_cast<const __half2*>(&z00),
+                *bq = reinterpret_cast<const __half2*>(&z01), *c = reinterpret_cast<const __half2*>(&z10),
+                *d = reinterpret_cast<const __half2*>(&z11);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fp = __half22float2(p[j]), fa = __half22float2(a[j]), fb = __half22float2(bq[j]), fc = __half22float2(c[j]),
+                 fd = __half22float2(d[j]);
+    // same evaluation order as the separable form: rows first, then columns
+    const float tx = (fa.x * (1.f - ly) + fc.x * ly), ux = (fb.x * (1.f - ly) + fd.x * ly);
+    const float ty = (fa.y * (1.f - ly) + fc.y * ly), uy = (fb.y * (1.f - ly) + fd.y * ly);
+    f[2 * j] = fp.x + tx * (1.f - lx) + ux * lx;
+    f[2 * j + 1] = fp.y + ty * (1.f - lx) + uy * lx;
+  }
+  if (out_f32) {
+    float* o = static_cast<float*>(out) + pix * Co + (v << 3);
+    *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(static_cast<__half*>(out) + pix * Co + (v << 3)) = o;
+  }
+}
+
+int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, int B, int H, int W, int Co, int r, cudaStream_t s) {
+  if (Co % 8) return fail(SUNET_E_SHAPE, "upsample: Co=%d must be a multiple of 8", Co);
+  const int64_t total = static_cast<int64_t>(B) * H * r * W * r * (Co / 8);
+  upsample_combine_kernel<<<blocks_for(total, 256), 256, 0, s>>>(Yp, Z, out, out_f32, H, W, Co, r, total);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ folded tail stencil
+__global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restrict__ Qp, const float* __restrict__ Rb,
+                                                           float* __restrict__ out, int H, int W, int OC, int NT, int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int OW = 4 * W, OH = 4 * H;
+  const int x = static_cast<int>(i % OW), y = static_cast<int>((i / OW) % OH);
+  const int64_t b = i / (static_cast<int64_t>(OW) * OH);
+  int yy0[3], yy1[3], xx0[3], xx1[3];
+  float ly[3], lx[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    bilinear_tap(min(max(y + d - 1, 0), OH - 1), 4, H, yy0[d], yy1[d], ly[d]);
+    bilinear_tap(min(max(x + d - 1, 0), OW - 1), 4, W, xx0[d], xx1[d], lx[d]);
+  }
+  float acc[3] = {0.f, 0.f, 0.f};
+  const float* rb = Rb + b * H * W * NT;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int ny = y + dy - 1;
+    if (ny < 0 || ny >= OH) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int nx = x + dx - 1;
+      if (nx < 0 || nx >= OW) continue;
+      const int t = dy * 3 + dx;
+      const float* q = Qp + ((((b * H + (ny >> 2)) * W + (nx >> 2)) << 4) + ((ny & 3) << 2) + (nx & 3)) * NT;
+      const float* r00 = rb + (static_cast<int64_t>(yy0[dy]) * W + xx0[dx]) * NT;
+      const float* r01 = rb + (static_cast<int64_t>(yy0[dy]) * W + xx1[dx]) * NT;
+      const float* r10 = rb + (static_cast<int64_t>(yy1[dy]) * W + xx0[dx]) * NT;
+      const float* r11 = rb + (static_cast<int64_t>(yy1[dy]) * W + xx1[dx]) * NT;
+      for (int oc = 0; oc < OC; ++oc) {
+        const int col = oc * 9 + t;
+        const float top = __ldg(r00 + col) * (1.f - ly[dy]) + __ldg(r10 + col) * ly[dy];
+        const float bot = __ldg(r01 + col) * (1.f - ly[dy]) + __ldg(r11 + col) * ly[dy];
+        acc[oc] += __ldg(q + col) + top * (1.f - lx[dx]) + bot * lx[dx];
+      }
+    }
+  }
+  for (int oc = 0; oc < OC; ++oc) out[((b * OC + oc) * OH + y) * OW + x] = acc[oc];
+}
+
+int tail_stencil(const float* Qp, const float* Rb, float* out, int B, int H, int W, int OC, int NT, cudaStream_t s) {
+  if (OC < 1 || OC > 3 || NT < OC * 9) return fail(SUNET_E_SHAPE, "tail: out_chans=%d (1..3) NT=%d", OC, NT);
+  const int64_t total = static_cast<int64_t>(B) * 16 * H * W;
+  tail_stencil_kernel<<<blocks_for(total, 256), 256, 0, s>>>(Qp, Rb, out, H, W, OC, NT, total);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ pre-pack helpers
+__global__ void pack_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int K, int scale_rows, float scale) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(N) * K) return;
+  const int n = static_cast<int>(i / K);
+  dst[i] = __float2half_rn(src[i] * (n < scale_rows ? scale : 1.f));
+}
+int pack_weight_f16(const float* src, __half* dst, int N, int K, int scale_rows, float scale, cudaStream_t s) {
+  pack_weight_kernel<<<blocks_for(static_cast<int64_t>(N) * K, 256), 256, 0, s>>>(src, dst, N, K, scale_rows, scale);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void pack_weight_shuffle_kernel(const float* __restrict__ src, __half* __restrict__ dst, int Cq, int rr, int K) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(Cq) * rr * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  const int c = n / rr, ij = n % rr;
+  dst[(static_cast<int64_t>(ij) * Cq + c) * K + k] = __float2half_rn(src[i]);
+}
+int pack_weight_shuffle_f16(const float* src, __half* dst, int Cq, int rr, int K, cudaStream_t s) {
+  pack_weight_shuffle_kernel<<<blocks_for(static_cast<int64_t>(Cq) * rr * K, 256), 256, 0, s>>>(src, dst, Cq, rr, K);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int scale_n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * (i < scale_n ? scale : 1.f);
+}
+int scale_copy_f32(const float* src, float* dst, int n, int scale_n, float scale, cudaStream_t s) {
+  scale_copy_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, dst, n, scale_n, scale);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void matmul_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                  int ldc, int m, int n, int k) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(m) * n) return;
+  const int r = static_cast<int>(i / n), c = static_cast<int>(i % n);
+  float acc = 0.f;
+  for (int j = 0; j < k; ++j) acc = fmaf(A[static_cast<int64_t>(r) * lda + j], B[static_cast<int64_t>(j) * ldb + c], acc);
+  C[static_cast<int64_t>(r) * ldc + c] = acc;
+}
+int matmul_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int m, int n, int k, cudaStream_t s) {
+  matmul_f32_kernel<<<blocks_for(static_cast<int64_t>(m) * n, 256), 256, 0, s>>>(A, lda, B, ldb, C, ldc, m, n, k);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void fold_patch_embed_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                        const float* __restrict__ b2, int Cin, int E, float* __restrict__ wfold,
+                                        float* __restrict__ bfold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Kf = Cin * 36;
+  if (i < Kf * E) {
+    const int k = i / E, e = i % E;
+    const int c = k / 36, u = (k / 6) % 6, v = k % 6;
+    double acc = 0.0;
+    for (int m = 0; m < E; ++m)
+      for (int ky = 0; ky < 4; ++ky) {
+        const int dy = u - ky;
+        if (dy < 0 || dy > 2) continue;
+        for (int kx = 0; kx < 4; ++kx) {
+          const int dx = v - kx;
+          if (dx < 0 || dx > 2) continue;
+          acc += static_cast<double>(w2[((e * E + m) * 4 + ky) * 4 + kx]) * w1[((m * Cin + c) * 3 + dy) * 3 + dx];
+        }
+      }
+    wfold[i] = static_cast<float>(acc);
+  }
+  if (i < E) {
+    double acc = b2[i];
+    for (int m = 0; m < E; ++m) {
+      double sw = 0.0;
+      for (int q = 0; q < 16; ++q) sw += w2[(i * E + m) * 16 + q];
+      acc += sw * b1[m];
+    }
+    bfold[i] = static_cast<float>(acc);
+  }
+}
+int fold_patch_embed(const float* w1, const float* b1, const float* w2, const float* b2, int Cin, int E, float* wfold, float* bfold,
+                     cudaStream_t s) {
+  fold_patch_embed_kernel<<<blocks_for(static_cast<int64_t>(Cin) * 36 * E, 128), 128, 0, s>>>(w1, b1, w2, b2, Cin, E, wfold, bfold);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void fold_tail_taps_kernel(const float* __restrict__ Wo, const float* __restrict__ A, __half* __restrict__ G, int OC, int E,
+                                      int NT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NT * E) return;
+  const int row = i / E, c = i % E;
+  float acc = 0.f;
+  if (row < OC * 9) {
+    const int oc = row / 9, t = row % 9;
+    double a = 0.0;
+    for (int m = 0; m < E; ++m) a += static_cast<double>(Wo[(oc * E + m) * 9 + t]) * A[m * E + c];
+    acc = static_cast<float>(a);
+  }
+  G[i] = __float2half_rn(acc);
+}
+int fold_tail_taps(const float* Wo, const float* A, __half* G, int OC, int E, int NT, cudaStream_t s) {
+  fold_tail_taps_kernel<<<blocks_for(static_cast<int64_t>(NT) * E, 128), 128, 0, s>>>(Wo, A, G, OC, E, NT);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace sunet

@@ -1,0 +1,737 @@
+// Host-side engine + C ABI: parameter pre-pack (fp16 cast, qk_scale fold, linear folds) and the forward sequencing
+// of SUNet (model/SUNet_detail.py:706-755) over the kernels in gemm_tcgen05.cu / attn_core.cu / elementwise.cu.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/sunet_b200.h"
+#include "attn_core.cuh"
+#include "elementwise.cuh"
+#include "error.h"
+#include "gemm.cuh"
+
+namespace sunet {
+
+// ------------------------------------------------------------------------------------------------ infrastructure
+struct Arena {  // device allocations owned by a handle (pre-pack time only)
+  std::vector<void*> ptrs;
+  ~Arena() { for (void* p : ptrs) cudaFree(p); }
+  int alloc(void** out, size_t bytes) {
+    void* p = nullptr;
+    SUNET_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    ptrs.push_back(p);
+    *out = p;
+    return 0;
+  }
+  template <typename T> int alloc_t(T** out, size_t n) { return alloc(reinterpret_cast<void**>(out), n * sizeof(T)); }
+};
+
+struct Params {
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> m;
+  bool has(const std::string& k) const { return m.count(k) != 0; }
+  int get(const std::string& k, int64_t numel, const float** out) const {
+    auto it = m.find(k);
+    if (it == m.end()) return fail(SUNET_E_ARG, "missing parameter '%s'", k.c_str());
+    if (it->second.second != numel)
+      return fail(SUNET_E_SHAPE, "parameter '%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.second, (long long)numel);
+    *out = it->second.first;
+    return 0;
+  }
+};
+
+// bump allocator over caller-provided scratch; `dry` only measures the high-water mark
+struct Scratch {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  int take(void** out, size_t bytes) {
+    const size_t a = (off + 255) & ~size_t(255);
+    if (!dry && a + bytes > cap) return fail(SUNET_E_WORKSPACE, "workspace too small: need %zu bytes, have %zu", a + bytes, cap);
+    *out = base + a;
+    off = a + bytes;
+    if (off > peak) peak = off;
+    return 0;
+  }
+  template <typename T> int take_t(T** out, size_t n) { return take(reinterpret_cast<void**>(out), n * sizeof(T)); }
+};
+struct ScratchMark {  // stack discipline
+  Scratch& s; size_t saved;
+  explicit ScratchMark(Scratch& sc) : s(sc), saved(sc.off) {}
+  ~ScratchMark() { s.off = saved; }
+};
+
+struct Ctx {
+  Scratch sc;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  bool dry() const { return sc.dry; }
+};
+
+#define RUN(ctx, expr)            \
+  do {                            \
+    (ctx).launches++;             \
+    if (!(ctx).dry()) SUNET_TRY(expr); \
+  } while (0)
+
+struct Linear {
+  __half* w = nullptr;
+  float* b = nullptr;
+  int N = 0, K = 0;
+};
+
+static int pack_linear(Arena& ar, const Params& P, const std::string& wkey, const std::string& bkey, int N, int K, Linear* L,
+                       cudaStream_t s, int scale_rows = 0, float scale = 1.f) {
+  const float* w;
+  SUNET_TRY(P.get(wkey, static_cast<int64_t>(N) * K, &w));
+  L->N = N; L->K = K;
+  SUNET_TRY(ar.alloc_t(&L->w, static_cast<size_t>(N) * K));
+  SUNET_TRY(pack_weight_f16(w, L->w, N, K, scale_rows, scale, s));
+  if (!bkey.empty() && P.has(bkey)) {
+    const float* b;
+    SUNET_TRY(P.get(bkey, N, &b));
+    SUNET_TRY(ar.alloc_t(&L->b, N));
+    SUNET_TRY(scale_copy_f32(b, L->b, N, scale_rows, scale, s));
+  }
+  return 0;
+}
+static int copy_vec(Arena& ar, const Params& P, const std::string& key, int n, float** out, cudaStream_t s) {
+  const float* src;
+  SUNET_TRY(P.get(key, n, &src));
+  SUNET_TRY(ar.alloc_t(out, n));
+  SUNET_CUDA(cudaMemcpyAsync(*out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+static int run_linear(Ctx& c, const Linear& L, const __half* A, int64_t lda, int64_t M, void* C, int64_t ldc, int act = ACT_NONE,
+                      const float* prelu = nullptr, const __half* R = nullptr, int64_t ldr = 0, int out_f32 = 0,
+                      const __half* A1 = nullptr, int64_t lda1 = 0, int K1 = 0) {
+  GemmArgs a;
+  a.A0 = A; a.lda0 = lda; a.K0 = L.K - K1;
+  a.A1 = A1; a.lda1 = lda1; a.K1 = K1;
+  a.W = L.w; a.ldw = L.K; a.M = M; a.N = L.N;
+  a.bias = L.b; a.act = act; a.prelu = prelu; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.out_f32 = out_f32;
+  RUN(c, gemm_run(a, c.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ module packs
+struct Handle {
+  std::string kind;
+  Arena arena;
+  virtual ~Handle() {}
+};
+
+struct AttnPack {  // WindowAttention parameters (SUNet_detail.py:83-105)
+  int dim = 0, heads = 0;
+  float scale = 1.f;
+  Linear qkv, proj;
+  float* table = nullptr;
+  int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int heads_, double qk_scale, cudaStream_t s) {
+    dim = dim_; heads = heads_;
+    if (heads <= 0 || dim % heads) return fail(SUNET_E_SHAPE, "attention: dim %d not divisible by heads %d", dim, heads);
+    scale = qk_scale > 0 ? static_cast<float>(qk_scale) : 1.f / sqrtf(static_cast<float>(dim / heads));  // :80
+    // q = q * scale (:117) folded into the first `dim` rows of qkv.weight / qkv.bias
+    SUNET_TRY(pack_linear(ar, P, pre + "qkv.weight", pre + "qkv.bias", 3 * dim, dim, &qkv, s, dim, scale));
+    SUNET_TRY(pack_linear(ar, P, pre + "proj.weight", pre + "proj.bias", dim, dim, &proj, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "relative_position_bias_table", 225 * heads, &table, s));
+    return 0;
+  }
+};
+
+struct MlpPack {
+  int cin = 0, hid = 0, cout = 0;
+  Linear fc1, fc2;
+  int pack(Arena& ar, const Params& P, const std::string& pre, int cin_, int hid_, int cout_, cudaStream_t s) {
+    cin = cin_; hid = hid_; cout = cout_;
+    SUNET_TRY(pack_linear(ar, P, pre + "fc1.weight", pre + "fc1.bias", hid, cin, &fc1, s));
+    SUNET_TRY(pack_linear(ar, P, pre + "fc2.weight", pre + "fc2.bias", cout, hid, &fc2, s));
+    return 0;
+  }
+};
+
+struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
+  int dim = 0, H = 0, W = 0, heads = 0, shift = 0;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  AttnPack attn;
+  MlpPack mlp;
+  int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, int heads_, int shift_, double qk_scale,
+           cudaStream_t s) {
+    dim = dim_; H = H_; W = W_; heads = heads_; shift = shift_;
+    if (H % 8 || W % 8) return fail(SUNET_E_SHAPE, "swin block: grid %dx%d must be a multiple of the 8x8 window", H, W);
+    if ((H < W ? H : W) <= 8) shift = 0;  // :186-189
+    if (shift != 0 && shift != 4) return fail(SUNET_E_SHAPE, "swin block: shift_size %d unsupported (0 or 4)", shift);
+    SUNET_TRY(copy_vec(ar, P, pre + "norm1.weight", dim, &g1, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "norm1.bias", dim, &b1, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "norm2.weight", dim, &g2, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "norm2.bias", dim, &b2, s));
+    SUNET_TRY(attn.pack(ar, P, pre + "attn.", dim, heads, qk_scale, s));
+    SUNET_TRY(mlp.pack(ar, P, pre + "mlp.", dim, 4 * dim, dim, s));
+    return 0;
+  }
+  // x_in [B*H*W][dim] -> x_out (may alias x_in); image-order rows throughout
+  int forward(Ctx& c, const __half* x_in, __half* x_out, int B) const {
+    ScratchMark mk(c.sc);
+    const int64_t M = static_cast<int64_t>(B) * H * W;
+    __half *T, *QKV, *O, *Hd;
+    SUNET_TRY(c.sc.take_t(&T, M * dim));
+    SUNET_TRY(c.sc.take_t(&QKV, M * 3 * dim));
+    SUNET_TRY(c.sc.take_t(&O, M * dim));
+    SUNET_TRY(c.sc.take_t(&Hd, M * 4 * dim));
+    RUN(c, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                       // :233
+    SUNET_TRY(run_linear(c, attn.qkv, T, dim, M, QKV, 3 * dim));                               // :114
+    AttnCoreArgs a;
+    a.qkv = QKV; a.ld = 3 * dim; a.out = O; a.ldo = dim; a.B = B; a.H = H; a.W = W; a.C = dim; a.heads = heads;
+    a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
+    RUN(c, attn_core_launch(a, c.stream));                                                    // :118-135, :236-257
+    SUNET_TRY(run_linear(c, attn.proj, O, dim, M, x_out, dim, ACT_NONE, nullptr, x_in, dim));   // :136, :261
+    RUN(c, layernorm_f16(x_out, dim, T, dim, g2, b2, M, dim, c.stream));                      // :262
+    SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
+    SUNET_TRY(run_linear(c, mlp.fc2, Hd, 4 * dim, M, x_out, dim, ACT_NONE, nullptr, x_out, dim));  // :22, :262
+    return 0;
+  }
+};
+
+struct MergePack {  // PatchMerging (SUNet_detail.py:294-322)
+  int dim = 0, H = 0, W = 0;
+  float *g = nullptr, *b = nullptr;
+  Linear red;
+  int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, cudaStream_t s) {
+    dim = dim_; H = H_; W = W_;
+    SUNET_TRY(copy_vec(ar, P, pre + "norm.weight", 4 * dim, &g, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "norm.bias", 4 * dim, &b, s));
+    SUNET_TRY(pack_linear(ar, P, pre + "reduction.weight", "", 2 * dim, 4 * dim, &red, s));
+    return 0;
+  }
+  int forward(Ctx& c, const __half* x, __half* y, int B) const {
+    ScratchMark mk(c.sc);
+    const int64_t M4 = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+    __half* T;
+    SUNET_TRY(c.sc.take_t(&T, M4 * 4 * dim));
+    RUN(c, merge_gather_ln_f16(x, T, g, b, B, H, W, dim, c.stream));
+    SUNET_TRY(run_linear(c, red, T, 4 * dim, M4, y, 2 * dim));
+    return 0;
+  }
+};
+
+// Dual up-sample (SUNet_detail.py:335-386) with its linear tail folded:
+//   out = conv([up_p, up_b]) = (Wc[:, :Cq] Wp3) PS(prelu(Wp0 x)) + bilinear((Wc[:, Cq:] Wb3) prelu(Wb0 x + b))
+// (1x1 convs without bias commute with the interpolation, whose taps sum to 1).
+struct UpPack {
+  int C = 0, r = 0, H = 0, W = 0, Cq = 0, Co = 0;
+  Linear p0, b0, pp, zz;
+  float *slope_p = nullptr, *slope_b = nullptr;
+  float *Ap = nullptr, *Ab = nullptr;  // fp32 folded matrices (kept for the tail fold)
+  int pack(Arena& ar, const Params& P, const std::string& pre, int C_, int r_, int H_, int W_, cudaStream_t s) {
+    C = C_; r = r_; H = H_; W = W_;
+    if (r != 2 && r != 4) return fail(SUNET_E_SHAPE, "upsample: factor %d unsupported (2 or 4)", r);
+    Cq = r == 2 ? C / 2 : C;
+    Co = Cq;
+    const int rr = r * r;
+    const float *wc, *wp0, *wp3, *wb3;
+    SUNET_TRY(P.get(pre + "conv.weight", static_cast<int64_t>(Co) * 2 * Cq, &wc));
+    SUNET_TRY(P.get(pre + "up_p.0.weight", static_cast<int64_t>(rr) * Cq * C, &wp0));
+    SUNET_TRY(P.get(pre + "up_p.3.weight", static_cast<int64_t>(Cq) * Cq, &wp3));
+    SUNET_TRY(P.get(pre + "up_b.3.weight", static_cast<int64_t>(Co) * C, &wb3));
+    // pixel-shuffle reorder of up_p[0] rows: (c*rr + ij) -> (ij*Cq + c), so each hi-res pixel's Cq channels are contiguous
+    p0.N = rr * Cq; p0.K = C;
+    SUNET_TRY(ar.alloc_t(&p0.w, static_cast<size_t>(p0.N) * C));
+    SUNET_TRY(pack_weight_shuffle_f16(wp0, p0.w, Cq, rr, C, s));
+    SUNET_TRY(pack_linear(ar, P, pre + "up_b.0.weight", pre + "up_b.0.bias", C, C, &b0, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "up_p.1.weight", 1, &slope_p, s));
+    SUNET_TRY(copy_vec(ar, P, pre + "up_b.1.weight", 1, &slope_b, s));
+    SUNET_TRY(ar.alloc_t(&Ap, static_cast<size_t>(Co) * Cq));
+    SUNET_TRY(ar.alloc_t(&Ab, static_cast<size_t>(Co) * C));
+    SUNET_TRY(matmul_f32(wc, 2 * Cq, wp3, Cq, Ap, Cq, Co, Cq, Cq, s));            // Wc[:, :Cq] @ Wp3
+    SUNET_TRY(matmul_f32(wc + Cq, 2 * Cq, wb3, C, Ab, C, Co, C, Co, s));          // Wc[:, Cq:] @ Wb3
+    pp.N = Co; pp.K = Cq; zz.N = Co; zz.K = C;
+    SUNET_TRY(ar.alloc_t(&pp.w, static_cast<size_t>(Co) * Cq));
+    SUNET_TRY(ar.alloc_t(&zz.w, static_cast<size_t>(Co) * C));
+    SUNET_TRY(pack_weight_f16(Ap, pp.w, Co, Cq, 0, 1.f, s));
+    SUNET_TRY(pack_weight_f16(Ab, zz.w, Co, C, 0, 1.f, s));
+    return 0;
+  }
+  // x [B*H*W][C] -> out raster [B*rH*rW][Co] (fp16, or fp32 when out_f32)
+  int forward(Ctx& c, const __half* x, void* out, int out_f32, int B) const {
+    ScratchMark mk(c.sc);
+    const int64_t M = static_cast<int64_t>(B) * H * W;
+    const int rr = r * r;
+    __half *Pb, *Yp, *Bb, *Z;
+    SUNET_TRY(c.sc.take_t(&Pb, M * rr * Cq));
+    SUNET_TRY(c.sc.take_t(&Yp, M * rr * Co));
+    SUNET_TRY(c.sc.take_t(&Bb, M * C));
+    SUNET_TRY(c.sc.take_t(&Z, M * Co));
+    SUNET_TRY(run_linear(c, p0, x, C, M, Pb, rr * Cq, ACT_PRELU, slope_p));           // up_p[0..2]
+    SUNET_TRY(run_linear(c, pp, Pb, Cq, M * rr, Yp, Co));                             // up_p[3] + conv (p half)
+    SUNET_TRY(run_linear(c, b0, x, C, M, Bb, C, ACT_PRELU, slope_b));                 // up_b[0..1]
+    SUNET_TRY(run_linear(c, zz, Bb, C, M, Z, Co));                                    // up_b[3] + conv (b half), at low res
+    RUN(c, upsample_combine(Yp, Z, out, out_f32, B, H, W, Co, r, c.stream));          // pixel shuffle + bilinear + add
+    return 0;
+  }
+};
+
+// Final x4 Dual up-sample + 3x3 output conv (SUNet_detail.py:742-753) folded into per-tap scalar maps.
+struct TailPack {
+  UpPack up;
+  int E = 0, OC = 0, NT = 0, H = 0, W = 0;
+  Linear gp, gb;
+  int pack(Arena& ar, const Params& P, const std::string& up_pre, const std::string& out_key, int E_, int OC_, int H_, int W_,
+           cudaStream_t s) {
+    E = E_; OC = OC_; H = H_; W = W_;
+    if (OC < 1 || OC > 3) return fail(SUNET_E_SHAPE, "out_chans %d unsupported (1..3)", OC);
+    NT = (OC * 9 + 15) / 16 * 16;
+    SUNET_TRY(up.pack(ar, P, up_pre, E, 4, H, W, s));
+    const float* wo;
+    SUNET_TRY(P.get(out_key, static_cast<int64_t>(OC) * E * 9, &wo));
+    gp.N = NT; gp.K = E; gb.N = NT; gb.K = E;
+    SUNET_TRY(ar.alloc_t(&gp.w, static_cast<size_t>(NT) * E));
+    SUNET_TRY(ar.alloc_t(&gb.w, static_cast<size_t>(NT) * E));
+    SUNET_TRY(fold_tail_taps(wo, up.Ap, gp.w, OC, E, NT, s));
+    SUNET_TRY(fold_tail_taps(wo, up.Ab, gb.w, OC, E, NT, s));
+    return 0;
+  }
+  int forward(Ctx& c, const __half* x, float* out, int B) const {
+    ScratchMark mk(c.sc);
+    const int64_t M = static_cast<int64_t>(B) * H * W;
+    __half *Pb, *Bb;
+    float *Qp, *Rb;
+    SUNET_TRY(c.sc.take_t(&Pb, M * 16 * E));
+    SUNET_TRY(c.sc.take_t(&Qp, M * 16 * NT));
+    SUNET_TRY(c.sc.take_t(&Bb, M * E));
+    SUNET_TRY(c.sc.take_t(&Rb, M * NT));
+    SUNET_TRY(run_linear(c, up.p0, x, E, M, Pb, 16 * E, ACT_PRELU, up.slope_p));
+    SUNET_TRY(run_linear(c, gp, Pb, E, M * 16, Qp, NT, ACT_NONE, nullptr, nullptr, 0, 1));
+    SUNET_TRY(run_linear(c, up.b0, x, E, M, Bb, E, ACT_PRELU, up.slope_b));
+    SUNET_TRY(run_linear(c, gb, Bb, E, M, Rb, NT, ACT_NONE, nullptr, nullptr, 0, 1));
+    RUN(c, tail_stencil(Qp, Rb, out, B, H, W, OC, NT, c.stream));
+    return 0;
+  }
+};
+
+struct PatchEmbedPack {  // stand-alone PatchEmbed (SUNet_detail.py:529-556)
+  int cin = 0, E = 0, P = 0, has_norm = 0;
+  Linear proj;
+  float *g = nullptr, *b = nullptr;
+};
+
+struct ModelPack {
+  int img = 0, patch = 0, in_chans = 0, out_chans = 0, E = 0, G = 0;
+  int depths[4] = {0, 0, 0, 0}, heads[4] = {0, 0, 0, 0};
+  float *wfold = nullptr, *bfold = nullptr, *pe_g = nullptr, *pe_b = nullptr;
+  std::vector<BlockPack> enc[4], dec[4];
+  MergePack merge[3];
+  float *norm_g = nullptr, *norm_b = nullptr, *normup_g = nullptr, *normup_b = nullptr;
+  UpPack up0, ups[4];
+  Linear cat[4];
+  TailPack tail;
+};
+
+// ------------------------------------------------------------------------------------------------ typed handles
+struct BlockHandle : Handle { BlockPack p; };
+struct AttnHandle : Handle { AttnPack p; };
+struct MlpHandle : Handle { MlpPack p; };
+struct MergeHandle : Handle { MergePack p; };
+struct UpHandle : Handle { UpPack p; };
+struct PatchEmbedHandle : Handle { PatchEmbedPack p; };
+struct ModelHandle : Handle { ModelPack p; };
+
+static int pack_model(ModelHandle* h, const Params& P, const int64_t* ia, int nia, double qk_scale, cudaStream_t s) {
+  if (nia < 14) return fail(SUNET_E_ARG, "sunet: 14 integer arguments expected, got %d", nia);
+  ModelPack& m = h->p;
+  Arena& ar = h->arena;
+  m.img = (int)ia[0]; m.patch = (int)ia[1]; m.in_chans = (int)ia[2]; m.out_chans = (int)ia[3]; m.E = (int)ia[4];
+  const int window = (int)ia[5];
+  for (int i = 0; i < 4; ++i) { m.depths[i] = (int)ia[6 + i]; m.heads[i] = (int)ia[10 + i]; }
+  if (window != 8) return fail(SUNET_E_SHAPE, "sunet: window_size %d unsupported (8)", window);
+  if (m.patch != 4) return fail(SUNET_E_SHAPE, "sunet: patch_size %d unsupported (4)", m.patch);
+  if (m.in_chans != 3) return fail(SUNET_E_SHAPE, "sunet: in_chans %d unsupported (3; grey inputs are repeated)", m.in_chans);
+  if (m.img % 256) return fail(SUNET_E_SHAPE, "sunet: img_size %d must be a multiple of 256 (8x8 windows at 4 scales)", m.img);
+  m.G = m.img / m.patch;
+  const int E = m.E, G = m.G;
+  // conv_first o patch_embed.proj -> 6x6 / stride 4 / pad 1 (exact linear fold)
+  const float *w1, *b1, *w2, *b2;
+  SUNET_TRY(P.get("conv_first.weight", static_cast<int64_t>(E) * 3 * 9, &w1));
+  SUNET_TRY(P.get("conv_first.bias", E, &b1));
+  SUNET_TRY(P.get("patch_embed.proj.weight", static_cast<int64_t>(E) * E * 16, &w2));
+  SUNET_TRY(P.get("patch_embed.proj.bias", E, &b2));
+  SUNET_TRY(ar.alloc_t(&m.wfold, static_cast<size_t>(108) * E));
+  SUNET_TRY(ar.alloc_t(&m.bfold, E));
+  SUNET_TRY(fold_patch_embed(w1, b1, w2, b2, 3, E, m.wfold, m.bfold, s));
+  if (P.has("patch_embed.norm.weight")) {
+    SUNET_TRY(copy_vec(ar, P, "patch_embed.norm.weight", E, &m.pe_g, s));
+    SUNET_TRY(copy_vec(ar, P, "patch_embed.norm.bias", E, &m.pe_b, s));
+  } else {
+    return fail(SUNET_E_ARG, "sunet: patch_norm=False is not supported by the fused patch embed");
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int dim = E << i, H = G >> i;
+    m.enc[i].resize(m.depths[i]);
+    for (int j = 0; j < m.depths[i]; ++j) {
+      const std::string pre = "layers." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
+      SUNET_TRY(m.enc[i][j].pack(ar, P, pre, dim, H, H, m.heads[i], (j % 2 == 0) ? 0 : 4, qk_scale, s));  // :423
+    }
+    if (i < 3) SUNET_TRY(m.merge[i].pack(ar, P, "layers." + std::to_string(i) + ".downsample.", dim, H, H, s));
+  }
+  SUNET_TRY(copy_vec(ar, P, "norm.weight", E * 8, &m.norm_g, s));
+  SUNET_TRY(copy_vec(ar, P, "norm.bias", E * 8, &m.norm_b, s));
+  SUNET_TRY(copy_vec(ar, P, "norm_up.weight", E, &m.normup_g, s));
+  SUNET_TRY(copy_vec(ar, P, "norm_up.bias", E, &m.normup_b, s));
+  SUNET_TRY(m.up0.pack(ar, P, "layers_up.0.", E * 8, 2, G >> 3, G >> 3, s));
+  for (int inx = 1; inx < 4; ++inx) {
+    const int i = 3 - inx;
+    const int dim = E << i, H = G >> i;
+    SUNET_TRY(pack_linear(ar, P, "concat_back_dim." + std::to_string(inx) + ".weight", "concat_back_dim." + std::to_string(inx) + ".bias",
+                          dim, 2 * dim, &m.cat[inx], s));
+    m.dec[inx].resize(m.depths[i]);
+    for (int j = 0; j < m.depths[i]; ++j) {
+      const std::string pre = "layers_up." + std::to_string(inx) + ".blocks." + std::to_string(j) + ".";
+      SUNET_TRY(m.dec[inx][j].pack(ar, P, pre, dim, H, H, m.heads[i], (j % 2 == 0) ? 0 : 4, qk_scale, s));  // :493
+    }
+    if (inx < 3) SUNET_TRY(m.ups[inx].pack(ar, P, "layers_up." + std::to_string(inx) + ".upsample.", dim, 2, H, H, s));
+  }
+  SUNET_TRY(m.tail.pack(ar, P, "up.", "output.weight", E, m.out_chans, G, G, s));
+  return 0;
+}
+
+// one chunk of Bc images; x NCHW fp32 -> out NCHW fp32
+static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int in_chans, int Bc, float* out) {
+  ScratchMark mk(c.sc);
+  const int E = m.E, G = m.G;
+  const int64_t S = static_cast<int64_t>(Bc) * G * G * E;  // elements of the stage-0 token stream
+  __half *skip[3], *Xa, *Xb, *T;
+  SUNET_TRY(c.sc.take_t(&skip[0], S));
+  SUNET_TRY(c.sc.take_t(&skip[1], S / 2));
+  SUNET_TRY(c.sc.take_t(&skip[2], S / 4));
+  SUNET_TRY(c.sc.take_t(&Xa, S));
+  SUNET_TRY(c.sc.take_t(&Xb, S));
+  SUNET_TRY(c.sc.take_t(&T, S));
+  RUN(c, patch_embed_fused(x, in_chans, Bc, m.img, m.img, m.wfold, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
+  // encoder + bottleneck (:714-716).  x_downsample[i] = input of stage i stays untouched in skip[i].
+  const __half* cur = skip[0];
+  for (int i = 0; i < 4; ++i) {
+    for (size_t j = 0; j < m.enc[i].size(); ++j) {
+      SUNET_TRY(m.enc[i][j].forward(c, cur, Xa, Bc));
+      cur = Xa;
+    }
+    if (i < 3) {
+      __half* dst = i < 2 ? skip[i + 1] : Xb;   // the input of stage 3 is not a skip (only x_downsample[0..2] are read, :728)
+      SUNET_TRY(m.merge[i].forward(c, cur, dst, Bc));
+      cur = dst;
+    }
+  }
+  const int64_t M3 = static_cast<int64_t>(Bc) * (G >> 3) * (G >> 3);
+  RUN(c, layernorm_f16(cur, 8 * E, T, 8 * E, m.norm_g, m.norm_b, M3, 8 * E, c.stream));  // :718
+  SUNET_TRY(m.up0.forward(c, T, Xb, 0, Bc));                                             // :726
+  for (int inx = 1; inx < 4; ++inx) {
+    const int i = 3 - inx;
+    const int dim = E << i, H = G >> i;
+    const int64_t M = static_cast<int64_t>(Bc) * H * H;
+    // cat([x, skip], -1) -> Linear(2C -> C) as two accumulating K-segments (:728-729)
+    SUNET_TRY(run_linear(c, m.cat[inx], Xb, dim, M, Xa, dim, ACT_NONE, nullptr, nullptr, 0, 0, skip[i], dim, dim));
+    for (size_t j = 0; j < m.dec[inx].size(); ++j) SUNET_TRY(m.dec[inx][j].forward(c, Xa, Xa, Bc));
+    if (inx < 3) SUNET_TRY(m.ups[inx].forward(c, Xa, Xb, 0, Bc));
+  }
+  const int64_t M0 = static_cast<int64_t>(Bc) * G * G;
+  RUN(c, layernorm_f16(Xa, E, T, E, m.normup_g, m.normup_b, M0, E, c.stream));            // :732
+  SUNET_TRY(m.tail.forward(c, T, out, Bc));                                              // :742-753
+  return 0;
+}
+
+static int model_forward(const ModelPack& m, Ctx& c, const float* x, int in_chans, int batch, int max_chunk, float* out) {
+  if (in_chans != 1 && in_chans != 3) return fail(SUNET_E_SHAPE, "sunet: input has %d channels (1 or 3)", in_chans);
+  if (batch <= 0) return fail(SUNET_E_SHAPE, "sunet: batch %d", batch);
+  if (max_chunk <= 0) max_chunk = 64;
+  const int64_t in_img = static_cast<int64_t>(in_chans) * m.img * m.img, out_img = static_cast<int64_t>(m.out_chans) * m.img * m.img;
+  for (int b0 = 0; b0 < batch; b0 += max_chunk) {
+    const int bc = batch - b0 < max_chunk ? batch - b0 : max_chunk;
+    SUNET_TRY(model_forward_chunk(m, c, x ? x + b0 * in_img : nullptr, in_chans, bc, out ? out + b0 * out_img : nullptr));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ per-module fp32 wrappers
+struct AsyncScratch {  // stream-ordered scratch for the per-module entry points
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit AsyncScratch(cudaStream_t st) : s(st) {}
+  ~AsyncScratch() { if (p) cudaFreeAsync(p, s); }
+  int alloc(size_t bytes) { SUNET_CUDA(cudaMallocAsync(&p, bytes, s)); return 0; }
+};
+
+template <typename F>
+static int with_scratch(cudaStream_t stream, F&& body) {
+  Ctx dry;
+  dry.sc.dry = true;
+  dry.stream = stream;
+  SUNET_TRY(body(dry));
+  AsyncScratch as(stream);
+  SUNET_TRY(as.alloc(dry.sc.peak + 256));
+  Ctx c;
+  c.stream = stream;
+  c.sc.base = static_cast<uint8_t*>(as.p);
+  c.sc.cap = dry.sc.peak + 256;
+  return body(c);
+}
+
+}  // namespace sunet
+
+// ================================================================================================ C ABI
+using namespace sunet;
+
+extern "C" {
+
+int sunet_abi_version(void) { return 1; }
+const char* sunet_last_error(void) { return last_error_buf(); }
+
+int sunet_prepack(const char* kind, const int64_t* ia, int nia, const double* fa, int nfa, const char* const* names,
+                  const void* const* ptrs, const int64_t* numels, int n_params, void* stream, sunet_handle_t* out) {
+  if (!kind || !out) return fail(SUNET_E_ARG, "prepack: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Params P;
+  for (int i = 0; i < n_params; ++i) {
+    if ((reinterpret_cast<uintptr_t>(ptrs[i]) & 3) != 0) return fail(SUNET_E_ALIGN, "parameter '%s' is not 4-byte aligned", names[i]);
+    P.m[names[i]] = {static_cast<const float*>(ptrs[i]), numels[i]};
+  }
+  const std::string k = kind;
+  const double f0 = nfa > 0 ? fa[0] : 0.0;
+  std::unique_ptr<Handle> h;
+  int rc = 0;
+  auto need = [&](int n) { return nia >= n ? 0 : fail(SUNET_E_ARG, "prepack(%s): %d integer arguments expected, got %d", kind, n, nia); };
+  if (k == "swin_block") {
+    SUNET_TRY(need(5));
+    auto* b = new BlockHandle(); h.reset(b);
+    rc = b->p.pack(b->arena, P, "", (int)ia[0], (int)ia[1], (int)ia[2], (int)ia[3], (int)ia[4], f0, s);
+  } else if (k == "window_attention") {
+    SUNET_TRY(need(2));
+    auto* a = new AttnHandle(); h.reset(a);
+    rc = a->p.pack(a->arena, P, "", (int)ia[0], (int)ia[1], f0, s);
+  } else if (k == "mlp") {
+    SUNET_TRY(need(3));
+    auto* m = new MlpHandle(); h.reset(m);
+    rc = m->p.pack(m->arena, P, "", (int)ia[0], (int)ia[1], (int)ia[2], s);
+  } else if (k == "patch_merging") {
+    SUNET_TRY(need(3));
+    auto* m = new MergeHandle(); h.reset(m);
+    rc = m->p.pack(m->arena, P, "", (int)ia[0], (int)ia[1], (int)ia[2], s);
+  } else if (k == "upsample") {
+    SUNET_TRY(need(4));
+    auto* u = new UpHandle(); h.reset(u);
+    rc = u->p.pack(u->arena, P, "", (int)ia[0], (int)ia[1], (int)ia[2], (int)ia[3], s);
+  } else if (k == "patch_embed") {
+    SUNET_TRY(need(4));
+    auto* e = new PatchEmbedHandle(); h.reset(e);
+    PatchEmbedPack& p = e->p;
+    p.cin = (int)ia[0]; p.E = (int)ia[1]; p.P = (int)ia[2]; p.has_norm = (int)ia[3];
+    if ((p.cin * p.P * p.P) % 16 || p.E % 16) rc = fail(SUNET_E_SHAPE, "patch_embed: in_chans*patch^2 and embed_dim must be multiples of 16");
+    if (!rc) rc = pack_linear(e->arena, P, "proj.weight", "proj.bias", p.E, p.cin * p.P * p.P, &p.proj, s);
+    if (!rc && p.has_norm) {
+      rc = copy_vec(e->arena, P, "norm.weight", p.E, &p.g, s);
+      if (!rc) rc = copy_vec(e->arena, P, "norm.bias", p.E, &p.b, s);
+    }
+  } else if (k == "sunet") {
+    auto* m = new ModelHandle(); h.reset(m);
+    rc = pack_model(m, P, ia, nia, f0, s);
+  } else {
+    return fail(SUNET_E_ARG, "prepack: unknown kind '%s'", kind);
+  }
+  if (rc) return rc;
+  h->kind = k;
+  SUNET_CUDA(cudaStreamSynchronize(s));  // the caller may free / mutate its fp32 parameters after this returns
+  *out = reinterpret_cast<sunet_handle_t>(h.release());
+  return 0;
+}
+
+int sunet_destroy(sunet_handle_t h) {
+  delete reinterpret_cast<Handle*>(h);
+  return 0;
+}
+
+#define GET_HANDLE(T, var, h, kindstr)                                                     \
+  Handle* _base = reinterpret_cast<Handle*>(h);                                            \
+  if (!_base || _base->kind != kindstr) return fail(SUNET_E_ARG, "handle is not a %s", kindstr); \
+  T* var = static_cast<T*>(_base);
+
+int sunet_swin_block_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream) {
+  GET_HANDLE(BlockHandle, bh, h, "swin_block");
+  const BlockPack& p = bh->p;
+  const int64_t n = static_cast<int64_t>(batch) * p.H * p.W * p.dim;
+  return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
+    __half *xi, *xo;
+    SUNET_TRY(c.sc.take_t(&xi, n));
+    SUNET_TRY(c.sc.take_t(&xo, n));
+    RUN(c, cast_f32_to_f16(x, xi, n, c.stream));
+    SUNET_TRY(p.forward(c, xi, xo, batch));
+    RUN(c, cast_f16_to_f32(xo, out, n, c.stream));
+    return 0;
+  });
+}
+
+int sunet_window_attention_fwd(sunet_handle_t h, const float* x, int64_t num_windows, const float* mask, int mask_nw, float* out,
+                               void* stream) {
+  GET_HANDLE(AttnHandle, ah, h, "window_attention");
+  const AttnPack& p = ah->p;
+  if (mask && (mask_nw <= 0 || num_windows % mask_nw)) return fail(SUNET_E_SHAPE, "window attention: %lld windows not divisible by mask nW=%d", (long long)num_windows, mask_nw);
+  const int64_t M = num_windows * 64, n = M * p.dim;
+  return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
+    __half *xi, *QKV, *O, *Y;
+    SUNET_TRY(c.sc.take_t(&xi, n));
+    SUNET_TRY(c.sc.take_t(&QKV, 3 * n));
+    SUNET_TRY(c.sc.take_t(&O, n));
+    SUNET_TRY(c.sc.take_t(&Y, n));
+    RUN(c, cast_f32_to_f16(x, xi, n, c.stream));
+    SUNET_TRY(run_linear(c, p.qkv, xi, p.dim, M, QKV, 3 * p.dim));
+    AttnCoreArgs a;
+    a.qkv = QKV; a.ld = 3 * p.dim; a.out = O; a.ldo = p.dim; a.B = 1; a.H = 8; a.W = 8; a.C = p.dim; a.heads = p.heads;
+    a.bias_table = p.table; a.windowed_input = 1; a.num_windows = num_windows;
+    a.mask_mode = mask ? 2 : 0; a.mask = mask; a.mask_nw = mask_nw;
+    RUN(c, attn_core_launch(a, c.stream));
+    SUNET_TRY(run_linear(c, p.proj, O, p.dim, M, Y, p.dim));
+    RUN(c, cast_f16_to_f32(Y, out, n, c.stream));
+    return 0;
+  });
+}
+
+int sunet_mlp_fwd(sunet_handle_t h, const float* x, int64_t rows, float* out, void* stream) {
+  GET_HANDLE(MlpHandle, mh, h, "mlp");
+  const MlpPack& p = mh->p;
+  return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
+    __half *xi, *Hd, *Y;
+    SUNET_TRY(c.sc.take_t(&xi, rows * p.cin));
+    SUNET_TRY(c.sc.take_t(&Hd, rows * p.hid));
+    SUNET_TRY(c.sc.take_t(&Y, rows * p.cout));
+    RUN(c, cast_f32_to_f16(x, xi, rows * p.cin, c.stream));
+    SUNET_TRY(run_linear(c, p.fc1, xi, p.cin, rows, Hd, p.hid, ACT_GELU));
+    SUNET_TRY(run_linear(c, p.fc2, Hd, p.hid, rows, Y, p.cout));
+    RUN(c, cast_f16_to_f32(Y, out, rows * p.cout, c.stream));
+    return 0;
+  });
+}
+
+int sunet_patch_merging_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream) {
+  GET_HANDLE(MergeHandle, mh, h, "patch_merging");
+  const MergePack& p = mh->p;
+  const int64_t n_in = static_cast<int64_t>(batch) * p.H * p.W * p.dim, n_out = n_in / 2;
+  return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
+    __half *xi, *Y;
+    SUNET_TRY(c.sc.take_t(&xi, n_in));
+    SUNET_TRY(c.sc.take_t(&Y, n_out));
+    RUN(c, cast_f32_to_f16(x, xi, n_in, c.stream));
+    SUNET_TRY(p.forward(c, xi, Y, batch));
+    RUN(c, cast_f16_to_f32(Y, out, n_out, c.stream));
+    return 0;
+  });
+}
+
+int sunet_upsample_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream) {
+  GET_HANDLE(UpHandle, uh, h, "upsample");
+  const UpPack& p = uh->p;
+  const int64_t n_in = static_cast<int64_t>(batch) * p.H * p.W * p.C;
+  return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
+    __half* xi;
+    SUNET_TRY(c.sc.take_t(&xi, n_in));
+    RUN(c, cast_f32_to_f16(x, xi, n_in, c.stream));
+    SUNET_TRY(p.forward(c, xi, out, 1, batch));  // raster NHWC == (B, 4L, C/2) for r=2 and (B, 4H, 4W, C) for r=4
+    return 0;
+  });
+}
+
+int sunet_patch_embed_fwd(sunet_handle_t h, const float* x, int batch, int himg, int wimg, float* out, void* stream) {
+  GET_HANDLE(PatchEmbedHandle, eh, h, "patch_embed");
+  const PatchEmbedPack& p = eh->p;
+  if (himg % p.P || wimg % p.P) return fail(SUNET_E_SHAPE, "patch_embed: image %dx%d not divisible by patch %d", himg, wimg, p.P);
+  const int64_t M = static_cast<int64_t>(batch) * (himg / p.P) * (wimg / p.P);
+  const int K = p.cin * p.P * p.P;
+  return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
+    __half *A, *Y, *Yn;
+    SUNET_TRY(c.sc.take_t(&A, M * K));
+    SUNET_TRY(c.sc.take_t(&Y, M * p.E));
+    SUNET_TRY(c.sc.take_t(&Yn, M * p.E));
+    RUN(c, im2col_patch(x, batch, p.cin, himg, wimg, p.P, A, c.stream));
+    SUNET_TRY(run_linear(c, p.proj, A, K, M, Y, p.E));
+    if (p.has_norm) {
+      RUN(c, layernorm_f16(Y, p.E, Yn, p.E, p.g, p.b, M, p.E, c.stream));
+      RUN(c, cast_f16_to_f32(Yn, out, M * p.E, c.stream));
+    } else {
+      RUN(c, cast_f16_to_f32(Y, out, M * p.E, c.stream));
+    }
+    return 0;
+  });
+}
+
+size_t sunet_workspace_bytes(sunet_handle_t h, int batch, int max_chunk) {
+  Handle* base = reinterpret_cast<Handle*>(h);
+  if (!base || base->kind != "sunet") { fail(SUNET_E_ARG, "handle is not a sunet model"); return 0; }
+  const ModelPack& m = static_cast<ModelHandle*>(base)->p;
+  Ctx dry;
+  dry.sc.dry = true;
+  if (model_forward(m, dry, nullptr, 3, batch, max_chunk, nullptr)) return 0;
+  return dry.sc.peak + 256;
+}
+
+int64_t sunet_forward_launches(sunet_handle_t h, int batch, int max_chunk) {
+  Handle* base = reinterpret_cast<Handle*>(h);
+  if (!base || base->kind != "sunet") { fail(SUNET_E_ARG, "handle is not a sunet model"); return -1; }
+  const ModelPack& m = static_cast<ModelHandle*>(base)->p;
+  Ctx dry;
+  dry.sc.dry = true;
+  if (model_forward(m, dry, nullptr, 3, batch, max_chunk, nullptr)) return -1;
+  return dry.launches;
+}
+
+int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  GET_HANDLE(ModelHandle, mh, h, "sunet");
+  if (!x || !out || !workspace) return fail(SUNET_E_ARG, "sunet_forward: null pointer");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SUNET_E_ALIGN, "sunet_forward: workspace must be 256-byte aligned");
+  Ctx c;
+  c.stream = static_cast<cudaStream_t>(stream);
+  c.sc.base = static_cast<uint8_t*>(workspace);
+  c.sc.cap = workspace_bytes;
+  return model_forward(mh->p, c, x, in_chans, batch, max_chunk, out);
+}
+
+int sunet_selftest_umma(void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int N = 96;
+  std::vector<__half> hA(128 * 64), hB(N * 64);
+  for (size_t i = 0; i < hA.size(); ++i) hA[i] = __float2half(((int)(i * 37 % 101) - 50) / 64.f);
+  for (size_t i = 0; i < hB.size(); ++i) hB[i] = __float2half(((int)(i * 53 % 89) - 44) / 64.f);
+  __half *dA, *dB;
+  float* dD;
+  SUNET_CUDA(cudaMalloc(&dA, hA.size() * 2));
+  SUNET_CUDA(cudaMalloc(&dB, hB.size() * 2));
+  SUNET_CUDA(cudaMalloc(&dD, 128 * N * 4));
+  SUNET_CUDA(cudaMemcpyAsync(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice, s));
+  SUNET_CUDA(cudaMemcpyAsync(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice, s));
+  int rc = umma_selftest(dA, dB, dD, N, s);
+  std::vector<float> D(128 * N);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail((int)e, "selftest: %s", cudaGetErrorString(e));
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  if (rc) return rc;
+  for (int i = 0; i < 128; ++i)
+    for (int j = 0; j < N; ++j) {
+      float ref = 0.f;
+      for (int k = 0; k < 64; ++k) ref += __half2float(hA[i * 64 + k]) * __half2float(hB[j * 64 + k]);
+      if (fabsf(ref - D[i * N + j]) > 1e-3f) return fail(SUNET_E_STATE, "umma selftest mismatch at (%d,%d): %f vs %f", i, j, D[i * N + j], ref);
+    }
+  return 0;
+}
+
+int sunet_gemm_f16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int act, void* stream) {
+  GemmArgs a;
+  a.A0 = static_cast<const __half*>(A); a.lda0 = K; a.K0 = K;
+  a.W = static_cast<const __half*>(W); a.ldw = K; a.M = M; a.N = N; a.bias = bias; a.act = act;
+  a.C = C; a.ldc = N;
+  if (act == ACT_PRELU) return fail(SUNET_E_ARG, "sunet_gemm_f16: PReLU not exposed here");
+  return gemm_run(a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

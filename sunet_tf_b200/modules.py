@@ -1,0 +1,510 @@
+"""Host-side mirror of the reference's module surface (model/SUNet_detail.py) over the sm_100a kernels.
+
+Same class names, constructor signatures, attribute tree (hence identical ``state_dict`` keys / shapes / dtypes) and
+forward tensor contracts as the reference, so ``load_state_dict`` of a reference checkpoint and the ``model(x)`` call
+of demo.py / demo_any_resolution.py work unchanged.  The nn.Linear / nn.Conv2d / nn.LayerNorm / nn.PReLU members
+are parameter containers only: every ``forward`` hands the fp32 parameters to ``sunet_prepack`` once (re-packed when
+a parameter changes) and then calls the C ABI (include/sunet_b200.h).  Forward-only: outputs carry no autograd
+graph, Dropout / DropPath are the eval-mode identities (the reference's inference scripts run ``model.eval()`` under
+``torch.no_grad()``, demo.py:65-75).  No CPU path.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def to_2tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def trunc_normal_(t, std=0.02):
+    return nn.init.trunc_normal_(t, std=std)
+
+
+def window_partition(x, window_size):
+    """(B, H, W, C) -> (B*nW, ws, ws, C); SUNet_detail.py:27-39.  Host-side helper for callers of the stand-alone
+    WindowAttention; the fused block never materialises windows (the gather lives in the attention kernel)."""
+    B, H, W, C = x.shape
+    nh, nw = H // window_size, W // window_size
+    return x.reshape(B, nh, window_size, nw, window_size, C).transpose(2, 3).reshape(B * nh * nw, window_size, window_size, C)
+
+
+def window_reverse(windows, window_size, H, W):
+    """(B*nW, ws, ws, C) -> (B, H, W, C); SUNet_detail.py:42-56."""
+    nh, nw = H // window_size, W // window_size
+    B = windows.shape[0] // (nh * nw)
+    return windows.reshape(B, nh, nw, window_size, window_size, -1).transpose(2, 3).reshape(B, H, W, -1)
+
+
+class _Packed(nn.Module):
+    """Owns the pre-packed device handle of a module and keeps it in sync with the fp32 parameters."""
+
+    _kind = None
+
+    def __init__(self):
+        super().__init__()
+        self.__dict__["_sunet_handle"] = None
+        self.__dict__["_sunet_key"] = None
+
+    def _pack_args(self):  # -> (iargs, fargs)
+        raise NotImplementedError
+
+    def _named_tensors(self):
+        sd = {}
+        for k, p in self.named_parameters():
+            sd[k] = p
+        for k, b in self.named_buffers():
+            if b is not None and b.dtype == torch.float32:
+                sd[k] = b
+        return list(sd.items())
+
+    def _handle(self):
+        named = self._named_tensors()
+        if not named or not named[0][1].is_cuda:
+            raise RuntimeError(f"{type(self).__name__}: parameters must live on a CUDA device (call .cuda()); there is no CPU path")
+        key = tuple((t.data_ptr(), t._version) for _, t in named)
+        if self._sunet_handle is None or key != self._sunet_key:
+            self._release()
+            iargs, fargs = self._pack_args()
+            self.__dict__["_sunet_handle"] = _lib.prepack(self._kind, iargs, fargs, named, named[0][1].device)
+            self.__dict__["_sunet_key"] = key
+        return ctypes.c_void_p(self._sunet_handle)
+
+    def _release(self):
+        if self.__dict__.get("_sunet_handle"):
+            _lib.destroy(self._sunet_handle)
+            self.__dict__["_sunet_handle"] = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Mlp(_Packed):
+    """SUNet_detail.py:8-24."""
+    _kind = "mlp"
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU:
+            raise RuntimeError("Mlp: only the exact-erf nn.GELU activation of the reference is implemented")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.Identity()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Identity()
+
+    def _pack_args(self):
+        return [self.fc1.in_features, self.fc1.out_features, self.fc2.out_features], []
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = _lib.require_cuda(x, "x")
+        rows = x.numel() // x.shape[-1]
+        out = torch.empty(*x.shape[:-1], self.fc2.out_features, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_mlp_fwd(self._handle(), _ptr(x), rows, _ptr(out), _lib.stream_ptr(x.device)))
+        return out
+
+
+class WindowAttention(_Packed):
+    """SUNet_detail.py:59-138.  window_size must be (8, 8)."""
+    _kind = "window_attention"
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.dim = dim
+        self.window_size = to_2tuple(window_size)
+        if self.window_size != (8, 8):
+            raise RuntimeError(f"WindowAttention: window_size {self.window_size} unsupported, the kernels are built for 8x8 windows")
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        ws = self.window_size
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws[0] - 1) * (2 * ws[1] - 1), num_heads))
+        t = torch.arange(ws[0] * ws[1])
+        r, c = t // ws[1], t % ws[1]
+        index = (r[:, None] - r[None, :] + ws[0] - 1) * (2 * ws[1] - 1) + (c[:, None] - c[None, :] + ws[1] - 1)
+        self.register_buffer("relative_position_index", index)
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Identity()
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Identity()
+        trunc_normal_(self.relative_position_bias_table, std=.02)
+
+    def _pack_args(self):
+        return [self.dim, self.num_heads], [float(self.scale)]
+
+    @torch.no_grad()
+    def forward(self, x, mask=None):
+        """x: (num_windows*B, 64, C); mask: (num_windows, 64, 64) additive or None."""
+        x = _lib.require_cuda(x, "x")
+        B_, N, C = x.shape
+        if N != 64 or C != self.dim:
+            raise RuntimeError(f"WindowAttention: expected (B_, 64, {self.dim}), got {tuple(x.shape)}")
+        out = torch.empty_like(x)
+        mptr, nw = ctypes.c_void_p(), 0
+        if mask is not None:
+            mask = _lib.require_cuda(mask, "mask")
+            nw = mask.shape[0]
+            mptr = _ptr(mask)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_window_attention_fwd(self._handle(), _ptr(x), B_, mptr, nw, _ptr(out), _lib.stream_ptr(x.device)))
+        return out
+
+    def extra_repr(self):
+        return f"dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}"
+
+
+class SwinTransformerBlock(_Packed):
+    """SUNet_detail.py:157-264: LN -> (shifted) window attention -> +res -> LN -> MLP -> +res, one fused call."""
+    _kind = "swin_block"
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = tuple(input_resolution)
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        if min(self.input_resolution) <= self.window_size:
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        if self.window_size != 8 or self.shift_size not in (0, 4):
+            raise RuntimeError("SwinTransformerBlock: the kernels are built for window 8 and shift 0/4")
+        if mlp_ratio != 4.0:
+            raise RuntimeError("SwinTransformerBlock: mlp_ratio must be 4")
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, window_size=to_2tuple(self.window_size), num_heads=num_heads, qkv_bias=qkv_bias,
+                                    qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        if self.shift_size > 0:
+            H, W = self.input_resolution
+            ws, s = self.window_size, self.shift_size
+            t = torch.arange(ws * ws)
+            rb, cb = (t // ws) >= ws - s, (t % ws) >= ws - s
+            neg = torch.tensor(-100.0)
+            zero = torch.tensor(0.0)
+            row = torch.where(rb[:, None] != rb[None, :], neg, zero)
+            col = torch.where(cb[:, None] != cb[None, :], neg, zero)
+            m = torch.zeros(H // ws, W // ws, ws * ws, ws * ws)
+            m[-1, :] = row
+            m[:, -1] = torch.minimum(m[:, -1], col)
+            attn_mask = m.reshape(-1, ws * ws, ws * ws)
+        else:
+            attn_mask = None
+        self.register_buffer("attn_mask", attn_mask)
+
+    def _pack_args(self):
+        H, W = self.input_resolution
+        return [self.dim, H, W, self.num_heads, self.shift_size], [float(self.attn.scale)]
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = _lib.require_cuda(x, "x")
+        H, W = self.input_resolution
+        B, L, C = x.shape
+        if L != H * W or C != self.dim:
+            raise RuntimeError(f"SwinTransformerBlock: expected (B, {H * W}, {self.dim}), got {tuple(x.shape)}")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_swin_block_fwd(self._handle(), _ptr(x), B, _ptr(out), _lib.stream_ptr(x.device)))
+        return out
+
+    def extra_repr(self):
+        return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
+                f"window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
+
+
+class PatchMerging(_Packed):
+    """SUNet_detail.py:285-322."""
+    _kind = "patch_merging"
+
+    def __init__(self, input_resolution, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution = tuple(input_resolution)
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def _pack_args(self):
+        return [self.dim, self.input_resolution[0], self.input_resolution[1]], []
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = _lib.require_cuda(x, "x")
+        H, W = self.input_resolution
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
+        out = torch.empty(B, L // 4, 2 * C, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_patch_merging_fwd(self._handle(), _ptr(x), B, _ptr(out), _lib.stream_ptr(x.device)))
+        return out
+
+
+class UpSample(_Packed):
+    """The Dual up-sample, SUNet_detail.py:335-386."""
+    _kind = "upsample"
+
+    def __init__(self, input_resolution, in_channels, scale_factor):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.factor = scale_factor
+        self.in_channels = in_channels
+        C = in_channels
+        if self.factor == 2:
+            self.conv = nn.Conv2d(C, C // 2, 1, 1, 0, bias=False)
+            self.up_p = nn.Sequential(nn.Conv2d(C, 2 * C, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(scale_factor),
+                                      nn.Conv2d(C // 2, C // 2, 1, stride=1, padding=0, bias=False))
+            self.up_b = nn.Sequential(nn.Conv2d(C, C, 1, 1, 0), nn.PReLU(),
+                                      nn.Upsample(scale_factor=scale_factor, mode='bilinear', align_corners=False),
+                                      nn.Conv2d(C, C // 2, 1, stride=1, padding=0, bias=False))
+        elif self.factor == 4:
+            self.conv = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
+            self.up_p = nn.Sequential(nn.Conv2d(C, 16 * C, 1, 1, 0, bias=False), nn.PReLU(), nn.PixelShuffle(scale_factor),
+                                      nn.Conv2d(C, C, 1, stride=1, padding=0, bias=False))
+            self.up_b = nn.Sequential(nn.Conv2d(C, C, 1, 1, 0), nn.PReLU(),
+                                      nn.Upsample(scale_factor=scale_factor, mode='bilinear', align_corners=False),
+                                      nn.Conv2d(C, C, 1, stride=1, padding=0, bias=False))
+        else:
+            raise RuntimeError("UpSample: scale_factor must be 2 or 4")
+
+    def _hw(self):
+        if isinstance(self.input_resolution, int):
+            return self.input_resolution, self.input_resolution
+        return tuple(self.input_resolution)
+
+    def _pack_args(self):
+        H, W = self._hw()
+        return [self.in_channels, self.factor, H, W], []
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = _lib.require_cuda(x, "x")
+        H, W = self._hw()
+        B, L, C = x.shape
+        r = self.factor
+        if r == 2:
+            out = torch.empty(B, L * 4, C // 2, device=x.device, dtype=torch.float32)
+        else:
+            out = torch.empty(B, H * 4, W * 4, C, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_upsample_fwd(self._handle(), _ptr(x), B, _ptr(out), _lib.stream_ptr(x.device)))
+        return out
+
+
+class PatchEmbed(_Packed):
+    """SUNet_detail.py:518-556."""
+    _kind = "patch_embed"
+
+    def __init__(self, img_size=224, patch_size=4, in_chans=1, embed_dim=96, norm_layer=None):
+        super().__init__()
+        img_size = to_2tuple(img_size)
+        patch_size = to_2tuple(patch_size)
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.patches_resolution = [img_size[0] // patch_size[0], img_size[1] // patch_size[1]]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans = in_chans
+        self.embed_dim = embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def _pack_args(self):
+        return [self.in_chans, self.embed_dim, self.patch_size[0], 1 if self.norm is not None else 0], []
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = _lib.require_cuda(x, "x")
+        B, C, H, W = x.shape
+        p = self.patch_size[0]
+        out = torch.empty(B, (H // p) * (W // p), self.embed_dim, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_patch_embed_fwd(self._handle(), _ptr(x), B, H, W, _ptr(out), _lib.stream_ptr(x.device)))
+        return out
+
+
+class BasicLayer(nn.Module):
+    """SUNet_detail.py:389-445 (host-side sequencing; used when the layer is called on its own)."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop=0.,
+                 attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads, window_size=window_size,
+                                 shift_size=0 if (i % 2 == 0) else window_size // 2, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                 qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                 drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path, norm_layer=norm_layer)
+            for i in range(depth)])
+        self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = blk(x)
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return x
+
+
+class BasicLayer_up(nn.Module):
+    """SUNet_detail.py:459-515."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop=0.,
+                 attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, upsample=None, use_checkpoint=False):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads, window_size=window_size,
+                                 shift_size=0 if (i % 2 == 0) else window_size // 2, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                 qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                 drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path, norm_layer=norm_layer)
+            for i in range(depth)])
+        self.upsample = UpSample(input_resolution, in_channels=dim, scale_factor=2) if upsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = blk(x)
+        if self.upsample is not None:
+            x = self.upsample(x)
+        return x
+
+
+class SUNet(_Packed):
+    """SUNet_detail.py:566-755.  forward() is ONE C-ABI call (sunet_forward) over a cached workspace."""
+    _kind = "sunet"
+
+    def __init__(self, img_size=224, patch_size=4, in_chans=1, out_chans=1, embed_dim=96, depths=[2, 2, 2, 2],
+                 num_heads=[3, 6, 12, 24], window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True, u1se_checkpoint=False,
+                 final_upsample="Dual up-sample", **kwargs):
+        super().__init__()
+        if len(depths) != 4:
+            raise RuntimeError("SUNet: four encoder stages are required")
+        if ape:
+            raise RuntimeError("SUNet: absolute position embedding (ape=True) is not implemented (training.yaml uses APE: False)")
+        if final_upsample != "Dual up-sample":
+            raise RuntimeError("SUNet: only the 'Dual up-sample' head is implemented")
+        self.out_chans = out_chans
+        self.in_chans = in_chans
+        self.num_layers = len(depths)
+        self.embed_dim = embed_dim
+        self.ape = ape
+        self.patch_norm = patch_norm
+        self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+        self.num_features_up = int(embed_dim * 2)
+        self.mlp_ratio = mlp_ratio
+        self.final_upsample = final_upsample
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.window_size = window_size
+        self.depths = list(depths)
+        self.heads = list(num_heads)
+        self.qk_scale = qk_scale
+        self.max_chunk = 64
+        self.prelu = nn.PReLU()  # registered but never used by the reference forward (:609)
+        self.conv_first = nn.Conv2d(in_chans, embed_dim, 3, 1, 1)
+        self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=embed_dim, embed_dim=embed_dim,
+                                      norm_layer=norm_layer if self.patch_norm else None)
+        patches_resolution = self.patch_embed.patches_resolution
+        self.patches_resolution = patches_resolution
+        self.pos_drop = nn.Identity()
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        for i_layer in range(self.num_layers):
+            self.layers.append(BasicLayer(
+                dim=int(embed_dim * 2 ** i_layer),
+                input_resolution=(patches_resolution[0] // (2 ** i_layer), patches_resolution[1] // (2 ** i_layer)),
+                depth=depths[i_layer], num_heads=num_heads[i_layer], window_size=window_size, mlp_ratio=self.mlp_ratio,
+                qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate,
+                drop_path=dpr[sum(depths[:i_layer]):sum(depths[:i_layer + 1])], norm_layer=norm_layer,
+                downsample=PatchMerging if (i_layer < self.num_layers - 1) else None))
+        self.layers_up = nn.ModuleList()
+        self.concat_back_dim = nn.ModuleList()
+        for i_layer in range(self.num_layers):
+            k = self.num_layers - 1 - i_layer
+            dim_k = int(embed_dim * 2 ** k)
+            self.concat_back_dim.append(nn.Linear(2 * dim_k, dim_k) if i_layer > 0 else nn.Identity())
+            if i_layer == 0:
+                self.layers_up.append(UpSample(input_resolution=patches_resolution[0] // (2 ** k), in_channels=dim_k, scale_factor=2))
+            else:
+                self.layers_up.append(BasicLayer_up(
+                    dim=dim_k, input_resolution=(patches_resolution[0] // (2 ** k), patches_resolution[1] // (2 ** k)),
+                    depth=depths[k], num_heads=num_heads[k], window_size=window_size, mlp_ratio=self.mlp_ratio, qkv_bias=qkv_bias,
+                    qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate,
+                    drop_path=dpr[sum(depths[:k]):sum(depths[:k + 1])], norm_layer=norm_layer,
+                    upsample=UpSample if (i_layer < self.num_layers - 1) else None))
+        self.norm = norm_layer(self.num_features)
+        self.norm_up = norm_layer(self.embed_dim)
+        self.up = UpSample(input_resolution=(img_size // patch_size, img_size // patch_size), in_channels=embed_dim, scale_factor=4)
+        self.output = nn.Conv2d(in_channels=embed_dim, out_channels=self.out_chans, kernel_size=3, stride=1, padding=1, bias=False)
+        self.apply(self._init_weights)
+        self.__dict__["_workspaces"] = {}
+
+    def _init_weights(self, m):  # SUNet_detail.py:688-695
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def _pack_args(self):
+        ia = [self.img_size, self.patch_size, self.in_chans, self.out_chans, self.embed_dim, self.window_size, *self.depths, *self.heads]
+        return ia, [float(self.qk_scale) if self.qk_scale else 0.0]
+
+    def _workspace(self, handle, batch, device):
+        chunk = min(batch, self.max_chunk)
+        key = (str(device), chunk)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = _lib.load().sunet_workspace_bytes(handle, chunk, self.max_chunk)
+            if nbytes == 0:
+                _lib.check(-1)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._workspaces.clear()
+            self._workspaces[key] = ws
+        return ws
+
+    def launches_per_forward(self, batch):
+        return int(_lib.load().sunet_forward_launches(self._handle(), batch, self.max_chunk))
+
+    @torch.no_grad()
+    def forward(self, x, out=None):
+        x = _lib.require_cuda(x, "x")
+        B, C, H, W = x.shape
+        if H != self.img_size or W != self.img_size:
+            raise RuntimeError(f"SUNet: input {H}x{W} does not match img_size {self.img_size} (masks and grids are baked at init, "
+                               "SUNet_detail.py:181,202-225); use sunet_tf_b200.tiles for other resolutions")
+        handle = self._handle()
+        ws = self._workspace(handle, B, x.device)
+        if out is None:
+            out = torch.empty(B, self.out_chans, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_forward(handle, _ptr(x), C, B, self.max_chunk, _ptr(out), _ptr(ws), ws.numel(),
+                                                _lib.stream_ptr(x.device)))
+        return out

@@ -1,0 +1,258 @@
+"""GPU parity tests (pytest -m gpu on a B200): every call goes through the C ABI of libsunet_b200.so.
+
+Reference values are (a) the committed golden outputs of the unmodified reference (tests/golden, made by
+oracle/make_golden.py) and (b) the CPU oracle restatement run live on the same seeded inputs.
+Tolerances: whole model max-abs <= 2e-3 and |dPSNR| <= 0.02 dB (BASELINE.json north_star); stand-alone modules
+max-abs / max|ref| <= 4e-3 (fp16 operands and fp16 activations between kernels, fp32 accumulation).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sunet_oracle as O
+from oracle import weights as Wt
+from tests.util import load_golden, max_abs, module_input, rel_err
+
+pytestmark = pytest.mark.gpu
+
+MODULE_TOL = 4e-3
+MODEL_TOL = 2e-3
+PSNR_TOL = 0.02
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    import sunet_tf_b200  # noqa: F401  (loads / builds the extension; must not fall back to anything)
+    from sunet_tf_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def report(name, got, ref, tol, relative=True):
+    e = rel_err(got, ref) if relative else max_abs(got, ref)
+    print(f"[parity] {name}: {'rel' if relative else 'abs'} err {e:.3e} (tol {tol:.1e}) max|ref| {ref.abs().max().item():.3f}")
+    assert np.isfinite(e) and e <= tol, f"{name}: error {e:.3e} > {tol:.1e}"
+
+
+def load_sd(module, sd, dev):
+    module.load_state_dict(sd, strict=True)
+    return module.to(dev).eval()
+
+
+def test_umma_selftest(dev):
+    from sunet_tf_b200 import _lib
+    _lib.check(_lib.load().sunet_selftest_umma(_lib.stream_ptr(dev)))
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1000, 288, 96, 0), (4096, 384, 96, 1), (333, 768, 3072, 0), (64, 96, 384, 0), (512, 16, 96, 0)])
+def test_gemm_tcgen05_vs_torch(dev, M, N, K, act):
+    from sunet_tf_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g)).half().to(dev)
+    W = (torch.randn(N, K, generator=g) * 0.05).half().to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    C = torch.empty(M, N, dtype=torch.float16, device=dev)
+    _lib.check(_lib.load().sunet_gemm_f16(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(W.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                          ctypes.c_void_p(C.data_ptr()), M, N, K, act, _lib.stream_ptr(dev)))
+    ref = A.float() @ W.float().t() + b
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    report(f"gemm {M}x{N}x{K} act{act}", C, ref, 2e-3)
+
+
+@pytest.mark.parametrize("dim", [96, 192, 384, 768])
+@pytest.mark.parametrize("shift", [0, 4])
+def test_swin_block_vs_reference_golden(dev, dim, shift):
+    from sunet_tf_b200 import SwinTransformerBlock
+    g = load_golden("modules.npz")
+    sd = Wt.synth_state_dict(Wt.block_spec("", dim, 16, 16, shift), seed=dim + shift, style="stress")
+    blk = load_sd(SwinTransformerBlock(dim, (16, 16), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+    x = module_input((1, 256, dim), seed=100 + dim + shift)
+    report(f"block dim{dim} shift{shift}", blk(x.to(dev)), torch.from_numpy(g[f"block_{dim}_{shift}"]), MODULE_TOL)
+
+
+@pytest.mark.parametrize("dim", [96, 192, 384, 768])
+@pytest.mark.parametrize("shift", [0, 4])
+def test_window_attention_vs_reference_golden(dev, dim, shift):
+    from sunet_tf_b200 import WindowAttention
+    g = load_golden("modules.npz")
+    sd_blk = Wt.synth_state_dict(Wt.block_spec("", dim, 16, 16, shift), seed=dim + shift, style="stress")
+    sd = {k[len("attn."):]: v for k, v in sd_blk.items() if k.startswith("attn.")}
+    att = load_sd(WindowAttention(dim, (8, 8), 8, qk_scale=8), sd, dev)
+    xw = module_input((4, 64, dim), seed=200 + dim + shift)
+    mask = sd_blk["attn_mask"].to(dev) if shift else None
+    # With QK_SCALE 8 the logits of a randn input have std ~ 1 / 3 / 8 / 24 for dim 96 / 192 / 384 / 768; the 2^-11 rounding of the
+    # fp16 q/k operands is amplified by exp(), so the stand-alone tolerance scales with dim (the block / whole-model bars do not).
+    tol = MODULE_TOL * max(1.0, dim / 256.0)
+    report(f"wattn dim{dim} shift{shift}", att(xw.to(dev), mask=mask), torch.from_numpy(g[f"wattn_{dim}_{shift}"]), tol)
+
+
+@pytest.mark.parametrize("dim", [96, 768])
+def test_mlp_vs_reference_golden(dev, dim):
+    from sunet_tf_b200 import Mlp
+    g = load_golden("modules.npz")
+    sd_blk = Wt.synth_state_dict(Wt.block_spec("", dim, 16, 16, 0), seed=dim, style="stress")
+    sd = {k[len("mlp."):]: v for k, v in sd_blk.items() if k.startswith("mlp.")}
+    mlp = load_sd(Mlp(dim, 4 * dim), sd, dev)
+    xw = module_input((4, 64, dim), seed=200 + dim)[:2]
+    report(f"mlp dim{dim}", mlp(xw.to(dev)), torch.from_numpy(g[f"mlp_{dim}"]), MODULE_TOL)
+
+
+def test_patch_merging_vs_reference_golden(dev):
+    from sunet_tf_b200 import PatchMerging
+    g = load_golden("modules.npz")
+    pm = load_sd(PatchMerging((16, 16), 96), Wt.synth_state_dict(Wt.merging_spec("", 96), seed=7, style="stress"), dev)
+    report("patch_merging", pm(module_input((2, 256, 96), seed=300).to(dev)), torch.from_numpy(g["merging_96"]), MODULE_TOL)
+
+
+@pytest.mark.parametrize("C,r,H", [(192, 2, 8), (768, 2, 8), (96, 4, 16)])
+def test_upsample_vs_reference_golden(dev, C, r, H):
+    from sunet_tf_b200 import UpSample
+    g = load_golden("modules.npz")
+    up = load_sd(UpSample((H, H), C, r), Wt.synth_state_dict(Wt.upsample_spec("", C, r), seed=11 + C + r, style="stress"), dev)
+    y = up(module_input((2, H * H, C), seed=400 + C + r).to(dev))
+    ref = torch.from_numpy(g[f"upsample_{C}_{r}"])
+    assert tuple(y.shape) == tuple(ref.shape)
+    report(f"upsample C{C} r{r}", y, ref, MODULE_TOL)
+
+
+def test_patch_embed_vs_reference_golden(dev):
+    from sunet_tf_b200 import PatchEmbed
+    g = load_golden("modules.npz")
+    pe = load_sd(PatchEmbed(64, 4, 96, 96, torch.nn.LayerNorm), Wt.synth_state_dict(Wt.patch_embed_spec("", 96, 96), seed=13, style="stress"), dev)
+    report("patch_embed", pe(module_input((2, 96, 64, 64), seed=500).to(dev)), torch.from_numpy(g["patch_embed_96"]), MODULE_TOL)
+
+
+@pytest.mark.parametrize("dim,grid,batch", [(96, 32, 2), (192, 24, 3), (384, 16, 1)])
+def test_swin_block_vs_live_oracle_larger_grids(dev, dim, grid, batch):
+    """multi-row / multi-column window grids, non-square window counts, batch > 1 (mask row/col logic, gather map)"""
+    from sunet_tf_b200 import SwinTransformerBlock
+    for shift in (0, 4):
+        sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, shift), seed=31 + dim + shift, style="stress")
+        blk = load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+        x = module_input((batch, grid * grid, dim), seed=77 + dim + shift)
+        ref = O.swin_block(sd, "", x, grid, grid, 8, shift, 8)
+        report(f"block-live dim{dim} grid{grid} shift{shift}", blk(x.to(dev)), ref, MODULE_TOL)
+
+
+def test_swin_block_default_scale_and_rect_grid(dev):
+    """qk_scale=None -> head_dim**-0.5 (SUNet_detail.py:80); rectangular token grid"""
+    from sunet_tf_b200 import SwinTransformerBlock
+    dim, H, W = 96, 16, 32
+    sd = Wt.synth_state_dict(Wt.block_spec("", dim, H, W, 4), seed=5, style="stress")
+    blk = load_sd(SwinTransformerBlock(dim, (H, W), 8, window_size=8, shift_size=4, qk_scale=None), sd, dev)
+    x = module_input((2, H * W, dim), seed=6)
+    ref = O.swin_block(sd, "", x, H, W, 8, 4, (dim // 8) ** -0.5)
+    report("block-live rect default-scale", blk(x.to(dev)), ref, MODULE_TOL)
+
+
+@pytest.fixture(scope="module")
+def model_init(dev):
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    m = SUNet_model(DEFAULT_OPT)
+    m.load_state_dict(Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="init"), strict=True)
+    return m.to(dev).eval()
+
+
+def psnr_delta(out, ref, clean):
+    tgt = Wt.luminance(clean)
+    return abs(O.torch_psnr(out.cpu(), tgt).item() - O.torch_psnr(ref, tgt).item())
+
+
+def test_whole_model_vs_reference_golden_init(dev, model_init):
+    g = load_golden("sunet_model_init.npz")
+    noisy, clean = Wt.awgn_input(2, seed=1)
+    out = model_init(noisy.to(dev))
+    ref = torch.from_numpy(g["output"])
+    assert tuple(out.shape) == (2, 1, 256, 256)
+    report("sunet_model init", out, ref, MODEL_TOL, relative=False)
+    d = psnr_delta(out, ref, clean)
+    print(f"[parity] sunet_model init: |dPSNR| {d:.4f} dB")
+    assert d <= PSNR_TOL
+
+
+def test_whole_model_vs_reference_golden_stress(dev):
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    g = load_golden("sunet_model_stress.npz")
+    m = SUNet_model(DEFAULT_OPT)
+    m.load_state_dict(Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="stress"), strict=True)
+    m = m.to(dev).eval()
+    noisy, clean = Wt.awgn_input(2, seed=1)
+    out = m(noisy.to(dev))
+    ref = torch.from_numpy(g["output"])
+    report("sunet_model stress", out, ref, MODEL_TOL, relative=False)
+    assert psnr_delta(out, ref, clean) <= PSNR_TOL
+
+
+def test_grey_input_and_batch_invariance(dev, model_init):
+    g = load_golden("sunet_model_grey.npz")
+    noisy, _ = Wt.awgn_input(2, seed=1)
+    out = model_init(noisy[:1, :1].contiguous().to(dev))
+    report("sunet_model grey", out, torch.from_numpy(g["output"]), MODEL_TOL, relative=False)
+    # images never interact: a batch of 5 in chunks of 2 equals the images run one by one, bit for bit
+    x = torch.cat([noisy, noisy.flip(0), noisy[:1]], 0).to(dev)
+    model_init.swin_unet.max_chunk = 2
+    y_chunked = model_init(x).clone()
+    model_init.swin_unet.max_chunk = 64
+    y_full = model_init(x)
+    assert torch.equal(y_chunked, y_full)
+    y_single = torch.cat([model_init(x[i:i + 1]) for i in range(5)], 0)
+    assert torch.equal(y_single, y_full)
+    assert torch.equal(y_full[0], y_full[3]) and torch.equal(y_full[1], y_full[2])
+
+
+def test_full_batch64_properties(dev, model_init):
+    """BASELINE config 2 size (B=64): replicas of the 2 golden inputs must reproduce the golden in every slot."""
+    g = load_golden("sunet_model_init.npz")
+    noisy, _ = Wt.awgn_input(2, seed=1)
+    x = noisy.repeat(32, 1, 1, 1).to(dev)
+    out = model_init(x)
+    assert torch.isfinite(out).all()
+    ref = torch.from_numpy(g["output"])
+    report("sunet_model B=64 slot 0-1", out[:2], ref, MODEL_TOL, relative=False)
+    assert torch.equal(out[:2], out[62:64]) and torch.equal(out[:2], out[30:32])
+
+
+def test_any_resolution_tiles_vs_reference_golden(dev):
+    from sunet_tf_b200 import SUNet, tiles
+    g = load_golden("tiles_300x420.npz")
+    h, w = int(g["h"]), int(g["w"])
+    net = SUNet(img_size=256, patch_size=4, in_chans=3, out_chans=3, embed_dim=96, depths=[8] * 4, num_heads=[8] * 4, window_size=8,
+                mlp_ratio=4.0, qkv_bias=True, qk_scale=8)
+    net.load_state_dict(Wt.synth_state_dict(Wt.sunet_spec(pre="", out_chans=3), seed=int(g["seed_weights"]), style="init"), strict=True)
+    net = net.to(dev).eval()
+    gen = torch.Generator().manual_seed(int(g["seed_input"]))
+    clean = torch.rand(1, 3, h, w, generator=gen)
+    noisy = torch.round(torch.clamp(clean + torch.randn(1, 3, h, w, generator=gen) * (50 / 255.0), 0, 1) * 255) / 255
+    # tile extraction equals the oracle's restatement of overlapped_square bit for bit
+    ot, _, X = O.overlapped_square(noisy)
+    dt = tiles.extract_tiles(noisy.to(dev), 0, ot.shape[0])
+    assert torch.equal(dt.cpu(), ot)
+    # identity "model": fold(extract(x)) == clamp(x)
+    back = tiles.finish(tiles.fold_tiles(dt, 0, h, w), h, w)
+    assert (back.cpu() - noisy).abs().max().item() < 1e-6
+    out = tiles.denoise_any_resolution(net, noisy.to(dev), tile_batch=4)
+    report("any-resolution 300x420 (9 tiles)", out, torch.from_numpy(g["restored"]), MODEL_TOL, relative=False)
+    # two emulated ranks: each folds its own tile range, canvases add up
+    from sunet_tf_b200.shard import tile_range
+    acc = None
+    for r in range(2):
+        lo, hi = tile_range(ot.shape[0], r, 2)
+        acc = tiles.fold_tiles(net(dt[lo:hi]), lo, h, w, acc)
+    assert torch.allclose(tiles.finish(acc, h, w), out, atol=1e-6)
+
+
+def test_error_paths(dev, model_init):
+    from sunet_tf_b200 import Mlp
+    with pytest.raises(RuntimeError):
+        model_init(torch.zeros(1, 3, 128, 128, device=dev))          # wrong resolution
+    with pytest.raises(RuntimeError):
+        model_init(torch.zeros(1, 2, 256, 256, device=dev))          # 2 channels
+    with pytest.raises(RuntimeError):
+        Mlp(96, 100).to(dev)(torch.zeros(4, 96, device=dev))         # hidden not a multiple of 16
