@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - SUNet 256x256 denoising forward throughput on N B200 (BASELINE.json metric, config 2 / 3).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = one forward of a batch of 64 synthetic AWGN(sigma=50) 256x256 RGB images per GPU (weak scaling: at N=8 the
+global batch is the 512 of config 3).  Weights are random-init at the training.yaml architecture.  The data path has no
+collective (batch shards are independent); torch.distributed is used only for the barrier and the max-over-ranks time.
+
+JSON line (rank 0): value = images/s with inputs resident in HBM, device-timed (CUDA events on the launching stream);
+e2e = same through the public API (SUNet_model.__call__) with pinned-host inputs and outputs copied inside the timed
+region; roofline = dominant kernel, timed live with per-launch CUDA events; cpu_baseline = the CPU oracle port of the
+reference forward timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 64
+N_INPUT_BUFFERS = 4          # 4 x 50 MB of distinct inputs > 126 MB L2; the forward itself streams a ~2 GB workspace
+REF_FLOPS_PER_IMAGE = 64.148e9   # reference formulation, 2*MAC over every Linear/Conv/bmm
+METRIC = "sunet_256x256_denoise_images_per_s"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"], "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(torch, device, seed, n_buffers, batch):
+    """BASELINE config 2 input recipe on the device: clean ~ U[0,1], + N(0, 50/255), clamp, 8-bit quantise (demo.py:70-72)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    bufs = []
+    for _ in range(n_buffers):
+        clean = torch.rand(batch, 3, 256, 256, generator=g, device=device)
+        noisy = clean + torch.randn(batch, 3, 256, 256, generator=g, device=device) * (50.0 / 255.0)
+        bufs.append(torch.round(torch.clamp(noisy, 0, 1) * 255.0) / 255.0)
+    return bufs
+
+
+def cpu_port_images_per_s(torch, state_dict, images, passes, warmup=1):
+    """Times the CPU oracle port (oracle/sunet_oracle.py) of the reference forward with all host threads."""
+    from oracle import sunet_oracle as O
+    from oracle import weights as Wt
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, _ = Wt.awgn_input(images, seed=1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + passes):
+            t0 = time.perf_counter()
+            O.sunet_model_forward(state_dict, x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return images / statistics.median(times), cores, times
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (the oracle port; the PyTorch reference tree
+    does not travel to the GPU box) on the host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import weights as Wt
+    sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="init")
+    images = 2
+    from oracle import sunet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, _ = Wt.awgn_input(images, seed=1)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.sunet_model_forward(sd, x)
+        steps = max(1, min(args.steps, 40))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.sunet_model_forward(sd, x)
+        dt = time.perf_counter() - t0
+    value = images * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SUNet fwd 256x256 RGB, training.yaml arch (emb 96, depths [8,8,8,8], heads 8, win 8), random init, AWGN sigma=50",
+                   "step": f"{images} images through the CPU oracle port of the reference forward (torch {torch.__version__} CPU fp32)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {images} images, {cores} threads"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown to this file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from sunet_tf_b200 import SUNet_model, shard
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU path to benchmark; use --impl reference for the CPU baseline)")
+    rank, world, local = shard.world()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        shard.init_process_group("nccl")
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    B = args.batch
+
+    torch.manual_seed(0)  # same random-init weights on every rank (replicated model, 199 MB fp16 after pre-pack)
+    model = SUNet_model(DEFAULT_OPT).to(device).eval()
+    inputs = make_inputs(torch, device, seed=2 + rank, n_buffers=N_INPUT_BUFFERS, batch=B)
+    out = torch.empty(B, 1, 256, 256, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        model(inputs[i % N_INPUT_BUFFERS], out=out)
+    sampler = ClockSampler(local)
+    # ---------------- value: device-resident inputs
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        model(inputs[i % N_INPUT_BUFFERS], out=out)
+    e1.record()
+    barrier()
+    ms_total = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---------------- e2e: public API, pinned host buffers, H2D + D2H inside the timed region (double-buffered copy streams)
+    host_in = [t.cpu().pin_memory() for t in inputs]
+    host_out = [torch.empty(B, 1, 256, 256).pin_memory() for _ in range(2)]
+    dev_in = [torch.empty_like(inputs[0]) for _ in range(2)]
+    dev_out = [torch.empty_like(out) for _ in range(2)]
+    copy_in, copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    main_stream = torch.cuda.current_stream(device)
+
+    def e2e_loop(steps):
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        comp_done = [torch.cuda.Event() for _ in range(2)]
+        out_done = [torch.cuda.Event() for _ in range(2)]
+        with torch.cuda.stream(copy_in):
+            dev_in[0].copy_(host_in[0], non_blocking=True)
+            in_ready[0].record(copy_in)
+        for i in range(steps):
+            s = i & 1
+            if i + 1 < steps:  # prefetch the next batch while this one computes
+                with torch.cuda.stream(copy_in):
+                    if i >= 1:
+                        copy_in.wait_event(comp_done[1 - s])   # the previous user of dev_in[1 - s] has finished
+                    dev_in[1 - s].copy_(host_in[(i + 1) % N_INPUT_BUFFERS], non_blocking=True)
+                    in_ready[1 - s].record(copy_in)
+            main_stream.wait_event(in_ready[s])
+            if i >= 2:
+                main_stream.wait_event(out_done[s])   # dev_out[s] has been drained
+            model(dev_in[s], out=dev_out[s])
+            comp_done[s].record(main_stream)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(comp_done[s])
+                host_out[s].copy_(dev_out[s], non_blocking=True)
+                out_done[s].record(copy_out)
+        main_stream.wait_stream(copy_out)
+
+    e2e_loop(min(W, 4))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_loop(K)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = shard.max_over_ranks(max(e0.elapsed_time(e1), 0.0), device)
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    clocks = sampler.stop()
+    h2d = inputs[0].numel() * 4
+    d2h = out.numel() * 4
+
+    # ---------------- per-kernel breakdown (rank 0, live, CUDA events around each launch)
+    peaks = read_peaks()
+    roofline, kernels = None, {}
+    if rank == 0:
+        model.swin_unet.profile_forward(inputs[0])
+        _, recs = model.swin_unet.profile_forward(inputs[1])
+        for kind, ms, flops, nbytes in recs:
+            k = kernels.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            k["launches"] += 1
+            k["ms"] += ms
+            k["flops"] += flops
+            k["bytes"] += nbytes
+        total_ms = sum(k["ms"] for k in kernels.values())
+        for k in kernels.values():
+            k["share"] = k["ms"] / total_ms
+            k["tflops"] = k["flops"] / (k["ms"] * 1e-3) * 1e-12 if k["ms"] > 0 else 0.0
+            k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) * 1e-9 if k["ms"] > 0 else 0.0
+        top = max(kernels, key=lambda n: kernels[n]["ms"])
+        kt = kernels[top]
+        if top in ("gemm_tcgen05", "attn_core"):
+            roofline = {"kernel": top, "bound": "tensor", "achieved": kt["tflops"], "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": kt["tflops"] / peaks["tflops_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)", "launches": kt["launches"],
+                        "avg_launch_us": kt["ms"] / kt["launches"] * 1e3, "share_of_step": kt["share"],
+                        "hbm_frac": kt["gbs"] / peaks["hbm_gbs"]}
+        else:
+            roofline = {"kernel": top, "bound": "hbm", "achieved": kt["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": kt["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"], "launches": kt["launches"],
+                        "avg_launch_us": kt["ms"] / kt["launches"] * 1e3, "share_of_step": kt["share"]}
+        if args.profile_json:
+            with open(args.profile_json, "w") as fh:
+                json.dump({"batch": B, "kernels": kernels, "launch_list": recs}, fh, indent=1)
+
+    # ---------------- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        v, cores, times = cpu_port_images_per_s(torch, sd, images=2, passes=5, warmup=1)
+        cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"5 timed passes x 2 images (median), same arch/input recipe, torch {torch.__version__} CPU fp32, {cores} threads"}
+
+    if rank == 0:
+        launches = model.swin_unet.launches_per_forward(B)
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: SUNet fwd 256x256 RGB batch 64 per GPU, training.yaml arch (emb 96, depths [8,8,8,8], "
+                                   "heads 8, win 8, qk_scale 8), random init, AWGN sigma=50 8-bit quantised input",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}, no collective",
+                       "l2": f"inputs rotate over {N_INPUT_BUFFERS} distinct batches ({N_INPUT_BUFFERS * h2d / 1e6:.0f} MB) and each forward "
+                             "streams a ~2 GB workspace, both > 126 MB L2",
+                       "precision": "fp16 operands/activations, fp32 accumulate/LN/softmax; parity max-abs 3.1e-4 vs reference (bar 2e-3)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K, "wall_ms_per_step": wall_ms / K,
+                    "how": "SUNet_model.__call__ -> sunet_forward (C ABI); pinned host in/out, copies on side streams double-buffered against compute"},
+            "gpu_launches": launches * K,
+            "launches_per_step": launches,
+            "roofline": roofline,
+            "kernels": {n: {"launches": k["launches"], "ms": round(k["ms"], 4), "share": round(k["share"], 4), "tflops": round(k["tflops"], 2),
+                            "gbs": round(k["gbs"], 1)} for n, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+            "model_flops_util": {"ref_gflop_per_image": REF_FLOPS_PER_IMAGE / 1e9,
+                                 "achieved_tflops_per_gpu": value / world * REF_FLOPS_PER_IMAGE / 1e12,
+                                 "frac_of_sustained_peak": value / world * REF_FLOPS_PER_IMAGE / 1e12 / peaks["tflops_sustained"]},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

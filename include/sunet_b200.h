@@ -72,6 +72,12 @@ int sunet_patch_embed_fwd(sunet_handle_t h, const float* x, int batch, int himg,
 size_t sunet_workspace_bytes(sunet_handle_t h, int batch, int max_chunk);
 int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
                   size_t workspace_bytes, void* stream);
+/* Same forward with every kernel launch bracketed by CUDA events on `stream` (synchronises before returning).
+ * recs[i] = {kind, device ms, algorithmic FLOPs, algorithmic bytes} in launch order; kind: 0 tcgen05 GEMM, 1 attention core,
+ * 2 LayerNorm, 3 merge-gather+LN, 4 patch-embed conv, 5 up-sample combine, 6 tail stencil, 7 cast, 8 im2col. */
+typedef struct sunet_prof_rec { int kind; float ms; double flops; double bytes; } sunet_prof_rec;
+int sunet_forward_profile(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream, sunet_prof_rec* recs, int max_recs, int* n_recs);
 /* number of kernels one sunet_forward of `batch` images launches (for bench.py's gpu_launches) */
 int64_t sunet_forward_launches(sunet_handle_t h, int batch, int max_chunk);
 

@@ -15,6 +15,13 @@ _lib = None
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 c_f64_p = ctypes.POINTER(ctypes.c_double)
 
+class ProfRec(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("ms", ctypes.c_float), ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
+KERNEL_KINDS = ("gemm_tcgen05", "attn_core", "layernorm", "merge_gather_ln", "patch_embed_conv", "upsample_combine", "tail_stencil",
+                "cast", "im2col")
+
 _SIGNATURES = {
     "sunet_abi_version": (ctypes.c_int, []),
     "sunet_last_error": (ctypes.c_char_p, []),
@@ -33,6 +40,9 @@ _SIGNATURES = {
     "sunet_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "sunet_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "sunet_forward_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.POINTER(ProfRec), ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_int)]),
     "sunet_forward_launches": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "sunet_tiles_extract": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),

@@ -65,17 +65,45 @@ struct ScratchMark {  // stack discipline
   ~ScratchMark() { s.off = saved; }
 };
 
+enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8 };
+
+struct ProfRec {
+  int kind;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+
 struct Ctx {
   Scratch sc;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  std::vector<ProfRec>* prof = nullptr;  // when set, every launch is bracketed by CUDA events on `stream`
   bool dry() const { return sc.dry; }
 };
 
-#define RUN(ctx, expr)            \
-  do {                            \
-    (ctx).launches++;             \
-    if (!(ctx).dry()) SUNET_TRY(expr); \
+static int prof_begin(Ctx& c, int kind, double flops, double bytes) {
+  ProfRec r{kind, flops, bytes, nullptr, nullptr};
+  SUNET_CUDA(cudaEventCreate(&r.e0));
+  SUNET_CUDA(cudaEventCreate(&r.e1));
+  SUNET_CUDA(cudaEventRecord(r.e0, c.stream));
+  c.prof->push_back(r);
+  return 0;
+}
+static int prof_end(Ctx& c) {
+  SUNET_CUDA(cudaEventRecord(c.prof->back().e1, c.stream));
+  return 0;
+}
+
+// one kernel launch: counted always, executed unless this is a dry (sizing) pass, event-bracketed when profiling.
+// flops / bytes are the ALGORITHMIC figures of the launch (2*M*N*K; each operand read once, result written once).
+#define RUN(ctx, kind, flops, bytes, expr)                         \
+  do {                                                             \
+    (ctx).launches++;                                              \
+    if (!(ctx).dry()) {                                            \
+      if ((ctx).prof) SUNET_TRY(prof_begin((ctx), (kind), (flops), (bytes))); \
+      SUNET_TRY(expr);                                             \
+      if ((ctx).prof) SUNET_TRY(prof_end((ctx)));                  \
+    }                                                              \
   } while (0)
 
 struct Linear {
@@ -115,7 +143,9 @@ static int run_linear(Ctx& c, const Linear& L, const __half* A, int64_t lda, int
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1;
   a.W = L.w; a.ldw = L.K; a.M = M; a.N = L.N;
   a.bias = L.b; a.act = act; a.prelu = prelu; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.out_f32 = out_f32;
-  RUN(c, gemm_run(a, c.stream));
+  const double K = L.K;
+  const double bytes = 2.0 * M * K + 2.0 * L.N * K + (out_f32 ? 4.0 : 2.0) * M * L.N + (R ? 2.0 * M * L.N : 0.0);
+  RUN(c, K_GEMM, 2.0 * M * L.N * K, bytes, gemm_run(a, c.stream));
   return 0;
 }
 
@@ -182,14 +212,14 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     SUNET_TRY(c.sc.take_t(&QKV, M * 3 * dim));
     SUNET_TRY(c.sc.take_t(&O, M * dim));
     SUNET_TRY(c.sc.take_t(&Hd, M * 4 * dim));
-    RUN(c, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                       // :233
+    RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                       // :233
     SUNET_TRY(run_linear(c, attn.qkv, T, dim, M, QKV, 3 * dim));                               // :114
     AttnCoreArgs a;
     a.qkv = QKV; a.ld = 3 * dim; a.out = O; a.ldo = dim; a.B = B; a.H = H; a.W = W; a.C = dim; a.heads = heads;
     a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
-    RUN(c, attn_core_launch(a, c.stream));                                                    // :118-135, :236-257
+    RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_launch(a, c.stream));               // :118-135, :236-257
     SUNET_TRY(run_linear(c, attn.proj, O, dim, M, x_out, dim, ACT_NONE, nullptr, x_in, dim));   // :136, :261
-    RUN(c, layernorm_f16(x_out, dim, T, dim, g2, b2, M, dim, c.stream));                      // :262
+    RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_out, dim, T, dim, g2, b2, M, dim, c.stream));                      // :262
     SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
     SUNET_TRY(run_linear(c, mlp.fc2, Hd, 4 * dim, M, x_out, dim, ACT_NONE, nullptr, x_out, dim));  // :22, :262
     return 0;
@@ -212,7 +242,7 @@ struct MergePack {  // PatchMerging (SUNet_detail.py:294-322)
     const int64_t M4 = static_cast<int64_t>(B) * (H / 2) * (W / 2);
     __half* T;
     SUNET_TRY(c.sc.take_t(&T, M4 * 4 * dim));
-    RUN(c, merge_gather_ln_f16(x, T, g, b, B, H, W, dim, c.stream));
+    RUN(c, K_MERGE_LN, 0.0, 16.0 * M4 * dim, merge_gather_ln_f16(x, T, g, b, B, H, W, dim, c.stream));
     SUNET_TRY(run_linear(c, red, T, 4 * dim, M4, y, 2 * dim));
     return 0;
   }
@@ -269,7 +299,7 @@ struct UpPack {
     SUNET_TRY(run_linear(c, pp, Pb, Cq, M * rr, Yp, Co));                             // up_p[3] + conv (p half)
     SUNET_TRY(run_linear(c, b0, x, C, M, Bb, C, ACT_PRELU, slope_b));                 // up_b[0..1]
     SUNET_TRY(run_linear(c, zz, Bb, C, M, Z, Co));                                    // up_b[3] + conv (b half), at low res
-    RUN(c, upsample_combine(Yp, Z, out, out_f32, B, H, W, Co, r, c.stream));          // pixel shuffle + bilinear + add
+    RUN(c, K_UP_COMBINE, 0.0, (2.0 * rr + 2.0 + (out_f32 ? 4.0 : 2.0) * rr) * M * Co, upsample_combine(Yp, Z, out, out_f32, B, H, W, Co, r, c.stream));          // pixel shuffle + bilinear + add
     return 0;
   }
 };
@@ -307,7 +337,7 @@ struct TailPack {
     SUNET_TRY(run_linear(c, gp, Pb, E, M * 16, Qp, NT, ACT_NONE, nullptr, nullptr, 0, 1));
     SUNET_TRY(run_linear(c, up.b0, x, E, M, Bb, E, ACT_PRELU, up.slope_b));
     SUNET_TRY(run_linear(c, gb, Bb, E, M, Rb, NT, ACT_NONE, nullptr, nullptr, 0, 1));
-    RUN(c, tail_stencil(Qp, Rb, out, B, H, W, OC, NT, c.stream));
+    RUN(c, K_TAIL, 0.0, 4.0 * M * NT * 17 + 4.0 * M * 16 * OC, tail_stencil(Qp, Rb, out, B, H, W, OC, NT, c.stream));
     return 0;
   }
 };
@@ -409,7 +439,7 @@ static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int i
   SUNET_TRY(c.sc.take_t(&Xa, S));
   SUNET_TRY(c.sc.take_t(&Xb, S));
   SUNET_TRY(c.sc.take_t(&T, S));
-  RUN(c, patch_embed_fused(x, in_chans, Bc, m.img, m.img, m.wfold, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
+  RUN(c, K_PATCH_EMBED, 2.0 * 108 * S, 4.0 * Bc * in_chans * m.img * m.img + 2.0 * S, patch_embed_fused(x, in_chans, Bc, m.img, m.img, m.wfold, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
   // encoder + bottleneck (:714-716).  x_downsample[i] = input of stage i stays untouched in skip[i].
   const __half* cur = skip[0];
   for (int i = 0; i < 4; ++i) {
@@ -424,7 +454,7 @@ static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int i
     }
   }
   const int64_t M3 = static_cast<int64_t>(Bc) * (G >> 3) * (G >> 3);
-  RUN(c, layernorm_f16(cur, 8 * E, T, 8 * E, m.norm_g, m.norm_b, M3, 8 * E, c.stream));  // :718
+  RUN(c, K_LAYERNORM, 0.0, 32.0 * M3 * E, layernorm_f16(cur, 8 * E, T, 8 * E, m.norm_g, m.norm_b, M3, 8 * E, c.stream));  // :718
   SUNET_TRY(m.up0.forward(c, T, Xb, 0, Bc));                                             // :726
   for (int inx = 1; inx < 4; ++inx) {
     const int i = 3 - inx;
@@ -436,7 +466,7 @@ static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int i
     if (inx < 3) SUNET_TRY(m.ups[inx].forward(c, Xa, Xb, 0, Bc));
   }
   const int64_t M0 = static_cast<int64_t>(Bc) * G * G;
-  RUN(c, layernorm_f16(Xa, E, T, E, m.normup_g, m.normup_b, M0, E, c.stream));            // :732
+  RUN(c, K_LAYERNORM, 0.0, 4.0 * M0 * E, layernorm_f16(Xa, E, T, E, m.normup_g, m.normup_b, M0, E, c.stream));            // :732
   SUNET_TRY(m.tail.forward(c, T, out, Bc));                                              // :742-753
   return 0;
 }
@@ -563,9 +593,9 @@ int sunet_swin_block_fwd(sunet_handle_t h, const float* x, int batch, float* out
     __half *xi, *xo;
     SUNET_TRY(c.sc.take_t(&xi, n));
     SUNET_TRY(c.sc.take_t(&xo, n));
-    RUN(c, cast_f32_to_f16(x, xi, n, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n), cast_f32_to_f16(x, xi, n, c.stream));
     SUNET_TRY(p.forward(c, xi, xo, batch));
-    RUN(c, cast_f16_to_f32(xo, out, n, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n), cast_f16_to_f32(xo, out, n, c.stream));
     return 0;
   });
 }
@@ -582,15 +612,15 @@ int sunet_window_attention_fwd(sunet_handle_t h, const float* x, int64_t num_win
     SUNET_TRY(c.sc.take_t(&QKV, 3 * n));
     SUNET_TRY(c.sc.take_t(&O, n));
     SUNET_TRY(c.sc.take_t(&Y, n));
-    RUN(c, cast_f32_to_f16(x, xi, n, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n), cast_f32_to_f16(x, xi, n, c.stream));
     SUNET_TRY(run_linear(c, p.qkv, xi, p.dim, M, QKV, 3 * p.dim));
     AttnCoreArgs a;
     a.qkv = QKV; a.ld = 3 * p.dim; a.out = O; a.ldo = p.dim; a.B = 1; a.H = 8; a.W = 8; a.C = p.dim; a.heads = p.heads;
     a.bias_table = p.table; a.windowed_input = 1; a.num_windows = num_windows;
     a.mask_mode = mask ? 2 : 0; a.mask = mask; a.mask_nw = mask_nw;
-    RUN(c, attn_core_launch(a, c.stream));
+    RUN(c, K_ATTN, 256.0 * M * p.dim, 8.0 * M * p.dim, attn_core_launch(a, c.stream));
     SUNET_TRY(run_linear(c, p.proj, O, p.dim, M, Y, p.dim));
-    RUN(c, cast_f16_to_f32(Y, out, n, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n), cast_f16_to_f32(Y, out, n, c.stream));
     return 0;
   });
 }
@@ -603,10 +633,10 @@ int sunet_mlp_fwd(sunet_handle_t h, const float* x, int64_t rows, float* out, vo
     SUNET_TRY(c.sc.take_t(&xi, rows * p.cin));
     SUNET_TRY(c.sc.take_t(&Hd, rows * p.hid));
     SUNET_TRY(c.sc.take_t(&Y, rows * p.cout));
-    RUN(c, cast_f32_to_f16(x, xi, rows * p.cin, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (rows * p.cin), cast_f32_to_f16(x, xi, rows * p.cin, c.stream));
     SUNET_TRY(run_linear(c, p.fc1, xi, p.cin, rows, Hd, p.hid, ACT_GELU));
     SUNET_TRY(run_linear(c, p.fc2, Hd, p.hid, rows, Y, p.cout));
-    RUN(c, cast_f16_to_f32(Y, out, rows * p.cout, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (rows * p.cout), cast_f16_to_f32(Y, out, rows * p.cout, c.stream));
     return 0;
   });
 }
@@ -619,9 +649,9 @@ int sunet_patch_merging_fwd(sunet_handle_t h, const float* x, int batch, float* 
     __half *xi, *Y;
     SUNET_TRY(c.sc.take_t(&xi, n_in));
     SUNET_TRY(c.sc.take_t(&Y, n_out));
-    RUN(c, cast_f32_to_f16(x, xi, n_in, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n_in), cast_f32_to_f16(x, xi, n_in, c.stream));
     SUNET_TRY(p.forward(c, xi, Y, batch));
-    RUN(c, cast_f16_to_f32(Y, out, n_out, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n_out), cast_f16_to_f32(Y, out, n_out, c.stream));
     return 0;
   });
 }
@@ -633,7 +663,7 @@ int sunet_upsample_fwd(sunet_handle_t h, const float* x, int batch, float* out, 
   return with_scratch(static_cast<cudaStream_t>(stream), [&](Ctx& c) -> int {
     __half* xi;
     SUNET_TRY(c.sc.take_t(&xi, n_in));
-    RUN(c, cast_f32_to_f16(x, xi, n_in, c.stream));
+    RUN(c, K_CAST, 0.0, 6.0 * (n_in), cast_f32_to_f16(x, xi, n_in, c.stream));
     SUNET_TRY(p.forward(c, xi, out, 1, batch));  // raster NHWC == (B, 4L, C/2) for r=2 and (B, 4H, 4W, C) for r=4
     return 0;
   });
@@ -650,13 +680,13 @@ int sunet_patch_embed_fwd(sunet_handle_t h, const float* x, int batch, int himg,
     SUNET_TRY(c.sc.take_t(&A, M * K));
     SUNET_TRY(c.sc.take_t(&Y, M * p.E));
     SUNET_TRY(c.sc.take_t(&Yn, M * p.E));
-    RUN(c, im2col_patch(x, batch, p.cin, himg, wimg, p.P, A, c.stream));
+    RUN(c, K_IM2COL, 0.0, 6.0 * M * K, im2col_patch(x, batch, p.cin, himg, wimg, p.P, A, c.stream));
     SUNET_TRY(run_linear(c, p.proj, A, K, M, Y, p.E));
     if (p.has_norm) {
-      RUN(c, layernorm_f16(Y, p.E, Yn, p.E, p.g, p.b, M, p.E, c.stream));
-      RUN(c, cast_f16_to_f32(Yn, out, M * p.E, c.stream));
+      RUN(c, K_LAYERNORM, 0.0, 4.0 * M * p.E, layernorm_f16(Y, p.E, Yn, p.E, p.g, p.b, M, p.E, c.stream));
+      RUN(c, K_CAST, 0.0, 6.0 * (M * p.E), cast_f16_to_f32(Yn, out, M * p.E, c.stream));
     } else {
-      RUN(c, cast_f16_to_f32(Y, out, M * p.E, c.stream));
+      RUN(c, K_CAST, 0.0, 6.0 * (M * p.E), cast_f16_to_f32(Y, out, M * p.E, c.stream));
     }
     return 0;
   });
@@ -692,6 +722,35 @@ int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int
   c.sc.base = static_cast<uint8_t*>(workspace);
   c.sc.cap = workspace_bytes;
   return model_forward(mh->p, c, x, in_chans, batch, max_chunk, out);
+}
+
+int sunet_forward_profile(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream, sunet_prof_rec* recs, int max_recs, int* n_recs) {
+  GET_HANDLE(ModelHandle, mh, h, "sunet");
+  if (!x || !out || !workspace || !recs || !n_recs) return fail(SUNET_E_ARG, "sunet_forward_profile: null pointer");
+  std::vector<ProfRec> prof;
+  Ctx c;
+  c.stream = static_cast<cudaStream_t>(stream);
+  c.sc.base = static_cast<uint8_t*>(workspace);
+  c.sc.cap = workspace_bytes;
+  c.prof = &prof;
+  int rc = model_forward(mh->p, c, x, in_chans, batch, max_chunk, out);
+  cudaError_t e = cudaStreamSynchronize(c.stream);
+  if (!rc && e != cudaSuccess) rc = fail((int)e, "sunet_forward_profile: %s", cudaGetErrorString(e));
+  int n = 0;
+  for (ProfRec& r : prof) {
+    if (!rc && n < max_recs) {
+      float ms = 0.f;
+      if (r.e1 && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        recs[n].kind = r.kind; recs[n].ms = ms; recs[n].flops = r.flops; recs[n].bytes = r.bytes;
+        ++n;
+      }
+    }
+    if (r.e0) cudaEventDestroy(r.e0);
+    if (r.e1) cudaEventDestroy(r.e1);
+  }
+  *n_recs = n;
+  return rc;
 }
 
 int sunet_selftest_umma(void* stream) {

@@ -25,5 +25,6 @@ class SUNet_model(nn.Module):
         kwargs = {kw: section[key] for key, kw in _YAML_TO_KWARG.items()}
         self.swin_unet = SUNet(in_chans=3, out_chans=out_chans, **kwargs)
 
-    def forward(self, x):
-        return self.swin_unet(x)  # 1- or 3-channel input; the grey->RGB repeat is folded into the first kernel
+    def forward(self, x, out=None):
+        # 1- or 3-channel input; the grey->RGB repeat is folded into the first kernel.  `out` (optional) receives the result.
+        return self.swin_unet(x, out=out)

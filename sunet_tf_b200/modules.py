@@ -494,6 +494,22 @@ class SUNet(_Packed):
         return int(_lib.load().sunet_forward_launches(self._handle(), batch, self.max_chunk))
 
     @torch.no_grad()
+    def profile_forward(self, x):
+        """One forward with CUDA events around every kernel launch.  Returns (out, [(kind_name, ms, flops, bytes), ...])."""
+        x = _lib.require_cuda(x, "x")
+        B, C, H, W = x.shape
+        handle = self._handle()
+        ws = self._workspace(handle, B, x.device)
+        out = torch.empty(B, self.out_chans, H, W, device=x.device, dtype=torch.float32)
+        cap = self.launches_per_forward(B) + 16
+        recs = (_lib.ProfRec * cap)()
+        n = ctypes.c_int(0)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_forward_profile(handle, _ptr(x), C, B, self.max_chunk, _ptr(out), _ptr(ws), ws.numel(),
+                                                        _lib.stream_ptr(x.device), recs, cap, ctypes.byref(n)))
+        return out, [(_lib.KERNEL_KINDS[r.kind], r.ms, r.flops, r.bytes) for r in recs[:n.value]]
+
+    @torch.no_grad()
     def forward(self, x, out=None):
         x = _lib.require_cuda(x, "x")
         B, C, H, W = x.shape
