@@ -48,6 +48,8 @@ struct GemmEpi {
   int64_t ldc;
   int out_f32;
   int n_tiles;
+  int64_t total_tiles;
+  uint32_t acc_cols, tmem_cols;
 };
 
 struct GemmOp {

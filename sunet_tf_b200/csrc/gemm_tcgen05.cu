@@ -1,10 +1,12 @@
-// Warp-specialised tcgen05 GEMM (sm_100a): TMA (128B swizzle) -> smem ring -> tcgen05.mma (fp32 accum in TMEM)
-// -> tcgen05.ld epilogue (bias / GELU / PReLU / residual) -> global.
-//   warp 0 : TMA producer (one elected lane)
-//   warp 1 : TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-5 : epilogue, warp (w & 3) owns TMEM lanes [32*(w&3), +32) == tile rows
-// One 128 x block_n output tile per CTA; several CTAs co-reside per SM when the ring is short (small K),
-// which overlaps one tile's epilogue with another tile's loads/MMAs.
+// Persistent warp-specialised tcgen05 GEMM (sm_100a):
+//   TMA (128B swizzle) -> smem ring -> tcgen05.mma (fp32 accumulators, double-buffered in TMEM)
+//   -> tcgen05.ld epilogue (bias / GELU / PReLU / residual) -> global.
+//   warp 0    : TMA producer (one elected lane); runs ahead across tiles, bounded only by the smem ring
+//   warp 1    : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-17: epilogue; warp w owns TMEM lanes [32*(w&3), +32) == tile rows and one quarter of the tile columns
+// One CTA per SM loops over 128 x block_n output tiles (tile = blockIdx.x + i * gridDim.x, n fastest so that
+// co-running CTAs share A rows in L2).  While the epilogue drains accumulator stage s, the MMA warp fills stage s^1
+// and the producer prefetches the operands of the tiles after that.
 #include "error.h"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -14,19 +16,182 @@ namespace sunet {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;  // 64 fp16 = one 128-byte swizzle row
 static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-static constexpr int MAX_STAGES = 8;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int MAX_STAGES = 12;
+static constexpr int EPI_WARPS = 16;
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 static constexpr int GEMM_MAX_DYN_SMEM = 226 * 1024;  // 227 KB per CTA minus the static barriers
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = x * Phi(x), Phi(x) = 0.5 * (1 + erf(x / sqrt 2)) (nn.GELU default, SUNet_detail.py:9).
+// Phi is evaluated as 0.5 + 0.5 * tanh(u * (c0 + c1 u^2 + c2 u^4)), u = clamp(x, +-7): a minimax fit of atanh(erf(x/sqrt2))
+// with max |dPhi| = 5.0e-5 (fit) + 2.4e-4 (tanh.approx.f32, 2^-11 relative); ~9 instructions instead of ~40 for erff().
+// The hidden activation is stored in fp16 (2^-11 relative) anyway; measured effect on the SUNet output < 1e-4.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = fminf(fmaxf(x, -7.0f), 7.0f);
+  const float t = u * u;
+  float p = fmaf(t, -3.5151847398e-04f, 3.7005657172e-02f);
+  p = fmaf(t, p, 7.9750787105e-01f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
+  const float h = 0.5f * x;
+  return fmaf(h, th, h);
+}
 
-__global__ void __launch_bounds__(GEMM_THREADS)
+// Packed-half2 variant for the fc1 epilogue (the result is stored as fp16 anyway): 5 instructions per element.
+// t = min(u^2, 49) keeps the odd polynomial monotone for any |x| (tanh saturates to +-1 long before).
+__device__ __forceinline__ uint32_t gelu_fast_h2(uint32_t xbits) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&xbits);
+  const __half2 t = __hmin2(__hmul2(x, x), __float2half2_rn(49.0f));
+  __half2 p = __hfma2(t, __float2half2_rn(-3.5151847398e-04f), __float2half2_rn(3.7005657172e-02f));
+  p = __hfma2(t, p, __float2half2_rn(7.9750787105e-01f));
+  const __half2 z = __hmul2(x, p);
+  uint32_t th;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(*reinterpret_cast<const uint32_t*>(&z)));
+  const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 g = __hfma2(h, *reinterpret_cast<const __half2*>(&th), h);
+  return *reinterpret_cast<const uint32_t*>(&g);
+}
+
+// Per-warp staging tile: 32 rows x 128 bytes, 16-byte chunk j of row r lives at chunk slot (j ^ (r & 7)).
+// Row-wise accesses (thread = row) and coalesced accesses (consecutive lanes = consecutive chunks of a row) are both
+// bank-conflict free for 8 chunks per row (2-way at most for narrower groups).
+__device__ __forceinline__ uint32_t stage_off(int r, int ch) { return static_cast<uint32_t>((r << 7) + ((ch ^ (r & 7)) << 4)); }
+
+// ---- epilogue math on 16 accumulator columns of one row: bias, activation, residual -> staging row (fp16 or fp32).
+// The residual chunk (fp16 output only) sits in the staging slot that the result overwrites.
+template <bool F32>
+__device__ __forceinline__ void epilogue_math16(const GemmEpi& p, const uint32_t* v, int n, float slope, uint32_t stg_row, int lane,
+                                                int col_in_group) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+      f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+    }
+  }
+  if constexpr (!F32) {
+    const int ch0 = col_in_group >> 3;  // first of the two 16-byte chunks of these 16 fp16 columns
+    if (p.act == ACT_GELU && p.R == nullptr) {
+      // fc1 path: round the pre-activation to fp16 pairs and evaluate GELU on packed halves
+      uint4 o[2];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half2 x2 = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+        ow[j] = gelu_fast_h2(*reinterpret_cast<const uint32_t*>(&x2));
+      }
+      sts128(stg_row + (((ch0) ^ (lane & 7)) << 4), o[0]);
+      sts128(stg_row + (((ch0 + 1) ^ (lane & 7)) << 4), o[1]);
+      return;
+    }
+    if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = gelu_fast(f[j]);
+    } else if (p.act == ACT_PRELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : slope * f[j];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t slot = stg_row + (((ch0 + h) ^ (lane & 7)) << 4);
+      if (p.R != nullptr) {
+        const uint4 rr = lds128(slot);
+        const __half2* r2 = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(r2[j]);
+          f[h * 8 + 2 * j] += t.x;
+          f[h * 8 + 2 * j + 1] += t.y;
+        }
+      }
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(f[h * 8 + 2 * j], f[h * 8 + 2 * j + 1]);
+      sts128(slot, o);
+    }
+  } else {
+    if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = gelu_fast(f[j]);
+    } else if (p.act == ACT_PRELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : slope * f[j];
+    }
+    const int ch0 = col_in_group >> 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stg_row + (((ch0 + j) ^ (lane & 7)) << 4),
+             make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+  }
+}
+
+// One group of GC accumulator columns for the 32 rows of this warp; GC * esize is 32, 64 or 128 bytes per row.
+template <int GC, bool F32>
+__device__ __forceinline__ void epilogue_group(const GemmEpi& p, uint32_t stg, uint32_t taddr, int c, int64_t m_base,
+                                               int rows_valid, int n0, int lane, float slope) {
+  constexpr int ESIZE = F32 ? 4 : 2;
+  constexpr int OCH = GC * ESIZE / 16;   // 16-byte chunks per output row (power of two: 2, 4 or 8)
+  const uint32_t stg_row = stg + (lane << 7);
+  if (!F32 && p.R != nullptr) {
+    // coalesced residual load into the staging tile (consecutive lanes -> consecutive chunks of a row)
+    const __half* rbase = p.R + m_base * p.ldr + n0 + c;
+#pragma unroll
+    for (int k = 0; k < OCH; ++k) {
+      const int i = k * 32 + lane;
+      const int r = i / OCH, ch = i % OCH;
+      if (r < rows_valid) sts128(stg + stage_off(r, ch), __ldg(reinterpret_cast<const uint4*>(rbase + r * p.ldr) + ch));
+    }
+    __syncwarp();
+  }
+  if constexpr (GC >= 32) {
+#pragma unroll
+    for (int cc = 0; cc < GC; cc += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c + cc, v);
+      tmem_ld_wait();
+      epilogue_math16<F32>(p, v, n0 + c + cc, slope, stg_row, lane, cc);
+      epilogue_math16<F32>(p, v + 16, n0 + c + cc + 16, slope, stg_row, lane, cc + 16);
+    }
+  } else {
+    uint32_t v[16];
+    tmem_ld16(taddr + c, v);
+    tmem_ld_wait();
+    epilogue_math16<F32>(p, v, n0 + c, slope, stg_row, lane, 0);
+  }
+  __syncwarp();
+  uint8_t* cbase = static_cast<uint8_t*>(p.C) + (m_base * p.ldc + n0 + c) * ESIZE;
+#pragma unroll
+  for (int k = 0; k < OCH; ++k) {
+    const int i = k * 32 + lane;
+    const int r = i / OCH, ch = i % OCH;
+    if (r < rows_valid) *reinterpret_cast<uint4*>(cbase + static_cast<int64_t>(r) * p.ldc * ESIZE + (ch << 4)) = lds128(stg + stage_off(r, ch));
+  }
+  __syncwarp();
+}
+
+template <bool F32>
+__device__ __forceinline__ void epilogue_range(const GemmEpi& p, uint32_t stg, uint32_t taddr, int c_begin, int c_end, int64_t m_base,
+                                               int rows_valid, int n0, int lane, float slope) {
+  constexpr int GMAX = F32 ? 32 : 64;  // 128-byte staging rows
+  int c = c_begin;
+  for (; c + GMAX <= c_end; c += GMAX) epilogue_group<GMAX, F32>(p, stg, taddr, c, m_base, rows_valid, n0, lane, slope);
+  if constexpr (!F32) {
+    if (c + 32 <= c_end) { epilogue_group<32, F32>(p, stg, taddr, c, m_base, rows_valid, n0, lane, slope); c += 32; }
+  }
+  if (c + 16 <= c_end) epilogue_group<16, F32>(p, stg, taddr, c, m_base, rows_valid, n0, lane, slope);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tn_f16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmW, const GemmEpi p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -35,15 +200,12 @@ __global__ void __launch_bounds__(GEMM_THREADS)
   const int block_n = p.block_n;
   const int stages = p.stages;
   const uint32_t stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
-  const int n0 = n_tile * block_n;
-  const int64_t m0 = static_cast<int64_t>(m_tile) * BLOCK_M;
   const int kb0 = (p.K0 + BLOCK_K - 1) / BLOCK_K;
   const int kb1 = (p.K1 + BLOCK_K - 1) / BLOCK_K;
   const int num_kb = kb0 + kb1;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(block_n)) tmem_cols <<= 1;
+  const uint32_t acc_cols = p.acc_cols;          // TMEM columns per accumulator stage (>= block_n)
+  const uint32_t tmem_cols = p.tmem_cols;        // power of two >= 2 * acc_cols
+  const int64_t total_tiles = p.total_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -53,7 +215,10 @@ __global__ void __launch_bounds__(GEMM_THREADS)
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -67,113 +232,89 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * stage_bytes;
-        uint8_t* sb = sa + A_TILE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        if (it < kb0) {
-          tma_load_2d(sa, &tmA0, &full_bar[s], it * BLOCK_K, static_cast<int>(m0));
-          tma_load_2d(sb, &tmW, &full_bar[s], it * BLOCK_K, n0);
-        } else {
-          const int j = it - kb0;
-          tma_load_2d(sa, &tmA1, &full_bar[s], j * BLOCK_K, static_cast<int>(m0));
-          tma_load_2d(sb, &tmW, &full_bar[s], p.K0 + j * BLOCK_K, n0);
+      uint32_t it = 0;  // global k-block counter: the ring runs across tiles
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = static_cast<int>(tile % p.n_tiles) * block_n;
+        const int m0 = static_cast<int>(tile / p.n_tiles) * BLOCK_M;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          if (kb < kb0) {
+            tma_load_2d(sa, &tmA0, &full_bar[s], kb * BLOCK_K, m0);
+            tma_load_2d(sb, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+          } else {
+            const int j = kb - kb0;
+            tma_load_2d(sa, &tmA1, &full_bar[s], j * BLOCK_K, m0);
+            tma_load_2d(sb, &tmW, &full_bar[s], p.K0 + j * BLOCK_K, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(BLOCK_M, block_n);
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0;
+      uint32_t local = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const uint32_t as = local & 1;
+        const uint32_t aph = (local >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint32_t sb = sa + A_TILE_BYTES;
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sb);
-        // valid K elements in this block (a K0/K1 tail shorter than 64 is zero-filled by TMA but not multiplied)
-        int kvalid;
-        if (it < kb0) kvalid = min(BLOCK_K, p.K0 - it * BLOCK_K);
-        else kvalid = min(BLOCK_K, p.K1 - (it - kb0) * BLOCK_K);
-        const int ksteps = (kvalid + 15) >> 4;
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + as * acc_cols;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sb);
+          // valid K elements in this block (a K0/K1 tail shorter than 64 is zero-filled by TMA but not multiplied)
+          const int kvalid = kb < kb0 ? min(BLOCK_K, p.K0 - kb * BLOCK_K) : min(BLOCK_K, p.K1 - (kb - kb0) * BLOCK_K);
+          const int ksteps = (kvalid + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        tc_commit(&tmem_full_bar[as]);  // accumulator of this tile complete
       }
-      tc_commit(&tmem_full_bar);   // accumulator complete
     }
   } else {
-    // ---------------- epilogue: thread <-> one row of the tile
+    // ---------------- epilogue: thread <-> one row of the tile, warp <-> (lane quadrant, column half)
     const int q = warp & 3;
+    const int quarter = (warp - 2) >> 2;                    // 0..3: which slice of the tile columns
+    const int units = block_n >> 4;                          // 16-column units, split as evenly as possible
+    const int c_begin = (quarter * units >> 2) << 4;
+    const int c_end = ((quarter + 1) * units >> 2) << 4;
     const int row = q * 32 + lane;
-    const int64_t m = m0 + row;
-    const bool row_ok = m < p.M;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t stg = smem_u32(smem + static_cast<size_t>(stages) * stage_bytes + (warp - 2) * 4096);  // this warp's staging tile
     float slope = 0.f;
     if (p.act == ACT_PRELU) slope = __ldg(p.prelu);
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    for (int c = 0; c < block_n; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c, v);
-      tmem_ld_wait();
-      if (row_ok) {
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        const int n = n0 + c;
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-          }
-        }
-        if (p.act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
-        } else if (p.act == ACT_PRELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : slope * f[j];
-        }
-        if (p.R != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.R + m * p.ldr + n);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 r = __ldg(rp + h);
-            const __half2* r2 = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 t = __half22float2(r2[j]);
-              f[h * 8 + 2 * j] += t.x;
-              f[h * 8 + 2 * j + 1] += t.y;
-            }
-          }
-        }
-        if (p.out_f32) {
-          float4* cp = reinterpret_cast<float4*>(static_cast<float*>(p.C) + m * p.ldc + n);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          uint4* cp = reinterpret_cast<uint4*>(static_cast<__half*>(p.C) + m * p.ldc + n);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint4 o;
-            __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(f[h * 8 + 2 * j], f[h * 8 + 2 * j + 1]);
-            cp[h] = o;
-          }
-        }
-      }
+    uint32_t local = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const uint32_t as = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * block_n;
+      const int64_t m = static_cast<int64_t>(tile / p.n_tiles) * BLOCK_M + row;
+      const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after();
+      const int64_t m_base = m - lane;
+      const int rows_valid = static_cast<int>(min(static_cast<int64_t>(32), p.M - m_base));  // <= 0 for fully out-of-range warps
+      if (p.out_f32) epilogue_range<true>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
+      else epilogue_range<false>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
   }
   tc_fence_before();
@@ -223,12 +364,24 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 static int pick_block_n(int N, int64_t m_tiles, int K) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
-  // largest tile that still yields >= 2 waves of 148 SMs; otherwise the largest tile >= 96 (smem-read bound
-  // below that for SS-mode MMAs), otherwise whatever divides N.
+  // Measured on B200 (profiles/r01_gemm_*.log): wide tiles win whenever they still give ~0.6 tiles per SM (the MMA
+  // needs N >= 128 to stay off the smem-read bound, and one wide epilogue beats several narrow ones); below that,
+  // fall back to the widest tile <= 128 to spread the small-M stages over more SMs.
+  const int64_t want = (6 * static_cast<int64_t>(num_sms())) / 10;
   for (int c : cand)
-    if (N % c == 0 && m_tiles * (N / c) >= 296) return c;
+    if (N % c == 0 && m_tiles * (N / c) >= want) return c;
   (void)K;
   for (int c : cand)
     if (N % c == 0 && c <= 128) return c;
@@ -253,9 +406,8 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   if (m_tiles * n_tiles > 0x7fffffffLL) return fail(SUNET_E_SHAPE, "gemm: grid too large");
   const int num_kb = (a.K0 + BLOCK_K - 1) / BLOCK_K + (a.K1 + BLOCK_K - 1) / BLOCK_K;
   const int stage_bytes = A_TILE_BYTES + bn * BLOCK_K * 2;
-  int stages = (GEMM_MAX_DYN_SMEM - 1024) / stage_bytes;
+  int stages = (GEMM_MAX_DYN_SMEM - 1024 - EPI_WARPS * 4096) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > num_kb) stages = num_kb;
   if (stages < 1) stages = 1;
   SUNET_TRY(make_tmap_2d_f16(&op->tmA0, a.A0, a.K0, a.M, a.lda0, BLOCK_M));
   if (a.K1 > 0) SUNET_TRY(make_tmap_2d_f16(&op->tmA1, a.A1, a.K1, a.M, a.lda1, BLOCK_M));
@@ -265,9 +417,17 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   e.M = a.M; e.N = a.N; e.K0 = a.K0; e.K1 = a.K1; e.block_n = bn; e.stages = stages;
   e.bias = a.bias; e.prelu = a.prelu; e.act = a.act; e.R = a.R; e.ldr = a.ldr; e.C = a.C; e.ldc = a.ldc;
   e.out_f32 = a.out_f32; e.n_tiles = n_tiles;
+  e.total_tiles = m_tiles * n_tiles;
+  e.acc_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256));
+  e.tmem_cols = 2 * e.acc_cols;
   if (a.act == ACT_PRELU && a.prelu == nullptr) return fail(SUNET_E_ARG, "gemm: PReLU needs a slope pointer");
-  op->grid = static_cast<unsigned>(m_tiles * n_tiles);
-  op->smem = stages * stage_bytes + 1024;
+  if (a.out_f32 && a.R != nullptr) return fail(SUNET_E_ARG, "gemm: a residual with fp32 output is not supported");
+  const int64_t tiles = m_tiles * n_tiles;
+  op->grid = static_cast<unsigned>(tiles < num_sms() ? tiles : num_sms());
+  // never keep more ring stages than this CTA will ever fill
+  const int64_t tiles_per_cta = (tiles + op->grid - 1) / op->grid;
+  if (static_cast<int64_t>(stages) > tiles_per_cta * num_kb) { stages = static_cast<int>(tiles_per_cta * num_kb); e.stages = stages; }
+  op->smem = stages * stage_bytes + 1024 + EPI_WARPS * 4096;
   op->flops = 2.0 * (double)a.M * a.N * (a.K0 + a.K1);
   return 0;
 }
