@@ -34,17 +34,153 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One 16-row query tile of one head.  MI (tile index within this warp) is a template parameter so that the
+// relative-position bias - held in registers as tb[e][k], k = 2*MI + row_half - key_row + 7 - is indexed at compile time.
+template <int HD, int MT, int MI, int MASK>
+__device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, const __half* v_h, __half* o_h, int mt, int lane,
+                                          const float (&tb)[2][2 * MT + 7], bool mrow, bool mcol, const float* mexp) {
+  constexpr int HD_PAD = (HD + 15) / 16 * 16;
+  constexpr int LDS = HD_PAD + 8;
+  constexpr int KS = HD_PAD / 16;
+  constexpr int NO = HD_PAD / 8;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t qa[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+    ldsm_x4(qa[ks], smem_u32(q_h + (mt * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
+  // S accumulators start from the bias (+ mask): rows i0 = mt*16+g (window row 2mt) and i1 = i0+8 (window row 2mt+1),
+  // keys j = nt*8 + 2*tq + e (window row nt, column 2*tq+e)
+  float s[8][4];
+  if (MASK == 1) {
+    // closed-form SW-MSA mask (SUNet_detail.py:202-221, shift = 4): -100 where the wrapped halves differ, applied once
+    const bool r0hi = (2 * mt) >= 4, r1hi = (2 * mt + 1) >= 4;
+    float cm[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cm[e] = (mcol && ((g >= 4) != ((2 * tq + e) >= 4))) ? -100.f : 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float rm0 = (mrow && (r0hi != (nt >= 4))) ? -100.f : 0.f;
+      const float rm1 = (mrow && (r1hi != (nt >= 4))) ? -100.f : 0.f;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = tb[e][2 * MI + 0 - nt + 7] + fminf(rm0, cm[e]);
+        s[nt][2 + e] = tb[e][2 * MI + 1 - nt + 7] + fminf(rm1, cm[e]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = tb[e][2 * MI + 0 - nt + 7];
+        s[nt][2 + e] = tb[e][2 * MI + 1 - nt + 7];
+      }
+    if (MASK == 2) {  // explicit additive mask tensor (stand-alone WindowAttention.forward(x, mask))
+      const int i0 = mt * 16 + g;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * tq + e;
+          s[nt][e] += __ldg(mexp + i0 * 64 + j);
+          s[nt][2 + e] += __ldg(mexp + (i0 + 8) * 64 + j);
+        }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; nt += 2) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      // matrices: (nt, k lo), (nt, k hi), (nt+1, k lo), (nt+1, k hi)
+      uint32_t kb[4];
+      ldsm_x4(kb, smem_u32(k_h + ((nt + (lane >> 4)) * 8 + (lane & 7)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8));
+      mma_16816(s[nt], qa[ks], kb[0], kb[1]);
+      mma_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
+    }
+  }
+  // ---- softmax over 64 keys (each row lives in the 4 lanes of a quad)
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+  const float mm0 = m0 * LOG2E, mm1 = m1 * LOG2E;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = exp2f(fmaf(s[nt][0], LOG2E, -mm0));
+    s[nt][1] = exp2f(fmaf(s[nt][1], LOG2E, -mm0));
+    s[nt][2] = exp2f(fmaf(s[nt][2], LOG2E, -mm1));
+    s[nt][3] = exp2f(fmaf(s[nt][3], LOG2E, -mm1));
+    sum0 += s[nt][0] + s[nt][1];
+    sum1 += s[nt][2] + s[nt][3];
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
+  // ---- O = P V
+  float o[NO][4];
+#pragma unroll
+  for (int n = 0; n < NO; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int n = 0; n < NO; n += 2) {
+      // transposed 8x8 loads of V[key][hd]: (keys lo, n), (keys hi, n), (keys lo, n+1), (keys hi, n+1)
+      uint32_t vb[4];
+      ldsm_x4_t(vb, smem_u32(v_h + (kk * 16 + (lane & 15)) * LDS + (n + (lane >> 4)) * 8));
+      mma_16816(o[n], pa, vb[0], vb[1]);
+      mma_16816(o[n + 1], pa, vb[2], vb[3]);
+    }
+  }
+  // ---- normalise and park O in this tile's own Q rows (already consumed into registers)
+  __syncwarp();
+  const int i0 = mt * 16 + g, i1 = i0 + 8;
+#pragma unroll
+  for (int n = 0; n < NO; ++n) {
+    const int c = n * 8 + 2 * tq;
+    if (c < HD) {
+      *reinterpret_cast<uint32_t*>(o_h + i0 * LDS + c) = pack_half2(o[n][0] * inv0, o[n][1] * inv0);
+      *reinterpret_cast<uint32_t*>(o_h + i1 * LDS + c) = pack_half2(o[n][2] * inv1, o[n][3] * inv1);
+    }
+  }
+}
+
+template <int HD, int MT, int MASK>
+__device__ __forceinline__ void attn_tiles(const __half* q_h, const __half* k_h, const __half* v_h, __half* o_h, int mbase, int lane,
+                                           const float (&tb)[2][2 * MT + 7], bool mrow, bool mcol, const float* mexp) {
+  attn_tile<HD, MT, 0, MASK>(q_h, k_h, v_h, o_h, mbase + 0, lane, tb, mrow, mcol, mexp);
+  if constexpr (MT > 1) attn_tile<HD, MT, 1, MASK>(q_h, k_h, v_h, o_h, mbase + 1, lane, tb, mrow, mcol, mexp);
+  if constexpr (MT > 2) {
+    attn_tile<HD, MT, 2, MASK>(q_h, k_h, v_h, o_h, mbase + 2, lane, tb, mrow, mcol, mexp);
+    attn_tile<HD, MT, 3, MASK>(q_h, k_h, v_h, o_h, mbase + 3, lane, tb, mrow, mcol, mexp);
+  }
+}
+
 template <int HD, int HPC>
 __global__ void __launch_bounds__(256) attn_core_kernel(const AttnCoreArgs p) {
   constexpr int HD_PAD = (HD + 15) / 16 * 16;
   constexpr int LDS = HD_PAD + 8;           // fp16 elements per smem row (pad breaks ldmatrix bank conflicts)
-  constexpr int KS = HD_PAD / 16;           // k-steps of Q K^T
-  constexpr int NO = HD_PAD / 8;            // n-tiles of O
   constexpr int WPH = 8 / HPC;              // warps per head
   constexpr int MT = 4 / WPH;               // 16-row query tiles per warp
   constexpr int SEG = HPC * HD;             // contiguous fp16 per token per q/k/v segment handled by this CTA
-  constexpr int CHUNKS = SEG / 8;           // 16-byte chunks per segment
-  static_assert(SEG % 8 == 0, "segment must be 16-byte granular");
+  constexpr int VEC = (HD % 8 == 0) ? 8 : 4;  // elements per global/shared vector (16 or 8 bytes); never straddles a head
+  constexpr int VPH = HD / VEC;             // vectors per head
+  constexpr int VPS = SEG / VEC;            // vectors per segment
+  static_assert(HD % VEC == 0, "head_dim must be a multiple of 4");
   constexpr int TBL = 232;                  // 225 padded
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -79,7 +215,7 @@ __global__ void __launch_bounds__(256) attn_core_kernel(const AttnCoreArgs p) {
     const int h = i / 225, e = i % 225;
     sTbl[h * TBL + e] = __ldg(p.bias_table + e * p.heads + hg * HPC + h);
   }
-  // zero the K-padding columns (and the unused tail) once
+  // zero the K-padding columns once
   if constexpr (HD_PAD != HD) {
     constexpr int PADW = (HD_PAD - HD) / 2;  // half2 words per row
     for (int i = tid; i < 3 * HPC * 64 * PADW; i += 256) {
@@ -89,156 +225,53 @@ __global__ void __launch_bounds__(256) attn_core_kernel(const AttnCoreArgs p) {
   }
   __syncthreads();
 
-  // ---- gather q/k/v rows: 16-byte global loads, 4-byte smem scatter (head boundaries are 4-byte granular)
-  for (int i = tid; i < 64 * 3 * CHUNKS; i += 256) {
-    const int t = i / (3 * CHUNKS);
-    const int rem = i % (3 * CHUNKS);
-    const int seg = rem / CHUNKS, ch = rem % CHUNKS;
-    const __half* src = p.qkv + sRow[t] * p.ld + seg * p.C + hg * SEG + ch * 8;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    __half* base = (seg == 0 ? sQ : (seg == 1 ? sK : sV));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = ch * 8 + j * 2;       // element within the segment
-      const int h = e / HD, c = e % HD;
-      *reinterpret_cast<uint32_t*>(base + (h * 64 + t) * LDS + c) = w[j];
-    }
+  // ---- gather q/k/v rows head-wise: one vector never straddles a head, consecutive threads read consecutive vectors
+  for (int i = tid; i < 64 * 3 * VPS; i += 256) {
+    const int t = i / (3 * VPS);
+    const int rem = i - t * (3 * VPS);
+    const int seg = rem / VPS, vv = rem - seg * VPS;
+    const int h = vv / VPH, v = vv - h * VPH;
+    const __half* src = p.qkv + sRow[t] * p.ld + seg * p.C + hg * SEG + vv * VEC;
+    __half* dst = (seg == 0 ? sQ : (seg == 1 ? sK : sV)) + (h * 64 + t) * LDS + v * VEC;
+    if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+    else *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(src));
   }
   __syncthreads();
 
-  const int h = warp % HPC;
-  const int mbase = (warp / HPC) * MT;
-  const __half* q_h = sQ + h * 64 * LDS;
-  const __half* k_h = sK + h * 64 * LDS;
-  const __half* v_h = sV + h * 64 * LDS;
-  const float* tbl = sTbl + h * TBL;
-  const int g = lane >> 2, tq = lane & 3;
-  constexpr float LOG2E = 1.4426950408889634f;
-
-  for (int mi = 0; mi < MT; ++mi) {
-    const int mt = mbase + mi;
-    uint32_t qa[KS][4];
+  {
+    const int h = warp % HPC;
+    const int mbase = (warp / HPC) * MT;
+    const __half* q_h = sQ + h * 64 * LDS;
+    const __half* k_h = sK + h * 64 * LDS;
+    const __half* v_h = sV + h * 64 * LDS;
+    __half* o_h = sQ + h * 64 * LDS;
+    const int g = lane >> 2, tq = lane & 3;
+    // this thread's slice of the relative-position bias: tb[e][k] = table[(k + 2*mbase) * 15 + (g - (2*tq+e) + 7)]
+    float tb[2][2 * MT + 7];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      ldsm_x4(qa[ks], smem_u32(q_h + (mt * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
-    float s[8][4];
+    for (int e = 0; e < 2; ++e)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-#pragma unroll
-    for (int nt = 0; nt < 8; nt += 2) {
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        // matrices: (nt, k lo), (nt, k hi), (nt+1, k lo), (nt+1, k hi)
-        uint32_t kb[4];
-        ldsm_x4(kb, smem_u32(k_h + ((nt + (lane >> 4)) * 8 + (lane & 7)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8));
-        mma_16816(s[nt], qa[ks], kb[0], kb[1]);
-        mma_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
-      }
-    }
-    // ---- bias + mask, rows i0 = mt*16+g and i1 = i0+8, keys j = nt*8 + 2*tq + {0,1}
-    const int i0 = mt * 16 + g, i1 = i0 + 8;
-    const int ri0 = i0 >> 3, ci0 = i0 & 7, ri1 = i1 >> 3, ci1 = i1 & 7;
-    const int sb = 8 - p.shift;   // tokens with r (c) >= sb wrapped around from the other image edge
+      for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = sTbl[h * TBL + (k + 2 * mbase) * 15 + (g - 2 * tq - e + 7)];
     const bool mrow = p.mask_mode == 1 && wr == nWr - 1;
     const bool mcol = p.mask_mode == 1 && wc == nWc - 1;
-    const float* mexp = p.mask_mode == 2 ? p.mask + static_cast<long long>(win % p.mask_nw) * 4096 : nullptr;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + 2 * tq + e;
-        const int rj = j >> 3, cj = j & 7;   // rj == nt
-        float b0 = tbl[(ri0 - rj + 7) * 15 + (ci0 - cj + 7)];
-        float b1 = tbl[(ri1 - rj + 7) * 15 + (ci1 - cj + 7)];
-        if (mrow) {
-          if ((ri0 >= sb) != (rj >= sb)) b0 -= 100.f;
-          if ((ri1 >= sb) != (rj >= sb)) b1 -= 100.f;
-        }
-        if (mcol) {
-          // the reference mask is 0 / -100 per pair (regions differ in row OR col split): apply at most once
-          if ((ci0 >= sb) != (cj >= sb) && !(mrow && (ri0 >= sb) != (rj >= sb))) b0 -= 100.f;
-          if ((ci1 >= sb) != (cj >= sb) && !(mrow && (ri1 >= sb) != (rj >= sb))) b1 -= 100.f;
-        }
-        if (mexp) {
-          b0 += __ldg(mexp + i0 * 64 + j);
-          b1 += __ldg(mexp + i1 * 64 + j);
-        }
-        s[nt][e] += b0;
-        s[nt][2 + e] += b1;
-      }
-    }
-    // ---- softmax over 64 keys (each row lives in the 4 lanes of a quad)
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
-    const float mm0 = m0 * LOG2E, mm1 = m1 * LOG2E;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] * LOG2E - mm0);
-      s[nt][1] = exp2f(s[nt][1] * LOG2E - mm0);
-      s[nt][2] = exp2f(s[nt][2] * LOG2E - mm1);
-      s[nt][3] = exp2f(s[nt][3] * LOG2E - mm1);
-      sum0 += s[nt][0] + s[nt][1];
-      sum1 += s[nt][2] + s[nt][3];
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-    // ---- O = P V
-    float o[NO][4];
-#pragma unroll
-    for (int n = 0; n < NO; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-      for (int n = 0; n < NO; n += 2) {
-        // transposed 8x8 loads of V[key][hd]: (keys lo, n), (keys hi, n), (keys lo, n+1), (keys hi, n+1)
-        uint32_t vb[4];
-        ldsm_x4_t(vb, smem_u32(v_h + (kk * 16 + (lane & 15)) * LDS + (n + (lane >> 4)) * 8));
-        mma_16816(o[n], pa, vb[0], vb[1]);
-        mma_16816(o[n + 1], pa, vb[2], vb[3]);
-      }
-    }
-    // ---- normalise and park O in this tile's own Q rows (already consumed into registers)
-    __syncwarp();
-    __half* o_h = sQ + h * 64 * LDS;
-#pragma unroll
-    for (int n = 0; n < NO; ++n) {
-      const int c = n * 8 + 2 * tq;
-      if (c < HD) {
-        *reinterpret_cast<uint32_t*>(o_h + i0 * LDS + c) = pack_half2(o[n][0] * inv0, o[n][1] * inv0);
-        *reinterpret_cast<uint32_t*>(o_h + i1 * LDS + c) = pack_half2(o[n][2] * inv1, o[n][3] * inv1);
-      }
+    if (p.mask_mode == 2) {
+      const float* mexp = p.mask + static_cast<long long>(win % p.mask_nw) * 4096;
+      attn_tiles<HD, MT, 2>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, mexp);
+    } else if (mrow || mcol) {
+      attn_tiles<HD, MT, 1>(q_h, k_h, v_h, o_h, mbase, lane, tb, mrow, mcol, nullptr);
+    } else {
+      attn_tiles<HD, MT, 0>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, nullptr);
     }
   }
   __syncthreads();
-  // ---- scatter O rows back (16-byte coalesced stores; heads are concatenated in order, :135)
-  for (int i = tid; i < 64 * CHUNKS; i += 256) {
-    const int t = i / CHUNKS, ch = i % CHUNKS;
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = ch * 8 + j * 2;
-      const int hh = e / HD, c = e % HD;
-      w[j] = *reinterpret_cast<const uint32_t*>(sQ + (hh * 64 + t) * LDS + c);
-    }
-    *reinterpret_cast<uint4*>(p.out + sRow[t] * p.ldo + hg * SEG + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  // ---- scatter O rows back (heads are concatenated in order, :135)
+  for (int i = tid; i < 64 * VPS; i += 256) {
+    const int t = i / VPS, vv = i - t * VPS;
+    const int h = vv / VPH, v = vv - h * VPH;
+    const __half* src = sQ + (h * 64 + t) * LDS + v * VEC;
+    __half* dst = p.out + sRow[t] * p.ldo + hg * SEG + vv * VEC;
+    if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
   }
 }
 
@@ -265,6 +298,7 @@ int attn_core_launch(const AttnCoreArgs& a, cudaStream_t stream) {
   if (a.ld % 8 || a.ldo % 8 || (reinterpret_cast<uintptr_t>(a.qkv) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15))
     return fail(SUNET_E_ALIGN, "attn: qkv/out need 16-byte aligned rows");
   if (a.mask_mode == 2 && (a.mask == nullptr || a.mask_nw <= 0)) return fail(SUNET_E_ARG, "attn: explicit mask missing");
+  if (a.mask_mode == 1 && a.shift != 4) return fail(SUNET_E_ARG, "attn: the closed-form mask is built for shift 4 (window 8)");
   const int hd = a.C / a.heads;
   const int64_t windows = a.windowed_input ? a.num_windows : static_cast<int64_t>(a.B) * (a.H / 8) * (a.W / 8);
   if (windows <= 0 || windows > 0x7fffffff) return fail(SUNET_E_SHAPE, "attn: bad window count");
