@@ -74,7 +74,7 @@ int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int
                   size_t workspace_bytes, void* stream);
 /* Same forward with every kernel launch bracketed by CUDA events on `stream` (synchronises before returning).
  * recs[i] = {kind, device ms, algorithmic FLOPs, algorithmic bytes} in launch order; kind: 0 tcgen05 GEMM, 1 attention core,
- * 2 LayerNorm, 3 merge-gather+LN, 4 patch-embed conv, 5 up-sample combine, 6 tail stencil, 7 cast, 8 im2col. */
+ * 2 LayerNorm, 3 merge-gather+LN, 4 patch-embed conv, 5 up-sample combine, 6 tail stencil, 7 cast, 8 im2col, 9 fused LN+MLP+residual. */
 typedef struct sunet_prof_rec { int kind; float ms; double flops; double bytes; } sunet_prof_rec;
 int sunet_forward_profile(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
                           size_t workspace_bytes, void* stream, sunet_prof_rec* recs, int max_recs, int* n_recs);
@@ -96,6 +96,10 @@ int sunet_tiles_finish(const float* acc, int chans, int h, int w, int kernel, in
 int sunet_selftest_umma(void* stream);
 /* C[M,N] (fp16) = A[M,K] (fp16) * W[N,K]^T (fp16) + bias; used by tests to pin the tcgen05 GEMM in isolation */
 int sunet_gemm_f16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int act, void* stream);
+/* out[rows,C] (fp16) = x + fc2(GELU(fc1(LayerNorm(x)))) on fp16 rows with fp32 device parameters (norm2 + Mlp + residual of
+ * SwinTransformerBlock.forward :262) - the fused tcgen05 kernel in isolation (C in {96, 192}); packs, runs, frees. */
+int sunet_ln_mlp_residual_f16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, const float* w1,
+                              const float* b1, const float* w2, const float* b2, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ class ProfRec(ctypes.Structure):
 
 
 KERNEL_KINDS = ("gemm_tcgen05", "attn_core", "layernorm", "merge_gather_ln", "patch_embed_conv", "upsample_combine", "tail_stencil",
-                "cast", "im2col")
+                "cast", "im2col", "mlp_fused")
 
 _SIGNATURES = {
     "sunet_abi_version": (ctypes.c_int, []),
@@ -51,6 +51,7 @@ _SIGNATURES = {
     "sunet_tiles_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "sunet_selftest_umma": (ctypes.c_int, [ctypes.c_void_p]),
+    "sunet_ln_mlp_residual_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 8),
     "sunet_gemm_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }

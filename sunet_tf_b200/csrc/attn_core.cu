@@ -4,17 +4,24 @@
 // The cyclic shift (torch.roll, :238/:255) and window_partition / window_reverse (:27-56) are never
 // materialised: q/k/v rows are gathered from the image-order token tensor with
 //     src = ((wr*8 + r + shift) mod H, (wc*8 + c + shift) mod W)
-// and O is scattered back through the same map.  q arrives pre-multiplied by qk_scale (folded into the
-// qkv weights at pre-pack).
+// and O is scattered back through the same map.
 //
-// Round-1 implementation: register-resident flash-style core on mma.sync.m16n8k16 (fp16 in, fp32 accum);
-// the linear layers around it (>= 90% of the block FLOPs) run on tcgen05 (gemm_tcgen05.cu).
-// CTA = one window x HPC heads, 8 warps; a warp owns (head, 16-row query tiles).
+// q arrives pre-multiplied by qk_scale * log2(e) (folded into the qkv weights at pre-pack), the bias table and the mask
+// are multiplied by log2(e) when they are staged, so the softmax is a bare exp2.
+//
+// Persistent kernel: a CTA walks (window, head-group) units.  The q/k/v rows of the NEXT unit are gathered with
+// cp.async (8- or 16-byte, head-wise re-pack into zero/one-padded rows) into the second smem stage while the warps
+// run the register-resident flash-style core (mma.sync.m16n8k16, fp16 in, fp32 accumulate) on the current one.
+// The linear layers around it (>= 90% of the block FLOPs) run on tcgen05 (gemm_tcgen05.cu, mlp_fused.cu).
 #include "attn_core.cuh"
 #include "error.h"
 #include "ptx.cuh"
 
 namespace sunet {
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -33,9 +40,24 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One 16-row query tile of one head.  MI (tile index within this warp) is a template parameter so that the
 // relative-position bias - held in registers as tb[e][k], k = 2*MI + row_half - key_row + 7 - is indexed at compile time.
+// With a padded head (HD < HD_PAD) column HD of V holds 1.0, so O[:, HD] is the softmax denominator summed by the MMA
+// over exactly the fp16-rounded probabilities that multiply V.
 template <int HD, int MT, int MI, int MASK>
 __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, const __half* v_h, __half* o_h, int mt, int lane,
                                           const float (&tb)[2][2 * MT + 7], bool mrow, bool mcol, const float* mexp) {
@@ -43,7 +65,7 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
   constexpr int LDS = HD_PAD + 8;
   constexpr int KS = HD_PAD / 16;
   constexpr int NO = HD_PAD / 8;
-  constexpr float LOG2E = 1.4426950408889634f;
+  constexpr bool MMA_SUM = HD_PAD != HD;
   const int g = lane >> 2, tq = lane & 3;
   uint32_t qa[KS][4];
 #pragma unroll
@@ -54,14 +76,15 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
   float s[8][4];
   if (MASK == 1) {
     // closed-form SW-MSA mask (SUNet_detail.py:202-221, shift = 4): -100 where the wrapped halves differ, applied once
+    constexpr float NEG = -100.f * LOG2E;
     const bool r0hi = (2 * mt) >= 4, r1hi = (2 * mt + 1) >= 4;
     float cm[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) cm[e] = (mcol && ((g >= 4) != ((2 * tq + e) >= 4))) ? -100.f : 0.f;
+    for (int e = 0; e < 2; ++e) cm[e] = (mcol && ((g >= 4) != ((2 * tq + e) >= 4))) ? NEG : 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float rm0 = (mrow && (r0hi != (nt >= 4))) ? -100.f : 0.f;
-      const float rm1 = (mrow && (r1hi != (nt >= 4))) ? -100.f : 0.f;
+      const float rm0 = (mrow && (r0hi != (nt >= 4))) ? NEG : 0.f;
+      const float rm1 = (mrow && (r1hi != (nt >= 4))) ? NEG : 0.f;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         s[nt][e] = tb[e][2 * MI + 0 - nt + 7] + fminf(rm0, cm[e]);
@@ -83,8 +106,8 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = nt * 8 + 2 * tq + e;
-          s[nt][e] += __ldg(mexp + i0 * 64 + j);
-          s[nt][2 + e] += __ldg(mexp + (i0 + 8) * 64 + j);
+          s[nt][e] = fmaf(__ldg(mexp + i0 * 64 + j), LOG2E, s[nt][e]);
+          s[nt][2 + e] = fmaf(__ldg(mexp + (i0 + 8) * 64 + j), LOG2E, s[nt][2 + e]);
         }
     }
   }
@@ -99,7 +122,7 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
       mma_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
     }
   }
-  // ---- softmax over 64 keys (each row lives in the 4 lanes of a quad)
+  // ---- softmax over 64 keys (each row lives in the 4 lanes of a quad); logits are already in the exp2 domain
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
@@ -111,21 +134,17 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float sum0 = 0.f, sum1 = 0.f;
-  const float mm0 = m0 * LOG2E, mm1 = m1 * LOG2E;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = exp2f(fmaf(s[nt][0], LOG2E, -mm0));
-    s[nt][1] = exp2f(fmaf(s[nt][1], LOG2E, -mm0));
-    s[nt][2] = exp2f(fmaf(s[nt][2], LOG2E, -mm1));
-    s[nt][3] = exp2f(fmaf(s[nt][3], LOG2E, -mm1));
-    sum0 += s[nt][0] + s[nt][1];
-    sum1 += s[nt][2] + s[nt][3];
+    s[nt][0] = ex2(s[nt][0] - m0);
+    s[nt][1] = ex2(s[nt][1] - m0);
+    s[nt][2] = ex2(s[nt][2] - m1);
+    s[nt][3] = ex2(s[nt][3] - m1);
+    if constexpr (!MMA_SUM) {
+      sum0 += s[nt][0] + s[nt][1];
+      sum1 += s[nt][2] + s[nt][3];
+    }
   }
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-  const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
   // ---- O = P V
   float o[NO][4];
 #pragma unroll
@@ -146,6 +165,23 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
       mma_16816(o[n + 1], pa, vb[2], vb[3]);
     }
   }
+  float inv0, inv1;
+  if constexpr (MMA_SUM) {
+    // column HD sits in n-tile HD/8 at in-tile column HD%8: held by the quad lane tq == (HD%8)/2, element (HD%8)&1
+    constexpr int NS = HD / 8, CS = HD % 8;
+    const float c0 = (CS & 1) ? o[NS][1] : o[NS][0];
+    const float c1 = (CS & 1) ? o[NS][3] : o[NS][2];
+    const int src = (lane & ~3) | (CS >> 1);
+    sum0 = __shfl_sync(0xffffffffu, c0, src);
+    sum1 = __shfl_sync(0xffffffffu, c1, src);
+  } else {
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  }
+  inv0 = __frcp_rn(sum0);
+  inv1 = __frcp_rn(sum1);
   // ---- normalise and park O in this tile's own Q rows (already consumed into registers)
   __syncwarp();
   const int i0 = mt * 16 + g, i1 = i0 + 8;
@@ -170,126 +206,183 @@ __device__ __forceinline__ void attn_tiles(const __half* q_h, const __half* k_h,
   }
 }
 
-template <int HD, int HPC>
-__global__ void __launch_bounds__(256) attn_core_kernel(const AttnCoreArgs p) {
-  constexpr int HD_PAD = (HD + 15) / 16 * 16;
-  constexpr int LDS = HD_PAD + 8;           // fp16 elements per smem row (pad breaks ldmatrix bank conflicts)
-  constexpr int WPH = 8 / HPC;              // warps per head
-  constexpr int MT = 4 / WPH;               // 16-row query tiles per warp
-  constexpr int SEG = HPC * HD;             // contiguous fp16 per token per q/k/v segment handled by this CTA
-  constexpr int VEC = (HD % 8 == 0) ? 8 : 4;  // elements per global/shared vector (16 or 8 bytes); never straddles a head
-  constexpr int VPH = HD / VEC;             // vectors per head
-  constexpr int VPS = SEG / VEC;            // vectors per segment
+template <int HD, int HPC, int NWARPS>
+struct CoreCfg {
+  static constexpr int HD_PAD = (HD + 15) / 16 * 16;
+  static constexpr int LDS = HD_PAD + 8;            // fp16 elements per smem row (pad breaks ldmatrix bank conflicts)
+  static constexpr int NT = NWARPS * 32;
+  static constexpr int WPH = NWARPS / HPC;          // warps per head
+  static constexpr int MT = 4 / WPH;                // 16-row query tiles per warp
+  static constexpr int SEG = HPC * HD;              // contiguous fp16 per token per q/k/v segment handled by one unit
+  static constexpr int VEC = (HD % 8 == 0) ? 8 : 4; // elements per copy (16 or 8 bytes); never straddles a head
+  static constexpr int VPH = HD / VEC;              // vectors per head
+  static constexpr int VPS = SEG / VEC;             // vectors per segment
+  static constexpr int NVEC = 64 * 3 * VPS;         // gather copies per unit
+  static constexpr int SLOTS = (NVEC + NT - 1) / NT;
+  static constexpr int OVEC = 64 * VPS;             // scatter vectors per unit
+  static constexpr int OSLOTS = (OVEC + NT - 1) / NT;
+  static constexpr int MAT = HPC * 64 * LDS;        // fp16 elements of one of q / k / v in a stage
+  static constexpr int STAGE_BYTES = 3 * MAT * 2;
+  static constexpr int TBL = 232;                   // 225 padded
+  static constexpr int SMEM = 2 * STAGE_BYTES + 8 * TBL * 4;   // table for up to... see launch (heads <= 8 staged per group)
+  static_assert(WPH >= 1 && WPH <= 4 && WPH * HPC == NWARPS && MT * WPH == 4, "warp / head split");
   static_assert(HD % VEC == 0, "head_dim must be a multiple of 4");
-  constexpr int TBL = 232;                  // 225 padded
+};
 
+template <int HD, int HPC, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCoreArgs p, const int64_t units) {
+  using K = CoreCfg<HD, HPC, NWARPS>;
+  constexpr int LDS = K::LDS, NT = K::NT, MT = K::MT, VEC = K::VEC, VPH = K::VPH, VPS = K::VPS, TBL = K::TBL;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __half* sQ = reinterpret_cast<__half*>(smem_raw);            // [HPC][64][LDS]
-  __half* sK = sQ + HPC * 64 * LDS;
-  __half* sV = sK + HPC * 64 * LDS;
-  float* sTbl = reinterpret_cast<float*>(sV + HPC * 64 * LDS);  // [HPC][TBL]
-  __shared__ long long sRow[64];
+  __half* stage0 = reinterpret_cast<__half*>(smem_raw);
+  float* sTbl = reinterpret_cast<float*>(smem_raw + 2 * K::STAGE_BYTES);   // [heads <= 8][TBL], already times log2(e)
+  __shared__ long long sRow[3][64];   // row map of the previous / current / next unit
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int win = blockIdx.x;
-  const int hg = blockIdx.y;
   const int nWc = p.W >> 3, nWr = p.H >> 3;
   const int nW = nWr * nWc;
-  const int wimg = win % nW;
-  const int wr = wimg / nWc, wc = wimg % nWc;
+  const int groups = p.heads / HPC;          // head groups per window
 
-  if (tid < 64) {
-    long long row;
-    if (p.windowed_input) {
-      row = static_cast<long long>(win) * 64 + tid;
-    } else {
-      const int b = win / nW;
-      const int r = (wr * 8 + (tid >> 3) + p.shift) % p.H;
-      const int c = (wc * 8 + (tid & 7) + p.shift) % p.W;
-      row = (static_cast<long long>(b) * p.H + r) * p.W + c;
-    }
-    sRow[tid] = row;
+  // ---- one-time setup: bias table of every head, pad columns of both stages (cp.async never touches them)
+  for (int i = tid; i < p.heads * 225; i += NT) {
+    const int e = i / p.heads, h = i - e * p.heads;
+    sTbl[h * TBL + e] = __ldg(p.bias_table + i) * LOG2E;
   }
-  // bias table slice for this CTA's heads: table is [225][heads]
-  for (int i = tid; i < HPC * 225; i += 256) {
-    const int h = i / 225, e = i % 225;
-    sTbl[h * TBL + e] = __ldg(p.bias_table + e * p.heads + hg * HPC + h);
-  }
-  // zero the K-padding columns once
-  if constexpr (HD_PAD != HD) {
-    constexpr int PADW = (HD_PAD - HD) / 2;  // half2 words per row
-    for (int i = tid; i < 3 * HPC * 64 * PADW; i += 256) {
-      const int row = i / PADW, w = i % PADW;
-      reinterpret_cast<uint32_t*>(sQ + row * LDS + HD)[w] = 0u;
+  if constexpr (K::HD_PAD != HD) {
+    constexpr int PADW = (K::HD_PAD - HD) / 2;  // half2 words per row
+    for (int i = tid; i < 2 * 3 * HPC * 64 * PADW; i += NT) {
+      const int row = i / PADW, w = i - row * PADW;     // row over [stage][q|k|v][head][token]
+      const bool is_v = (row / (HPC * 64)) % 3 == 2;
+      // V: column HD := 1.0 (softmax denominator through the MMA); everything else 0
+      reinterpret_cast<uint32_t*>(stage0 + static_cast<size_t>(row) * LDS + HD)[w] = (is_v && w == 0) ? 0x00003C00u : 0u;
     }
   }
-  __syncthreads();
-
-  // ---- gather q/k/v rows head-wise: one vector never straddles a head, consecutive threads read consecutive vectors
-  for (int i = tid; i < 64 * 3 * VPS; i += 256) {
+  // ---- per-thread copy slots (window independent)
+  int g_t[K::SLOTS], g_src[K::SLOTS], g_dst[K::SLOTS];
+#pragma unroll
+  for (int s = 0; s < K::SLOTS; ++s) {
+    const int i = tid + s * NT;
     const int t = i / (3 * VPS);
     const int rem = i - t * (3 * VPS);
     const int seg = rem / VPS, vv = rem - seg * VPS;
     const int h = vv / VPH, v = vv - h * VPH;
-    const __half* src = p.qkv + sRow[t] * p.ld + seg * p.C + hg * SEG + vv * VEC;
-    __half* dst = (seg == 0 ? sQ : (seg == 1 ? sK : sV)) + (h * 64 + t) * LDS + v * VEC;
-    if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
-    else *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(src));
+    g_t[s] = i < K::NVEC ? t : -1;
+    g_src[s] = seg * p.C + vv * VEC;
+    g_dst[s] = (seg * K::MAT + (h * 64 + t) * LDS + v * VEC) * 2;   // bytes within a stage
   }
-  __syncthreads();
 
-  {
-    const int h = warp % HPC;
-    const int mbase = (warp / HPC) * MT;
-    const __half* q_h = sQ + h * 64 * LDS;
-    const __half* k_h = sK + h * 64 * LDS;
-    const __half* v_h = sV + h * 64 * LDS;
-    __half* o_h = sQ + h * 64 * LDS;
-    const int g = lane >> 2, tq = lane & 3;
-    // this thread's slice of the relative-position bias: tb[e][k] = table[(k + 2*mbase) * 15 + (g - (2*tq+e) + 7)]
-    float tb[2][2 * MT + 7];
+  auto unit_rows = [&](int64_t u, int st) {   // 64 threads: global row of each window token (st: row-map buffer)
+    if (tid < 64) {
+      const int64_t win = u / groups;
+      long long row;
+      if (p.windowed_input) {
+        row = win * 64 + tid;
+      } else {
+        const int wimg = static_cast<int>(win % nW);
+        const int64_t b = win / nW;
+        const int wr = wimg / nWc, wc = wimg - wr * nWc;
+        const int r = (wr * 8 + (tid >> 3) + p.shift) % p.H;
+        const int c = (wc * 8 + (tid & 7) + p.shift) % p.W;
+        row = (b * p.H + r) * p.W + c;
+      }
+      sRow[st][tid] = row;
+    }
+  };
+  auto unit_gather = [&](int64_t u, int st, int rb) {
+    const int hg = static_cast<int>(u % groups);
+    const __half* base = p.qkv + hg * K::SEG;
+    const uint32_t sbase = smem_u32(stage0) + st * K::STAGE_BYTES;
 #pragma unroll
-    for (int e = 0; e < 2; ++e)
+    for (int s = 0; s < K::SLOTS; ++s)
+      if (g_t[s] >= 0) cp_async<VEC * 2>(sbase + g_dst[s], base + sRow[rb][g_t[s]] * p.ld + g_src[s]);
+    cp_async_commit();
+  };
+
+  int64_t u = blockIdx.x;
+  if (u < units) unit_rows(u, 0);
+  __syncthreads();
+  if (u < units) unit_gather(u, 0, 0);
+  int st = 0, rb = 0;                      // smem stage / row-map buffer of the current unit
+  for (; u < units; u += gridDim.x, st ^= 1, rb = (rb == 2 ? 0 : rb + 1)) {
+    const int64_t un = u + gridDim.x;
+    const int rbn = rb == 2 ? 0 : rb + 1;  // last read two units ago (its scatter), before the previous sync (A)
+    if (un < units) unit_rows(un, rbn);
+    __syncthreads();                       // (A) next unit's row map visible; every warp is done with stage st^1
+    if (un < units) unit_gather(un, st ^ 1, rbn);
+    else cp_async_commit();
+    cp_async_wait<1>();                    // this thread's copies of the current unit have landed
+    __syncthreads();                       // (B) ... and everybody else's
+    __half* sQ = stage0 + static_cast<size_t>(st) * (K::STAGE_BYTES / 2);
+    __half* sK = sQ + K::MAT;
+    __half* sV = sK + K::MAT;
+    const int64_t win = u / groups;
+    const int hg = static_cast<int>(u % groups);
+    {
+      const int h = warp % HPC;
+      const int mbase = (warp / HPC) * MT;
+      const __half* q_h = sQ + h * 64 * LDS;
+      const __half* k_h = sK + h * 64 * LDS;
+      const __half* v_h = sV + h * 64 * LDS;
+      __half* o_h = sQ + h * 64 * LDS;
+      const int g = lane >> 2, tq = lane & 3;
+      // this thread's slice of the relative-position bias: tb[e][k] = table[(k + 2*mbase) * 15 + (g - (2*tq+e) + 7)]
+      const float* tbl = sTbl + (hg * HPC + h) * TBL;
+      float tb[2][2 * MT + 7];
 #pragma unroll
-      for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = sTbl[h * TBL + (k + 2 * mbase) * 15 + (g - 2 * tq - e + 7)];
-    const bool mrow = p.mask_mode == 1 && wr == nWr - 1;
-    const bool mcol = p.mask_mode == 1 && wc == nWc - 1;
-    if (p.mask_mode == 2) {
-      const float* mexp = p.mask + static_cast<long long>(win % p.mask_nw) * 4096;
-      attn_tiles<HD, MT, 2>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, mexp);
-    } else if (mrow || mcol) {
-      attn_tiles<HD, MT, 1>(q_h, k_h, v_h, o_h, mbase, lane, tb, mrow, mcol, nullptr);
-    } else {
-      attn_tiles<HD, MT, 0>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, nullptr);
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (g - 2 * tq - e + 7)];
+      if (p.mask_mode == 2) {
+        const float* mexp = p.mask + (win % p.mask_nw) * 4096;
+        attn_tiles<HD, MT, 2>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, mexp);
+      } else {
+        const int wimg = static_cast<int>(win % nW);
+        const int wr = wimg / nWc, wc = wimg - wr * nWc;
+        const bool mrow = p.mask_mode == 1 && wr == nWr - 1;
+        const bool mcol = p.mask_mode == 1 && wc == nWc - 1;
+        if (mrow || mcol) attn_tiles<HD, MT, 1>(q_h, k_h, v_h, o_h, mbase, lane, tb, mrow, mcol, nullptr);
+        else attn_tiles<HD, MT, 0>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, nullptr);
+      }
+    }
+    __syncthreads();                       // (C) O rows of every head parked in sQ
+    // ---- scatter O rows back (heads are concatenated in order, :135)
+#pragma unroll
+    for (int s = 0; s < K::OSLOTS; ++s) {
+      const int i = tid + s * NT;
+      if (i < K::OVEC) {
+        const int t = i / VPS, vv = i - t * VPS;
+        const int h = vv / VPH, v = vv - h * VPH;
+        const __half* src = sQ + (h * 64 + t) * LDS + v * VEC;
+        __half* dst = p.out + sRow[rb][t] * p.ldo + hg * K::SEG + vv * VEC;
+        if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+      }
     }
   }
-  __syncthreads();
-  // ---- scatter O rows back (heads are concatenated in order, :135)
-  for (int i = tid; i < 64 * VPS; i += 256) {
-    const int t = i / VPS, vv = i - t * VPS;
-    const int h = vv / VPH, v = vv - h * VPH;
-    const __half* src = sQ + (h * 64 + t) * LDS + v * VEC;
-    __half* dst = p.out + sRow[t] * p.ldo + hg * SEG + vv * VEC;
-    if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-    else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
-  }
+  cp_async_wait<0>();
 }
 
-template <int HD, int HPC>
-static int launch_core(const AttnCoreArgs& a, int64_t windows, cudaStream_t stream) {
-  constexpr int HD_PAD = (HD + 15) / 16 * 16;
-  constexpr int LDS = HD_PAD + 8;
-  const int smem = 3 * HPC * 64 * LDS * 2 + HPC * 232 * 4;
+template <int HD, int HPC, int NWARPS>
+int launch_core(const AttnCoreArgs& a, int64_t windows, cudaStream_t stream) {
+  using K = CoreCfg<HD, HPC, NWARPS>;
+  if (a.heads > 8) return fail(SUNET_E_SHAPE, "attn: at most 8 heads are staged (got %d)", a.heads);
   static bool configured = false;
+  static int sms = 148;
   if (!configured) {
-    SUNET_CUDA(cudaFuncSetAttribute(attn_core_kernel<HD, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SUNET_CUDA(cudaFuncSetAttribute(attn_core_kernel<HD, HPC, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     configured = true;
   }
-  dim3 grid(static_cast<unsigned>(windows), a.heads / HPC);
-  attn_core_kernel<HD, HPC><<<grid, 256, smem, stream>>>(a);
+  const int64_t units = windows * (a.heads / HPC);
+  const unsigned grid = static_cast<unsigned>(units < sms ? units : sms);
+  attn_core_kernel<HD, HPC, NWARPS><<<grid, K::NT, K::SMEM, stream>>>(a, units);
   SUNET_CHECK_LAUNCH();
   return 0;
 }
+
+}  // namespace
 
 int attn_core_launch(const AttnCoreArgs& a, cudaStream_t stream) {
   if (a.C % a.heads != 0) return fail(SUNET_E_SHAPE, "attn: C=%d not divisible by heads=%d", a.C, a.heads);
@@ -304,12 +397,12 @@ int attn_core_launch(const AttnCoreArgs& a, cudaStream_t stream) {
   if (windows <= 0 || windows > 0x7fffffff) return fail(SUNET_E_SHAPE, "attn: bad window count");
   const bool h8 = a.heads % 8 == 0;
   switch (hd) {
-    case 12: return h8 ? launch_core<12, 8>(a, windows, stream) : launch_core<12, 4>(a, windows, stream);
-    case 24: return h8 ? launch_core<24, 8>(a, windows, stream) : launch_core<24, 4>(a, windows, stream);
-    case 48: return h8 ? launch_core<48, 8>(a, windows, stream) : launch_core<48, 4>(a, windows, stream);
-    case 96: return launch_core<96, 4>(a, windows, stream);
-    case 16: return h8 ? launch_core<16, 8>(a, windows, stream) : launch_core<16, 4>(a, windows, stream);
-    case 32: return h8 ? launch_core<32, 8>(a, windows, stream) : launch_core<32, 4>(a, windows, stream);
+    case 12: return h8 ? launch_core<12, 8, 16>(a, windows, stream) : launch_core<12, 4, 16>(a, windows, stream);
+    case 16: return h8 ? launch_core<16, 8, 16>(a, windows, stream) : launch_core<16, 4, 16>(a, windows, stream);
+    case 24: return launch_core<24, 4, 16>(a, windows, stream);
+    case 32: return launch_core<32, 4, 16>(a, windows, stream);
+    case 48: return launch_core<48, 4, 16>(a, windows, stream);
+    case 96: return launch_core<96, 2, 8>(a, windows, stream);
     default: return fail(SUNET_E_SHAPE, "attn: head_dim %d not instantiated (12/16/24/32/48/96)", hd);
   }
 }

@@ -7,6 +7,7 @@
 // One CTA per SM loops over 128 x block_n output tiles (tile = blockIdx.x + i * gridDim.x, n fastest so that
 // co-running CTAs share A rows in L2).  While the epilogue drains accumulator stage s, the MMA warp fills stage s^1
 // and the producer prefetches the operands of the tiles after that.
+#include "act.cuh"
 #include "error.h"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -20,36 +21,6 @@ static constexpr int MAX_STAGES = 12;
 static constexpr int EPI_WARPS = 16;
 static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 static constexpr int GEMM_MAX_DYN_SMEM = 226 * 1024;  // 227 KB per CTA minus the static barriers
-
-// GELU(x) = x * Phi(x), Phi(x) = 0.5 * (1 + erf(x / sqrt 2)) (nn.GELU default, SUNet_detail.py:9).
-// Phi is evaluated as 0.5 + 0.5 * tanh(u * (c0 + c1 u^2 + c2 u^4)), u = clamp(x, +-7): a minimax fit of atanh(erf(x/sqrt2))
-// with max |dPhi| = 5.0e-5 (fit) + 2.4e-4 (tanh.approx.f32, 2^-11 relative); ~9 instructions instead of ~40 for erff().
-// The hidden activation is stored in fp16 (2^-11 relative) anyway; measured effect on the SUNet output < 1e-4.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float u = fminf(fmaxf(x, -7.0f), 7.0f);
-  const float t = u * u;
-  float p = fmaf(t, -3.5151847398e-04f, 3.7005657172e-02f);
-  p = fmaf(t, p, 7.9750787105e-01f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
-  const float h = 0.5f * x;
-  return fmaf(h, th, h);
-}
-
-// Packed-half2 variant for the fc1 epilogue (the result is stored as fp16 anyway): 5 instructions per element.
-// t = min(u^2, 49) keeps the odd polynomial monotone for any |x| (tanh saturates to +-1 long before).
-__device__ __forceinline__ uint32_t gelu_fast_h2(uint32_t xbits) {
-  const __half2 x = *reinterpret_cast<const __half2*>(&xbits);
-  const __half2 t = __hmin2(__hmul2(x, x), __float2half2_rn(49.0f));
-  __half2 p = __hfma2(t, __float2half2_rn(-3.5151847398e-04f), __float2half2_rn(3.7005657172e-02f));
-  p = __hfma2(t, p, __float2half2_rn(7.9750787105e-01f));
-  const __half2 z = __hmul2(x, p);
-  uint32_t th;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(*reinterpret_cast<const uint32_t*>(&z)));
-  const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
-  const __half2 g = __hfma2(h, *reinterpret_cast<const __half2*>(&th), h);
-  return *reinterpret_cast<const uint32_t*>(&g);
-}
 
 // Per-warp staging tile: 32 rows x 128 bytes, 16-byte chunk j of row r lives at chunk slot (j ^ (r & 7)).
 // Row-wise accesses (thread = row) and coalesced accesses (consecutive lanes = consecutive chunks of a row) are both

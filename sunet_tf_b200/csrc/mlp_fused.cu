@@ -1,0 +1,431 @@
+// Fused LayerNorm -> fc1 -> GELU -> fc2 -> +residual for one Swin block (SUNet_detail.py:262 with Mlp :18-24).
+//
+// One persistent CTA per SM walks 128-token tiles.  Per tile the 4C-wide hidden activation is produced and consumed in
+// 128-column chunks and never leaves the SM:
+//
+//   TMA  : x tile [128][C] fp16 (raw residual stream)  -> smem (SW128)         \  warp 0 (one lane)
+//          fc1 / fc2 weight k-blocks                   -> two smem rings       /
+//   MMA1 : H_j  = x * W1g_j^T          (tcgen05, fp32 in TMEM, N = 128)        \  warp 1 (one lane)
+//   MMA2 : Y   += G_j * W2_j^T         (tcgen05, fp32 in TMEM, N = C)          /
+//   GELU : G_j  = gelu(rstd * H_j - rstd * mu * s + b1f)  TMEM -> regs -> fp16 SW128 smem (A operand of MMA2)   \ warps 2..17
+//   OUT  : y    = Y + b2 + x           TMEM -> regs -> global                                                   /
+//
+// LayerNorm fold (exact algebra):  fc1(LN(x))_n = rstd * (sum_k (W1[n,k] g[k]) x_k  -  mu * s_n) + (b1_n + sum_k W1[n,k] beta[k])
+// with s_n = sum_k fp16(W1[n,k] g[k]) summed over the SAME rounded weights the MMA multiplies, so the only difference to
+// "normalise, round to fp16, multiply" is that the activations are not rounded a second time.  mu / rstd per token are
+// computed by the epilogue warps from the smem tile (fp32, shifted one-pass variance), which also keeps the residual in
+// registers so the tile buffer can be refilled as soon as the last fc1 MMA of the tile has read it.
+#include "mlp_fused.cuh"
+
+#include "act.cuh"
+#include "error.h"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace sunet {
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NC = 128;                 // hidden columns per chunk
+constexpr int KBYTES = TILE_M * 128;    // one [128 rows][64 fp16] SW128 k-block
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+
+template <int C>
+struct Cfg {
+  static constexpr int HID = 4 * C;
+  static constexpr int NCH = HID / NC;                     // hidden chunks per tile
+  static constexpr int KB1 = (C + 63) / 64;                // k-blocks of fc1 (K = C)
+  static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;  // k-steps in the last fc1 k-block
+  static constexpr int NXBUF = C <= 96 ? 2 : 1;            // token-tile buffers
+  static constexpr int NYBUF = C <= 128 ? 2 : 1;           // fc2 accumulators in TMEM
+  static constexpr int R1 = 3;                             // fc1 weight ring: [128 rows][64] k-blocks
+  static constexpr int R2 = C <= 96 ? 3 : 2;               // fc2 weight ring: [C rows][64] k-blocks
+  static constexpr int R2BYTES = C * 128;
+  static constexpr int QC = C / 4;                         // output columns per epilogue column-quarter
+  static constexpr int QCH = C / 32;                       // 16-byte chunks (8 fp16) per quarter
+  // shared memory map (offsets from the 1024-aligned base)
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_HS = OFF_X + NXBUF * KB1 * KBYTES;
+  static constexpr int OFF_R1 = OFF_HS + 2 * 2 * KBYTES;
+  static constexpr int OFF_R2 = OFF_R1 + R1 * KBYTES;
+  static constexpr int OFF_HC = OFF_R2 + R2 * R2BYTES;     // float2 [HID]
+  static constexpr int OFF_B2 = OFF_HC + HID * 8;          // float [C]
+  static constexpr int OFF_ST = OFF_B2 + C * 4;            // float2 [2][4][128]
+  static constexpr int SMEM = OFF_ST + 2 * 4 * 128 * 8 + 1024;
+  static constexpr uint32_t TM_Y = 0;                      // Y[b] at column b * 128 (NYBUF == 2) or 0
+  static constexpr uint32_t TM_H = 256;                    // H[b] at column 256 + 128 b
+  static_assert(C % 32 == 0 && C <= 256, "C must be a multiple of 32, at most 256");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct Params {
+  const float2* hconst;
+  const float* b2;
+  __half* out;
+  int64_t M;
+  int64_t tiles;
+};
+
+template <int C>
+__global__ void __launch_bounds__(THREADS, 1)
+    mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const Params p) {
+  using K = Cfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t x_full[2], x_empty[2];
+  __shared__ __align__(8) uint64_t r1_full[K::R1], r1_empty[K::R1], r2_full[K::R2], r2_empty[K::R2];
+  __shared__ __align__(8) uint64_t h_full[2], gelu_done[2], hs_empty[2], y_full[2], y_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // 1024-byte alignment for the SW128 tiles; pointer arithmetic on smem_raw keeps the shared address space visible to
+  // the compiler (LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1 + EPI_WARPS);
+      mbar_init(&h_full[i], 1);
+      mbar_init(&gelu_done[i], EPI_WARPS);
+      mbar_init(&hs_empty[i], 1);
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], EPI_WARPS);
+    }
+    for (int i = 0; i < K::R1; ++i) { mbar_init(&r1_full[i], 1); mbar_init(&r1_empty[i], 1); }
+    for (int i = 0; i < K::R2; ++i) { mbar_init(&r2_full[i], 1); mbar_init(&r2_empty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, 512);
+    tmem_relinquish();
+  }
+  {  // per-column constants of the two epilogues
+    float2* hc = reinterpret_cast<float2*>(smem + K::OFF_HC);
+    for (int i = threadIdx.x; i < K::HID; i += THREADS) hc[i] = __ldg(p.hconst + i);
+    float* b2s = reinterpret_cast<float*>(smem + K::OFF_B2);
+    for (int i = threadIdx.x; i < C; i += THREADS) b2s[i] = __ldg(p.b2 + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t i1 = 0, i2 = 0, g = 0;
+      int lt = 0;
+      auto load_x = [&](int64_t tile, int ltile) {
+        const int xb = K::NXBUF == 2 ? (ltile & 1) : 0;
+        const uint32_t use = K::NXBUF == 2 ? (ltile >> 1) : ltile;
+        mbar_wait(&x_empty[xb], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&x_full[xb], K::KB1 * KBYTES);
+        for (int kb = 0; kb < K::KB1; ++kb)
+          tma_load_2d(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES, &tmX, &x_full[xb], kb * 64, static_cast<int>(tile * TILE_M));
+      };
+      auto load_w2 = [&](uint32_t chunk) {  // chunk index within its tile
+        for (int kb = 0; kb < 2; ++kb, ++i2) {
+          const int s = i2 % K::R2;
+          mbar_wait(&r2_empty[s], ((i2 / K::R2) & 1) ^ 1);
+          mbar_arrive_expect_tx(&r2_full[s], K::R2BYTES);
+          tma_load_2d(smem + K::OFF_R2 + s * K::R2BYTES, &tmW2, &r2_full[s], static_cast<int>(chunk) * NC + kb * 64, 0);
+        }
+      };
+      if (K::NXBUF == 2 && static_cast<int64_t>(blockIdx.x) < p.tiles) load_x(blockIdx.x, 0);
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        if (K::NXBUF == 2) {
+          if (tile + gridDim.x < p.tiles) load_x(tile + gridDim.x, lt + 1);   // prefetch one tile ahead
+        } else {
+          load_x(tile, lt);
+        }
+        for (int j = 0; j < K::NCH; ++j, ++g) {
+          for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
+            const int s = i1 % K::R1;
+            mbar_wait(&r1_empty[s], ((i1 / K::R1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&r1_full[s], KBYTES);
+            tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
+          }
+          if (g > 0) load_w2(j == 0 ? K::NCH - 1 : j - 1);   // fc2 weights of the previous chunk (MMA order)
+        }
+      }
+      if (g > 0) load_w2(K::NCH - 1);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_f16(TILE_M, NC);
+      const uint32_t idesc2 = umma_idesc_f16(TILE_M, C);
+      uint32_t i1 = 0, i2 = 0, g = 0;
+      int lt = 0;
+      bool pending = false;
+      uint32_t pg = 0;    // global chunk index of the pending fc2
+      int pj = 0, plt = 0;
+      auto mma2 = [&]() {
+        const uint32_t hb = pg & 1;
+        const int yb = K::NYBUF == 2 ? (plt & 1) : 0;
+        const uint32_t yuse = K::NYBUF == 2 ? (plt >> 1) : plt;
+        mbar_wait(&gelu_done[hb], (pg >> 1) & 1);
+        if (pj == 0) mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+        for (int kb = 0; kb < 2; ++kb, ++i2) {
+          const int s = i2 % K::R2;
+          mbar_wait(&r2_full[s], (i2 / K::R2) & 1);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_HS + (hb * 2 + kb) * KBYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
+                        (pj > 0 || kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r2_empty[s]);
+        }
+        tc_commit(&hs_empty[hb]);
+        if (pj == K::NCH - 1) tc_commit(&y_full[yb]);
+      };
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+        const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
+        mbar_wait(&x_full[xb], xuse & 1);
+        tc_fence_after();
+        for (int j = 0; j < K::NCH; ++j, ++g) {
+          const uint32_t hb = g & 1;
+          // H[hb] was drained by the GELU pass of chunk g-2: mma2(g-2), issued earlier, already waited for it
+          const uint32_t d = tmem_base + K::TM_H + hb * 128;
+          for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
+            const int s = i1 % K::R1;
+            mbar_wait(&r1_full[s], (i1 / K::R1) & 1);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
+            const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r1_empty[s]);
+          }
+          tc_commit(&h_full[hb]);
+          if (j == K::NCH - 1) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read the token tile
+          if (pending) mma2();
+          pending = true; pg = g; pj = j; plt = lt;
+        }
+      }
+      if (pending) mma2();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int e = warp - 2;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may touch
+    const int quarter = e >> 2;        // column quarter
+    const int row = q * 32 + lane;     // row of the tile
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float2* hc = reinterpret_cast<const float2*>(smem + K::OFF_HC);
+    const float* b2s = reinterpret_cast<const float*>(smem + K::OFF_B2);
+    float2* stats = reinterpret_cast<float2*>(smem + K::OFF_ST);
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    uint32_t g = 0;
+    int lt = 0;
+    for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+      const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+      const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
+      // ---- row statistics + residual capture
+      mbar_wait(&x_full[xb], xuse & 1);
+      const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
+      uint4 res[K::QCH];
+      float s1 = 0.f, s2 = 0.f;
+      {
+        const uint4 first = lds128(xs + row * 128 + (sw << 4));   // chunk 0 of this row (columns 0..7)
+        const float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(first.x & 0xffffu)));
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) {
+          const int gi = quarter * K::QCH + i;
+          const int kb = gi >> 3, ch = gi & 7;
+          res[i] = lds128(xs + kb * KBYTES + row * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4));
+          const __half2* h2 = reinterpret_cast<const __half2*>(&res[i]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h2[t]);
+            const float d0 = f.x - k0, d1 = f.y - k0;
+            s1 += d0 + d1;
+            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+          }
+        }
+        float2* st = stats + (lt & 1) * 4 * 128;
+        st[quarter * 128 + row] = make_float2(s1, s2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_empty[xb]);        // this warp no longer reads the token tile
+        named_bar_sync(1, EPI_THREADS);
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 v = st[t * 128 + row];
+          s1 += v.x; s2 += v.y;
+        }
+        const float ms = s1 * (1.0f / C);
+        const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        s1 = rstd;                  // a
+        s2 = -(k0 + ms) * rstd;     // b
+      }
+      const float a = s1, b = s2;
+      // ---- GELU passes
+      for (int j = 0; j < K::NCH; ++j, ++g) {
+        const uint32_t hb = g & 1, ph = (g >> 1) & 1;
+        mbar_wait(&h_full[hb], ph);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
+        tmem_ld_wait();
+        const float4* hc4 = reinterpret_cast<const float4*>(hc + j * NC + quarter * 32);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 c2 = hc4[i];   // (s, b1f) of two consecutive hidden columns (warp-uniform address: broadcast)
+          const float h0 = fmaf(a, __uint_as_float(v[2 * i]), fmaf(b, c2.x, c2.y));
+          const float h1 = fmaf(a, __uint_as_float(v[2 * i + 1]), fmaf(b, c2.z, c2.w));
+          const __half2 x2 = __floats2half2_rn(h0, h1);
+          w[i] = gelu_fast_h2(*reinterpret_cast<const uint32_t*>(&x2));
+        }
+        mbar_wait(&hs_empty[hb], ph ^ 1);   // fc2 of chunk g-2 has consumed this buffer
+        const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(hs + (((static_cast<uint32_t>((quarter & 1) * 4 + i)) ^ sw) << 4), make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gelu_done[hb]);
+      }
+      // ---- output: Y + b2 + residual -> global
+      {
+        const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
+        const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
+        mbar_wait(&y_full[yb], yuse & 1);
+        tc_fence_after();
+        const uint32_t ty = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
+        uint32_t y[K::QC];
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) tmem_ld8(ty + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&y[i * 8]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&y_empty[yb]);
+        const int64_t m = tile * TILE_M + row;
+        if (m < p.M) {
+          __half* orow = p.out + m * C + quarter * K::QC;
+#pragma unroll
+          for (int i = 0; i < K::QCH; ++i) {
+            const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
+            const float* bb = b2s + quarter * K::QC + i * 8;
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 r = __half22float2(r2[t]);
+              o2[t] = __floats2half2_rn(__uint_as_float(y[i * 8 + 2 * t]) + bb[2 * t] + r.x,
+                                        __uint_as_float(y[i * 8 + 2 * t + 1]) + bb[2 * t + 1] + r.y);
+            }
+            *reinterpret_cast<uint4*>(orow + i * 8) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- pre-pack: W1g = fp16(W1 * gamma), s = rowsum(W1g as rounded), b1f = b1 + W1 beta; one warp per hidden unit
+__global__ void mlp_fold_ln_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, __half* __restrict__ w1g, float2* __restrict__ hconst, int HID, int C) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= HID) return;
+  float s = 0.f, bb = 0.f;
+  for (int k = lane; k < C; k += 32) {
+    const float w = w1[static_cast<size_t>(n) * C + k];
+    const __half h = __float2half_rn(w * gamma[k]);
+    w1g[static_cast<size_t>(n) * C + k] = h;
+    s += __half2float(h);
+    bb = fmaf(w, beta[k], bb);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+  }
+  if (lane == 0) hconst[n] = make_float2(s, bb + (b1 ? b1[n] : 0.f));
+}
+
+__global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
+}
+
+template <int C>
+int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
+  using K = Cfg<C>;
+  static bool configured = false;
+  if (!configured) {
+    SUNET_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    configured = true;
+  }
+  alignas(64) CUtensorMap tmX;
+  SUNET_TRY(make_tmap_2d_f16(&tmX, x, C, M, C, TILE_M));
+  Params prm;
+  prm.hconst = reinterpret_cast<const float2*>(p.hconst);
+  prm.b2 = p.b2;
+  prm.out = out;
+  prm.M = M;
+  prm.tiles = (M + TILE_M - 1) / TILE_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
+  mlp_fused_kernel<C><<<grid, THREADS, K::SMEM, stream>>>(tmX, p.tmW1, p.tmW2, prm);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+bool mlp_fused_supported(int C) { return C == 96 || C == 192; }
+
+int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* beta, const float* w1, const float* b1,
+                      const float* w2, const float* b2, cudaStream_t stream) {
+  if (!mlp_fused_supported(C)) return fail(SUNET_E_SHAPE, "fused mlp: C=%d not instantiated (96, 192)", C);
+  if (!p->w1g || !p->w2 || !p->hconst || !p->b2) return fail(SUNET_E_ARG, "fused mlp: pack buffers not allocated");
+  p->C = C;
+  const int HID = 4 * C;
+  mlp_fold_ln_kernel<<<(HID + 7) / 8, 256, 0, stream>>>(w1, b1, gamma, beta, p->w1g, reinterpret_cast<float2*>(p->hconst), HID, C);
+  SUNET_CHECK_LAUNCH();
+  cast_f16_kernel<<<148, 256, 0, stream>>>(w2, p->w2, static_cast<size_t>(C) * HID);
+  SUNET_CHECK_LAUNCH();
+  if (b2) SUNET_CUDA(cudaMemcpyAsync(p->b2, b2, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  else SUNET_CUDA(cudaMemsetAsync(p->b2, 0, C * sizeof(float), stream));
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW1, p->w1g, C, HID, C, NC));
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW2, p->w2, HID, C, HID, C));
+  return 0;
+}
+
+int mlp_fused_launch(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
+  if (M <= 0 || M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "fused mlp: bad row count %lld", (long long)M);
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "fused mlp: x/out must be 16-byte aligned");
+  switch (p.C) {
+    case 96: return launch_t<96>(p, x, out, M, stream);
+    case 192: return launch_t<192>(p, x, out, M, stream);
+    default: return fail(SUNET_E_SHAPE, "fused mlp: C=%d not instantiated", p.C);
+  }
+}
+
+}  // namespace sunet

@@ -2,6 +2,7 @@
 // of SUNet (model/SUNet_detail.py:706-755) over the kernels in gemm_tcgen05.cu / attn_core.cu / elementwise.cu.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -14,6 +15,7 @@
 #include "elementwise.cuh"
 #include "error.h"
 #include "gemm.cuh"
+#include "mlp_fused.cuh"
 
 namespace sunet {
 
@@ -65,7 +67,7 @@ struct ScratchMark {  // stack discipline
   ~ScratchMark() { s.off = saved; }
 };
 
-enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8 };
+enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8, K_MLP_FUSED = 9 };
 
 struct ProfRec {
   int kind;
@@ -165,8 +167,9 @@ struct AttnPack {  // WindowAttention parameters (SUNet_detail.py:83-105)
     dim = dim_; heads = heads_;
     if (heads <= 0 || dim % heads) return fail(SUNET_E_SHAPE, "attention: dim %d not divisible by heads %d", dim, heads);
     scale = qk_scale > 0 ? static_cast<float>(qk_scale) : 1.f / sqrtf(static_cast<float>(dim / heads));  // :80
-    // q = q * scale (:117) folded into the first `dim` rows of qkv.weight / qkv.bias
-    SUNET_TRY(pack_linear(ar, P, pre + "qkv.weight", pre + "qkv.bias", 3 * dim, dim, &qkv, s, dim, scale));
+    // q = q * scale (:117) folded into the first `dim` rows of qkv.weight / qkv.bias, together with log2(e): the
+    // attention core works in the exp2 domain (its bias table / mask are scaled the same way when staged)
+    SUNET_TRY(pack_linear(ar, P, pre + "qkv.weight", pre + "qkv.bias", 3 * dim, dim, &qkv, s, dim, scale * 1.4426950408889634f));
     SUNET_TRY(pack_linear(ar, P, pre + "proj.weight", pre + "proj.bias", dim, dim, &proj, s));
     SUNET_TRY(copy_vec(ar, P, pre + "relative_position_bias_table", 225 * heads, &table, s));
     return 0;
@@ -189,6 +192,8 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
   float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
   AttnPack attn;
   MlpPack mlp;
+  MlpFusedPack mf;      // norm2 + mlp + residual as one kernel (dims with a fused instantiation)
+  bool use_mf = false;
   int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, int heads_, int shift_, double qk_scale,
            cudaStream_t s) {
     dim = dim_; H = H_; W = W_; heads = heads_; shift = shift_;
@@ -200,7 +205,23 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     SUNET_TRY(copy_vec(ar, P, pre + "norm2.weight", dim, &g2, s));
     SUNET_TRY(copy_vec(ar, P, pre + "norm2.bias", dim, &b2, s));
     SUNET_TRY(attn.pack(ar, P, pre + "attn.", dim, heads, qk_scale, s));
-    SUNET_TRY(mlp.pack(ar, P, pre + "mlp.", dim, 4 * dim, dim, s));
+    use_mf = mlp_fused_supported(dim) && getenv("SUNET_NO_FUSED_MLP") == nullptr;
+    if (use_mf) {
+      const float *gw, *gb, *w1, *b1, *w2, *b2v;
+      SUNET_TRY(P.get(pre + "norm2.weight", dim, &gw));
+      SUNET_TRY(P.get(pre + "norm2.bias", dim, &gb));
+      SUNET_TRY(P.get(pre + "mlp.fc1.weight", static_cast<int64_t>(4) * dim * dim, &w1));
+      SUNET_TRY(P.get(pre + "mlp.fc1.bias", 4 * dim, &b1));
+      SUNET_TRY(P.get(pre + "mlp.fc2.weight", static_cast<int64_t>(4) * dim * dim, &w2));
+      SUNET_TRY(P.get(pre + "mlp.fc2.bias", dim, &b2v));
+      SUNET_TRY(ar.alloc_t(&mf.w1g, static_cast<size_t>(4) * dim * dim));
+      SUNET_TRY(ar.alloc_t(&mf.w2, static_cast<size_t>(4) * dim * dim));
+      SUNET_TRY(ar.alloc_t(&mf.hconst, static_cast<size_t>(8) * dim));
+      SUNET_TRY(ar.alloc_t(&mf.b2, dim));
+      SUNET_TRY(mlp_fused_prepack(&mf, dim, gw, gb, w1, b1, w2, b2v, s));
+    } else {
+      SUNET_TRY(mlp.pack(ar, P, pre + "mlp.", dim, 4 * dim, dim, s));
+    }
     return 0;
   }
   // x_in [B*H*W][dim] -> x_out (may alias x_in); image-order rows throughout
@@ -211,7 +232,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     SUNET_TRY(c.sc.take_t(&T, M * dim));
     SUNET_TRY(c.sc.take_t(&QKV, M * 3 * dim));
     SUNET_TRY(c.sc.take_t(&O, M * dim));
-    SUNET_TRY(c.sc.take_t(&Hd, M * 4 * dim));
+    SUNET_TRY(c.sc.take_t(&Hd, use_mf ? 0 : M * 4 * dim));
     RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                       // :233
     SUNET_TRY(run_linear(c, attn.qkv, T, dim, M, QKV, 3 * dim));                               // :114
     AttnCoreArgs a;
@@ -219,6 +240,10 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
     RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_launch(a, c.stream));               // :118-135, :236-257
     SUNET_TRY(run_linear(c, attn.proj, O, dim, M, x_out, dim, ACT_NONE, nullptr, x_in, dim));   // :136, :261
+    if (use_mf) {
+      RUN(c, K_MLP_FUSED, 16.0 * M * dim * dim, 4.0 * M * dim, mlp_fused_launch(mf, x_out, x_out, M, c.stream));               // :262 (norm2, mlp, +res)
+      return 0;
+    }
     RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_out, dim, T, dim, g2, b2, M, dim, c.stream));                      // :262
     SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
     SUNET_TRY(run_linear(c, mlp.fc2, Hd, 4 * dim, M, x_out, dim, ACT_NONE, nullptr, x_out, dim));  // :22, :262
@@ -791,6 +816,23 @@ int sunet_gemm_f16(const void* A, const void* W, const float* bias, void* C, int
   a.C = C; a.ldc = N;
   if (act == ACT_PRELU) return fail(SUNET_E_ARG, "sunet_gemm_f16: PReLU not exposed here");
   return gemm_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int sunet_ln_mlp_residual_f16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, const float* w1,
+                              const float* b1, const float* w2, const float* b2, void* out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!mlp_fused_supported(C)) return fail(SUNET_E_SHAPE, "fused mlp: C=%d not instantiated", C);
+  Arena ar;
+  MlpFusedPack mf;
+  SUNET_TRY(ar.alloc_t(&mf.w1g, static_cast<size_t>(4) * C * C));
+  SUNET_TRY(ar.alloc_t(&mf.w2, static_cast<size_t>(4) * C * C));
+  SUNET_TRY(ar.alloc_t(&mf.hconst, static_cast<size_t>(8) * C));
+  SUNET_TRY(ar.alloc_t(&mf.b2, C));
+  SUNET_TRY(mlp_fused_prepack(&mf, C, gamma, beta, w1, b1, w2, b2, s));
+  int rc = mlp_fused_launch(mf, static_cast<const __half*>(x), static_cast<__half*>(out), rows, s);
+  cudaError_t e = cudaStreamSynchronize(s);   // the pack buffers are freed when `ar` goes out of scope
+  if (!rc && e != cudaSuccess) rc = fail((int)e, "sunet_ln_mlp_residual_f16: %s", cudaGetErrorString(e));
+  return rc;
 }
 
 }  // extern "C"

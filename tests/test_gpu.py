@@ -64,6 +64,31 @@ def test_gemm_tcgen05_vs_torch(dev, M, N, K, act):
     report(f"gemm {M}x{N}x{K} act{act}", C, ref, 2e-3)
 
 
+@pytest.mark.parametrize("C,rows,mean", [(96, 128, 0.0), (96, 1000, 0.5), (96, 40000, -3.0), (192, 333, 0.0), (192, 70001, 2.0)])
+def test_fused_ln_mlp_residual_vs_torch(dev, C, rows, mean):
+    """norm2 -> Mlp -> +residual (SUNet_detail.py:262) as ONE tcgen05 kernel; rows not a multiple of the 128-token tile,
+    more tiles than SMs, and a large per-token mean (the LayerNorm fold subtracts mu * rowsum(W) after the MMA)."""
+    from sunet_tf_b200 import _lib
+    g = torch.Generator().manual_seed(C + rows)
+    x = (torch.randn(rows, C, generator=g) * 1.5 + mean).half()
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    w1, b1 = torch.randn(4 * C, C, generator=g) * (C ** -0.5), 0.1 * torch.randn(4 * C, generator=g)
+    w2, b2 = torch.randn(C, 4 * C, generator=g) * ((4 * C) ** -0.5), 0.1 * torch.randn(C, generator=g)
+    d = [t.to(dev).contiguous() for t in (x, gamma, beta, w1, b1, w2, b2)]
+    out = torch.empty_like(d[0])
+    _lib.check(_lib.load().sunet_ln_mlp_residual_f16(ctypes.c_void_p(d[0].data_ptr()), rows, C, *[ctypes.c_void_p(t.data_ptr()) for t in d[1:]],
+                                                     ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr(dev)))
+    xf = x.float()
+    h = torch.nn.functional.layer_norm(xf, (C,), gamma, beta, 1e-5)
+    ref = xf + torch.nn.functional.gelu(h @ w1.t() + b1) @ w2.t() + b2
+    report(f"fused ln+mlp+res C{C} rows{rows} mean{mean}", out, ref, MODULE_TOL)
+    # in place (out aliases x), as the block forward calls it
+    xin = d[0].clone()
+    _lib.check(_lib.load().sunet_ln_mlp_residual_f16(ctypes.c_void_p(xin.data_ptr()), rows, C, *[ctypes.c_void_p(t.data_ptr()) for t in d[1:]],
+                                                     ctypes.c_void_p(xin.data_ptr()), _lib.stream_ptr(dev)))
+    assert torch.equal(xin, out), "in-place call differs from out-of-place"
+
+
 @pytest.mark.parametrize("dim", [96, 192, 384, 768])
 @pytest.mark.parametrize("shift", [0, 4])
 def test_swin_block_vs_reference_golden(dev, dim, shift):
