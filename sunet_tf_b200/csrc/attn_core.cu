@@ -32,7 +32,7 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -221,7 +221,10 @@ struct CoreCfg {
   static constexpr int SLOTS = (NVEC + NT - 1) / NT;
   static constexpr int OVEC = 64 * VPS;             // scatter vectors per unit
   static constexpr int OSLOTS = (OVEC + NT - 1) / NT;
-  static constexpr int MAT = HPC * 64 * LDS;        // fp16 elements of one of q / k / v in a stage
+  // Heads are 64 * LDS elements plus a skew apart and q / k / v a further 64 bytes, so that the head-wise gather copies
+  // and the O scatter of one warp spread over the banks instead of piling onto the ones a multiple of 128 bytes apart.
+  static constexpr int HS = 64 * LDS + (HD * 2 + 15) / 16 * 8;   // fp16 elements between consecutive heads
+  static constexpr int MAT = HPC * HS + 32;         // fp16 elements of one of q / k / v in a stage
   static constexpr int STAGE_BYTES = 3 * MAT * 2;
   static constexpr int TBL = 232;                   // 225 padded
   static constexpr int SMEM = 2 * STAGE_BYTES + 8 * TBL * 4;   // table for up to... see launch (heads <= 8 staged per group)
@@ -230,13 +233,13 @@ struct CoreCfg {
 };
 
 template <int HD, int HPC, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCoreArgs p, const int64_t units) {
+__global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCoreArgs p, const int units) {
   using K = CoreCfg<HD, HPC, NWARPS>;
   constexpr int LDS = K::LDS, NT = K::NT, MT = K::MT, VEC = K::VEC, VPH = K::VPH, VPS = K::VPS, TBL = K::TBL;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* stage0 = reinterpret_cast<__half*>(smem_raw);
   float* sTbl = reinterpret_cast<float*>(smem_raw + 2 * K::STAGE_BYTES);   // [heads <= 8][TBL], already times log2(e)
-  __shared__ long long sRow[3][64];   // row map of the previous / current / next unit
+  __shared__ long long sRow[3][64];   // global row of each window token: previous / current / next unit
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWc = p.W >> 3, nWr = p.H >> 3;
@@ -252,13 +255,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCor
     constexpr int PADW = (K::HD_PAD - HD) / 2;  // half2 words per row
     for (int i = tid; i < 2 * 3 * HPC * 64 * PADW; i += NT) {
       const int row = i / PADW, w = i - row * PADW;     // row over [stage][q|k|v][head][token]
-      const bool is_v = (row / (HPC * 64)) % 3 == 2;
+      const int t = row & 63, h = (row >> 6) % HPC, mat = (row >> 6) / HPC;   // mat = stage * 3 + (q|k|v)
       // V: column HD := 1.0 (softmax denominator through the MMA); everything else 0
-      reinterpret_cast<uint32_t*>(stage0 + static_cast<size_t>(row) * LDS + HD)[w] = (is_v && w == 0) ? 0x00003C00u : 0u;
+      reinterpret_cast<uint32_t*>(stage0 + static_cast<size_t>(mat) * K::MAT + h * K::HS + t * LDS + HD)[w] =
+          (mat % 3 == 2 && w == 0) ? 0x00003C00u : 0u;
     }
   }
   // ---- per-thread copy slots (window independent)
-  int g_t[K::SLOTS], g_src[K::SLOTS], g_dst[K::SLOTS];
+  int g_src[K::SLOTS], g_dt[K::SLOTS];   // g_dt = smem byte offset within a stage | token << 18 | valid << 24
 #pragma unroll
   for (int s = 0; s < K::SLOTS; ++s) {
     const int i = tid + s * NT;
@@ -266,45 +270,51 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCor
     const int rem = i - t * (3 * VPS);
     const int seg = rem / VPS, vv = rem - seg * VPS;
     const int h = vv / VPH, v = vv - h * VPH;
-    g_t[s] = i < K::NVEC ? t : -1;
     g_src[s] = seg * p.C + vv * VEC;
-    g_dst[s] = (seg * K::MAT + (h * 64 + t) * LDS + v * VEC) * 2;   // bytes within a stage
+    g_dt[s] = i < K::NVEC ? (((seg * K::MAT + h * K::HS + t * LDS + v * VEC) * 2) | (t << 18) | (1 << 24)) : 0;   // only the last slot can be partial
   }
 
-  auto unit_rows = [&](int64_t u, int st) {   // 64 threads: global row of each window token (st: row-map buffer)
+  auto unit_rows = [&](int u, int st) {   // 64 threads: global row of each window token (st: row-map buffer)
     if (tid < 64) {
-      const int64_t win = u / groups;
+      const int win = u / groups;
       long long row;
       if (p.windowed_input) {
-        row = win * 64 + tid;
+        row = static_cast<long long>(win) * 64 + tid;
       } else {
-        const int wimg = static_cast<int>(win % nW);
-        const int64_t b = win / nW;
+        const int b = win / nW;
+        const int wimg = win - b * nW;
         const int wr = wimg / nWc, wc = wimg - wr * nWc;
         const int r = (wr * 8 + (tid >> 3) + p.shift) % p.H;
         const int c = (wc * 8 + (tid & 7) + p.shift) % p.W;
-        row = (b * p.H + r) * p.W + c;
+        row = (static_cast<long long>(b) * p.H + r) * p.W + c;
       }
       sRow[st][tid] = row;
     }
   };
-  auto unit_gather = [&](int64_t u, int st, int rb) {
-    const int hg = static_cast<int>(u % groups);
+  const long long ld = p.ld;
+  auto unit_gather = [&](int u, int st, int rb) {
+    const int hg = u % groups;
     const __half* base = p.qkv + hg * K::SEG;
     const uint32_t sbase = smem_u32(stage0) + st * K::STAGE_BYTES;
 #pragma unroll
     for (int s = 0; s < K::SLOTS; ++s)
-      if (g_t[s] >= 0) cp_async<VEC * 2>(sbase + g_dst[s], base + sRow[rb][g_t[s]] * p.ld + g_src[s]);
+      if (s + 1 < K::SLOTS || g_dt[s] != 0)
+        cp_async<VEC * 2>(sbase + (g_dt[s] & 0x3ffff), base + sRow[rb][(g_dt[s] >> 18) & 63] * ld + g_src[s]);
     cp_async_commit();
   };
 
-  int64_t u = blockIdx.x;
+  int u = blockIdx.x;
   if (u < units) unit_rows(u, 0);
   __syncthreads();
   if (u < units) unit_gather(u, 0, 0);
   int st = 0, rb = 0;                      // smem stage / row-map buffer of the current unit
+  const int h = warp % HPC;                // this warp's head within the group and its first 16-row query tile
+  const int mbase = (warp / HPC) * MT;
+  const int g = lane >> 2, tq = lane & 3;
+  float tb[2][2 * MT + 7];
+  int tb_hg = -1;
   for (; u < units; u += gridDim.x, st ^= 1, rb = (rb == 2 ? 0 : rb + 1)) {
-    const int64_t un = u + gridDim.x;
+    const int un = u + static_cast<int>(gridDim.x);
     const int rbn = rb == 2 ? 0 : rb + 1;  // last read two units ago (its scatter), before the previous sync (A)
     if (un < units) unit_rows(un, rbn);
     __syncthreads();                       // (A) next unit's row map visible; every warp is done with stage st^1
@@ -315,28 +325,26 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCor
     __half* sQ = stage0 + static_cast<size_t>(st) * (K::STAGE_BYTES / 2);
     __half* sK = sQ + K::MAT;
     __half* sV = sK + K::MAT;
-    const int64_t win = u / groups;
-    const int hg = static_cast<int>(u % groups);
+    const int win = u / groups;
+    const int hg = u - win * groups;
     {
-      const int h = warp % HPC;
-      const int mbase = (warp / HPC) * MT;
-      const __half* q_h = sQ + h * 64 * LDS;
-      const __half* k_h = sK + h * 64 * LDS;
-      const __half* v_h = sV + h * 64 * LDS;
-      __half* o_h = sQ + h * 64 * LDS;
-      const int g = lane >> 2, tq = lane & 3;
-      // this thread's slice of the relative-position bias: tb[e][k] = table[(k + 2*mbase) * 15 + (g - (2*tq+e) + 7)]
-      const float* tbl = sTbl + (hg * HPC + h) * TBL;
-      float tb[2][2 * MT + 7];
+      const __half* q_h = sQ + h * K::HS;
+      const __half* k_h = sK + h * K::HS;
+      const __half* v_h = sV + h * K::HS;
+      __half* o_h = sQ + h * K::HS;
+      if (hg != tb_hg) {   // this thread's slice of the relative-position bias (constant per CTA when groups | gridDim.x)
+        const float* tbl = sTbl + (hg * HPC + h) * TBL;
 #pragma unroll
-      for (int e = 0; e < 2; ++e)
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
-        for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (g - 2 * tq - e + 7)];
+          for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (g - 2 * tq - e + 7)];
+        tb_hg = hg;
+      }
       if (p.mask_mode == 2) {
-        const float* mexp = p.mask + (win % p.mask_nw) * 4096;
+        const float* mexp = p.mask + static_cast<long long>(win % p.mask_nw) * 4096;
         attn_tiles<HD, MT, 2>(q_h, k_h, v_h, o_h, mbase, lane, tb, false, false, mexp);
       } else {
-        const int wimg = static_cast<int>(win % nW);
+        const int wimg = win % nW;
         const int wr = wimg / nWc, wc = wimg - wr * nWc;
         const bool mrow = p.mask_mode == 1 && wr == nWr - 1;
         const bool mcol = p.mask_mode == 1 && wc == nWc - 1;
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCor
       if (i < K::OVEC) {
         const int t = i / VPS, vv = i - t * VPS;
         const int h = vv / VPH, v = vv - h * VPH;
-        const __half* src = sQ + (h * 64 + t) * LDS + v * VEC;
+        const __half* src = sQ + h * K::HS + t * LDS + v * VEC;
         __half* dst = p.out + sRow[rb][t] * p.ldo + hg * K::SEG + vv * VEC;
         if constexpr (VEC == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
         else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
@@ -376,8 +384,9 @@ int launch_core(const AttnCoreArgs& a, int64_t windows, cudaStream_t stream) {
     configured = true;
   }
   const int64_t units = windows * (a.heads / HPC);
+  if (units > 0x7fffffff) return fail(SUNET_E_SHAPE, "attn: too many (window, head-group) units");
   const unsigned grid = static_cast<unsigned>(units < sms ? units : sms);
-  attn_core_kernel<HD, HPC, NWARPS><<<grid, K::NT, K::SMEM, stream>>>(a, units);
+  attn_core_kernel<HD, HPC, NWARPS><<<grid, K::NT, K::SMEM, stream>>>(a, static_cast<int>(units));
   SUNET_CHECK_LAUNCH();
   return 0;
 }

@@ -33,6 +33,7 @@ struct GemmArgs {
   int64_t ldc = 0;
   int out_f32 = 0;
   int force_block_n = 0;         // tuning / tests
+  int pair_mode = 0;             // 0 auto, 1 single-CTA tiles, 2 CTA-pair (cta_group::2) 256-row tiles
 };
 
 struct GemmEpi {
@@ -59,6 +60,7 @@ struct GemmOp {
   GemmEpi epi;
   unsigned grid = 0;
   int smem = 0;
+  int pair = 0;
   double flops = 0;
 };
 

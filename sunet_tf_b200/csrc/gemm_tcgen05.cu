@@ -296,6 +296,153 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair variant
+// Same pipeline with tcgen05 cta_group::2: two CTAs of a cluster (one TPC) work on one 256 x block_n tile.  Each CTA
+// stages its own 128 rows of A and HALF of the weight tile (block_n / 2 rows), the leader's MMA warp issues M = 256
+// instructions that read both CTAs' shared memory and write both CTAs' TMEM, and each CTA drains its own 128 rows.
+// Per CTA this halves the weight bytes pulled through L2 -> smem and the smem a ring stage costs (deeper ring).
+// Barriers: full[] lives in the leader (both CTAs' TMA loads complete on it), empty[] / tmem_full[] exist in both CTAs
+// and are signalled by multicast commits, tmem_empty[] lives in the leader and collects both CTAs' epilogue warps.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tn_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                            const __grid_constant__ CUtensorMap tmW, const GemmEpi p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0: leader (issues the MMAs)
+  const int block_n = p.block_n;
+  const int half_n = block_n >> 1;
+  const int stages = p.stages;
+  const uint32_t stage_bytes = A_TILE_BYTES + half_n * BLOCK_K * 2;
+  const int kb0 = (p.K0 + BLOCK_K - 1) / BLOCK_K;
+  const int kb1 = (p.K1 + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = kb0 + kb1;
+  const uint32_t acc_cols = p.acc_cols;
+  const uint32_t tmem_cols = p.tmem_cols;
+  const int64_t total_tiles = p.total_tiles;     // 256 x block_n tiles
+  const int64_t cluster_id = blockIdx.x >> 1;
+  const int64_t n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.K1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(&tmem_base_smem, tmem_cols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / peer TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int n0 = static_cast<int>(tile % p.n_tiles) * block_n + static_cast<int>(rank) * half_n;
+        const int m0 = static_cast<int>(tile / p.n_tiles) * (2 * BLOCK_M) + static_cast<int>(rank) * BLOCK_M;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);   // both CTAs' bytes land on the leader's barrier
+          if (kb < kb0) {
+            tma_load_2d_pair(sa, &tmA0, &full_bar[s], kb * BLOCK_K, m0);
+            tma_load_2d_pair(sb, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+          } else {
+            const int j = kb - kb0;
+            tma_load_2d_pair(sa, &tmA1, &full_bar[s], j * BLOCK_K, m0);
+            tma_load_2d_pair(sb, &tmW, &full_bar[s], p.K0 + j * BLOCK_K, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, block_n);
+      uint32_t it = 0;
+      uint32_t local = 0;
+      for (int64_t tile = cluster_id; tile < total_tiles; tile += n_clusters, ++local) {
+        const uint32_t as = local & 1;
+        const uint32_t aph = (local >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);   // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * acc_cols;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sb);
+          const int kvalid = kb < kb0 ? min(BLOCK_K, p.K0 - kb * BLOCK_K) : min(BLOCK_K, p.K1 - (kb - kb0) * BLOCK_K);
+          const int ksteps = (kvalid + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_pair(&empty_bar[s], 3);        // frees the slot in both CTAs
+        }
+        tc_commit_pair(&tmem_full_bar[as], 3);     // accumulator complete: wake both CTAs' epilogues
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int quarter = (warp - 2) >> 2;
+    const int units = block_n >> 4;
+    const int c_begin = (quarter * units >> 2) << 4;
+    const int c_end = ((quarter + 1) * units >> 2) << 4;
+    const int row = q * 32 + lane;
+    const uint32_t stg = smem_u32(smem + static_cast<size_t>(stages) * stage_bytes + (warp - 2) * 4096);
+    float slope = 0.f;
+    if (p.act == ACT_PRELU) slope = __ldg(p.prelu);
+    uint32_t local = 0;
+    for (int64_t tile = cluster_id; tile < total_tiles; tile += n_clusters, ++local) {
+      const uint32_t as = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * block_n;
+      const int64_t m = static_cast<int64_t>(tile / p.n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M + row;
+      const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after();
+      const int64_t m_base = m - lane;
+      const int rows_valid = static_cast<int>(min(static_cast<int64_t>(32), p.M - m_base));
+      if (p.out_f32) epilogue_range<true>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
+      else epilogue_range<false>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // the leader's MMA warp owns the accumulator hand-back
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -370,20 +517,22 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
       (reinterpret_cast<uintptr_t>(a.bias) & 15))
     return fail(SUNET_E_ALIGN, "gemm: C/R/bias must be 16-byte aligned");
   if (a.M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "gemm: M too large for 32-bit TMA coordinates");
-  const int64_t m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const bool pair = a.pair_mode == 2;   // cta_group::2: 256-row tiles shared by a CTA pair
+  const int64_t m_tiles = pair ? (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (a.M + BLOCK_M - 1) / BLOCK_M;
   int bn = a.force_block_n ? a.force_block_n : pick_block_n(a.N, m_tiles, a.K0 + a.K1);
+  if (pair && bn % 32 != 0) return fail(SUNET_E_SHAPE, "gemm: the CTA-pair path needs a tile width that is a multiple of 32 (bn=%d)", bn);
   if (bn == 0 || a.N % bn != 0 || bn % 16 != 0 || bn > 256) return fail(SUNET_E_SHAPE, "gemm: no tile width for N=%d (bn=%d)", a.N, bn);
   const int n_tiles = a.N / bn;
   if (m_tiles * n_tiles > 0x7fffffffLL) return fail(SUNET_E_SHAPE, "gemm: grid too large");
   const int num_kb = (a.K0 + BLOCK_K - 1) / BLOCK_K + (a.K1 + BLOCK_K - 1) / BLOCK_K;
-  const int stage_bytes = A_TILE_BYTES + bn * BLOCK_K * 2;
+  const int stage_bytes = A_TILE_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2;
   int stages = (GEMM_MAX_DYN_SMEM - 1024 - EPI_WARPS * 4096) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 1) stages = 1;
   SUNET_TRY(make_tmap_2d_f16(&op->tmA0, a.A0, a.K0, a.M, a.lda0, BLOCK_M));
   if (a.K1 > 0) SUNET_TRY(make_tmap_2d_f16(&op->tmA1, a.A1, a.K1, a.M, a.lda1, BLOCK_M));
   else op->tmA1 = op->tmA0;
-  SUNET_TRY(make_tmap_2d_f16(&op->tmW, a.W, a.K0 + a.K1, a.N, a.ldw, bn));
+  SUNET_TRY(make_tmap_2d_f16(&op->tmW, a.W, a.K0 + a.K1, a.N, a.ldw, pair ? bn / 2 : bn));
   GemmEpi& e = op->epi;
   e.M = a.M; e.N = a.N; e.K0 = a.K0; e.K1 = a.K1; e.block_n = bn; e.stages = stages;
   e.bias = a.bias; e.prelu = a.prelu; e.act = a.act; e.R = a.R; e.ldr = a.ldr; e.C = a.C; e.ldc = a.ldc;
@@ -394,9 +543,16 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   if (a.act == ACT_PRELU && a.prelu == nullptr) return fail(SUNET_E_ARG, "gemm: PReLU needs a slope pointer");
   if (a.out_f32 && a.R != nullptr) return fail(SUNET_E_ARG, "gemm: a residual with fp32 output is not supported");
   const int64_t tiles = m_tiles * n_tiles;
-  op->grid = static_cast<unsigned>(tiles < num_sms() ? tiles : num_sms());
+  op->pair = pair ? 1 : 0;
+  if (pair) {
+    const int64_t clusters = num_sms() / 2;
+    op->grid = static_cast<unsigned>(2 * (tiles < clusters ? tiles : clusters));
+  } else {
+    op->grid = static_cast<unsigned>(tiles < num_sms() ? tiles : num_sms());
+  }
   // never keep more ring stages than this CTA will ever fill
-  const int64_t tiles_per_cta = (tiles + op->grid - 1) / op->grid;
+  const int64_t workers = pair ? op->grid / 2 : op->grid;
+  const int64_t tiles_per_cta = (tiles + workers - 1) / workers;
   if (static_cast<int64_t>(stages) > tiles_per_cta * num_kb) { stages = static_cast<int>(tiles_per_cta * num_kb); e.stages = stages; }
   op->smem = stages * stage_bytes + 1024 + EPI_WARPS * 4096;
   op->flops = 2.0 * (double)a.M * a.N * (a.K0 + a.K1);
@@ -407,9 +563,11 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   static bool configured = false;  // per process; one device per process (one rank per GPU)
   if (!configured) {
     SUNET_CUDA(cudaFuncSetAttribute(gemm_tn_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_MAX_DYN_SMEM));
+    SUNET_CUDA(cudaFuncSetAttribute(gemm_tn_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_MAX_DYN_SMEM));
     configured = true;
   }
-  gemm_tn_f16_kernel<<<op.grid, GEMM_THREADS, op.smem, stream>>>(op.tmA0, op.tmA1, op.tmW, op.epi);
+  if (op.pair) gemm_tn_f16_pair_kernel<<<op.grid, GEMM_THREADS, op.smem, stream>>>(op.tmA0, op.tmA1, op.tmW, op.epi);
+  else gemm_tn_f16_kernel<<<op.grid, GEMM_THREADS, op.smem, stream>>>(op.tmA0, op.tmA1, op.tmW, op.epi);
   SUNET_CHECK_LAUNCH();
   return 0;
 }

@@ -19,6 +19,9 @@ struct MlpFusedPack {
   float* b2 = nullptr;       // [C]
   alignas(64) CUtensorMap tmW1;
   alignas(64) CUtensorMap tmW2;
+  alignas(64) CUtensorMap tmW1p;  // CTA-pair kernel: half-tile boxes
+  alignas(64) CUtensorMap tmW2p;
+  int pair = 0;                   // 1: run the cta_group::2 kernel with resident weights (C = 96)
 };
 
 bool mlp_fused_supported(int C);

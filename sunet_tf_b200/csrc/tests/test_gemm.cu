@@ -76,7 +76,7 @@ static void test_selftest(int N) {
 }
 
 struct Case {
-  int64_t M; int N, K0, K1; int bias, act, res, f32; int bn;
+  int64_t M; int N, K0, K1; int bias, act, res, f32; int bn; int pair = 0;
 };
 
 static void test_gemm(const Case& c, bool check, int time_iters) {
@@ -109,7 +109,7 @@ static void test_gemm(const Case& c, bool check, int time_iters) {
   a.A0 = dA0; a.lda0 = c.K0; a.K0 = c.K0; a.A1 = dA1; a.lda1 = c.K1; a.K1 = c.K1;
   a.W = dW; a.ldw = K; a.M = c.M; a.N = c.N;
   a.bias = c.bias ? dBias : nullptr; a.act = c.act; a.prelu = dSlope; a.R = dR; a.ldr = c.N;
-  a.C = dC; a.ldc = c.N; a.out_f32 = c.f32; a.force_block_n = c.bn;
+  a.C = dC; a.ldc = c.N; a.out_f32 = c.f32; a.force_block_n = c.bn; a.pair_mode = c.pair;
   GemmOp op;
   int rc = gemm_prepare(a, &op);
   if (rc) { printf("gemm prepare rc=%d: %s\n", rc, last_error_buf()); g_fail++; return; }
@@ -118,8 +118,8 @@ static void test_gemm(const Case& c, bool check, int time_iters) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("gemm M=%lld N=%d K=%d+%d: CUDA error %s\n", (long long)c.M, c.N, c.K0, c.K1, cudaGetErrorString(e)); exit(3); }
   char tag[160];
-  snprintf(tag, sizeof tag, "gemm M=%lld N=%d K=%d+%d bias%d act%d res%d f32%d bn=%d st=%d grid=%u", (long long)c.M, c.N, c.K0, c.K1,
-           c.bias, c.act, c.res, c.f32, op.epi.block_n, op.epi.stages, op.grid);
+  snprintf(tag, sizeof tag, "gemm M=%lld N=%d K=%d+%d bias%d act%d res%d f32%d bn=%d st=%d grid=%u%s", (long long)c.M, c.N, c.K0, c.K1,
+           c.bias, c.act, c.res, c.f32, op.epi.block_n, op.epi.stages, op.grid, op.pair ? " PAIR" : "");
   if (check) {
     std::vector<uint8_t> hC(csz);
     CK(cudaMemcpy(hC.data(), dC, csz, cudaMemcpyDeviceToHost));
@@ -196,6 +196,12 @@ int main(int argc, char** argv) {
       {384, 48, 96, 0, 0, 0, 0, 0, 0},
   };
   for (const Case& c : small) test_gemm(c, true, 0);
+  for (Case c : small) {   // the same ladder on CTA pairs (cta_group::2) where the tile width allows it
+    c.pair = 2;
+    if (c.bn == 0) c.bn = c.N % 256 == 0 ? 256 : (c.N % 192 == 0 ? 192 : (c.N % 128 == 0 ? 128 : (c.N % 96 == 0 ? 96 : (c.N % 64 == 0 ? 64 : (c.N % 32 == 0 ? 32 : 0)))));
+    if (c.bn == 0 || c.bn % 32) continue;
+    test_gemm(c, true, 0);
+  }
   if (do_time && !g_fail) {
     const Case big[] = {
         {262144, 288, 96, 0, 1, 0, 0, 0, 0},   {262144, 288, 96, 0, 1, 0, 0, 0, 96}, {262144, 288, 96, 0, 1, 0, 0, 0, 48},
@@ -214,6 +220,13 @@ int main(int argc, char** argv) {
         {262144, 1536, 96, 0, 0, ACT_PRELU, 0, 0, 0}, {4194304, 16, 96, 0, 0, 0, 0, 1, 0},
     };
     for (const Case& c : big) test_gemm(c, false, 20);
+    printf("---- CTA pairs\n");
+    for (Case c : big) {
+      c.pair = 2;
+      if (c.bn == 0) c.bn = c.N % 256 == 0 ? 256 : (c.N % 192 == 0 ? 192 : (c.N % 128 == 0 ? 128 : (c.N % 96 == 0 ? 96 : 0)));
+      if (c.bn == 0 || c.bn % 32) continue;
+      test_gemm(c, false, 20);
+    }
   }
   printf(g_fail ? "RESULT: %d FAILURES\n" : "RESULT: ALL OK\n", g_fail);
   return g_fail ? 1 : 0;
