@@ -29,6 +29,8 @@ PER_GPU_BATCH = 64
 N_INPUT_BUFFERS = 4          # 4 x 50 MB of distinct inputs > 126 MB L2; the forward itself streams a ~2 GB workspace
 REF_FLOPS_PER_IMAGE = 64.148e9   # reference formulation, 2*MAC over every Linear/Conv/bmm
 METRIC = "sunet_256x256_denoise_images_per_s"
+WORKLOAD = ("BASELINE configs[1]: SUNet fwd 256x256 RGB batch 64 per GPU, training.yaml arch (emb 96, depths [8,8,8,8], "
+            "heads 8, win 8, qk_scale 8), random init, AWGN sigma=50 8-bit quantised input")
 
 
 def read_peaks():
@@ -140,8 +142,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SUNet fwd 256x256 RGB, training.yaml arch (emb 96, depths [8,8,8,8], heads 8, win 8), random init, AWGN sigma=50",
-                   "step": f"{images} images through the CPU oracle port of the reference forward (torch {torch.__version__} CPU fp32)"},
+        "config": {"workload": WORKLOAD,
+                   "step": f"bounded sample: {images} images of that workload per step through the CPU oracle port of the reference "
+                           f"forward (torch {torch.__version__} CPU fp32, {cores} threads)"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps x {images} images, {cores} threads"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -301,8 +304,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: SUNet fwd 256x256 RGB batch 64 per GPU, training.yaml arch (emb 96, depths [8,8,8,8], "
-                                   "heads 8, win 8, qk_scale 8), random init, AWGN sigma=50 8-bit quantised input",
+            "config": {"workload": WORKLOAD,
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}, no collective",
                        "l2": f"inputs rotate over {N_INPUT_BUFFERS} distinct batches ({N_INPUT_BUFFERS * h2d / 1e6:.0f} MB) and each forward "
                              "streams a ~2 GB workspace, both > 126 MB L2",
