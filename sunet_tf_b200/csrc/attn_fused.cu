@@ -1,0 +1,613 @@
+// Fused window attention (front half of a Swin block) for the bandwidth-bound stages (C = 96, 192):
+//
+//   norm1 (:233) -> roll (:238) -> window_partition (:243) -> qkv Linear (:114) -> q*scale (:117) -> q k^T (:118)
+//   -> + relative_position_bias (:120-123) -> + shifted-window mask (:125-129) -> softmax -> @ v (:135)
+//   -> window_reverse (:251) -> roll back (:255)                                  [SUNet_detail.py]
+//
+// in ONE kernel: the token stream is read once and the per-head attention output is written once; LayerNorm output,
+// q/k/v and the 64x64 score matrices never exist in HBM.
+//
+// One persistent CTA per SM walks tiles of TWO windows (128 tokens):
+//   gather : the 128 token rows are fetched through the roll+partition index map with 16-byte cp.async straight into
+//            the 128-byte-swizzled K-major layout tcgen05.mma reads (window_partition / torch.roll are address arithmetic)
+//   QKV    : D[128 x 3*GH*hd] = X[128 x C] * Wg^T on tcgen05 (fp16 in, fp32 accumulators in TMEM); the weights of the
+//            current head group arrive by TMA.  LayerNorm is folded: Wg = W * gamma (pre-pack), and
+//            qkv = rstd * D - rstd * mu * rowsum(Wg) + (b + W beta), applied when the accumulators are drained
+//   drain  : TMEM -> registers -> fp16 q/k/v operand tiles in shared memory (head_dim padded to 16/32, XOR-swizzled rows)
+//   core   : per (window, head): S = q k^T + bias (+ closed-form mask), exp2 softmax, O = P V on mma.sync.m16n8k16 with
+//            register-resident S/P (K = 12/24: a 64x64xhd problem per head is below any tcgen05 tile), O parked in the q rows
+//   scatter: O rows go back through the same index map (window_reverse + un-roll).
+// C = 96 handles all 8 heads per pass (288 accumulator columns); C = 192 walks 4 groups of 2 heads (144 columns).
+#include "attn_fused.cuh"
+
+#include "error.h"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace sunet {
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int NTHREADS = 512;
+constexpr int TBL = 232;   // 225 bias entries per head, padded
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+template <int C_, int GH_>
+struct FCfg {
+  static constexpr int C = C_, HEADS = 8, HD = C / 8, HD_PAD = (HD + 15) / 16 * 16, GH = GH_, NG = HEADS / GH;
+  static constexpr int BR = GH * HD;             // rows of one of q / k / v in a head group
+  static constexpr int NGC = 3 * BR;             // accumulator columns per head group
+  static constexpr int NMMA = NGC > 256 ? 3 : 1; // tcgen05.mma instructions per k-step (N <= 256 each)
+  static constexpr int NPM = NGC / NMMA;
+  static constexpr int KB = (C + 63) / 64;       // 64-wide k-blocks (one 128-byte swizzle row each)
+  static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;
+  static constexpr int RB = HD_PAD * 2;          // bytes per q/k/v operand row
+  static constexpr int UNIT_BYTES = 64 * RB;     // one (q|k|v, window, head) operand tile
+  static constexpr int NU = 2 * GH;              // (window, head) units per pass
+  static constexpr int WPU = 16 / NU;            // warps per unit
+  static constexpr int MT = 4 / WPU;             // 16-row query tiles per warp
+  static constexpr int QC = NGC / 4;             // accumulator columns drained by one column-quarter
+  static constexpr int QCH = C / 32;             // 16-byte chunks of a token row per quarter (statistics pass)
+  static constexpr int CPR = C / 8;              // 16-byte chunks per token row
+  static constexpr int VEC = (HD % 8 == 0) ? 8 : 4;
+  static constexpr int VPH = HD / VEC;
+  static constexpr int VPT = BR / VEC;           // output vectors per token per pass
+  static constexpr int X_BYTES = KB * 16384;
+  static constexpr int W_BYTES = KB * NGC * 128;
+  static constexpr int QKV_BYTES = 3 * NU * UNIT_BYTES;
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_W = OFF_X + X_BYTES;
+  static constexpr int OFF_QKV = OFF_W + W_BYTES;
+  static constexpr int OFF_TBL = OFF_QKV + QKV_BYTES;
+  static constexpr int OFF_HC = OFF_TBL + HEADS * TBL * 4;
+  static constexpr int OFF_ST = OFF_HC + 3 * C * 8;
+  static constexpr int SMEM = OFF_ST + 4 * 128 * 8 + 1024;
+  static constexpr uint32_t TMEM_COLS = NGC <= 256 ? 256 : 512;
+  static_assert(C % 32 == 0 && HD % 4 == 0 && QC % 4 == 0, "column slices must be whole 4-column groups");
+  static_assert((NPM * 128) % 1024 == 0 && NPM % 16 == 0 && NPM <= 256, "weight sub-tiles must be whole swizzle atoms");
+  static_assert(WPU >= 1 && WPU <= 4 && WPU * NU == 16 && MT * WPU == 4, "warp / unit split");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// byte offset of 16-byte chunk `ch` of row `row` inside a [64][HD_PAD] operand tile: consecutive rows are RB bytes apart and
+// the chunk index is XOR-swizzled with the 128-byte line number so that the 8 rows of an ldmatrix phase hit 8 distinct
+// 16-byte bank groups
+template <int RB>
+__device__ __forceinline__ uint32_t op_off(int row, int ch) {
+  if constexpr (RB == 32) return static_cast<uint32_t>(row * 32 + ((ch ^ ((row >> 2) & 1)) << 4));
+  else return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+}
+
+// One 16-row query tile of one (window, head) unit; see attn_core.cu for the register-level scheme.  tb[e][k] holds this
+// lane's slice of the relative-position bias, k = 2*MI + row_half - key_row + 7.  With a padded head column HD of V is
+// 1.0, so O[:, HD] is the softmax denominator summed by the MMA over the fp16-rounded probabilities that multiply V.
+template <int HD, int MT, int MI, bool MASK>
+__device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v_h, int mt, int lane, const float (&tb)[2][2 * MT + 7],
+                                          bool mrow, bool mcol) {
+  constexpr int HD_PAD = (HD + 15) / 16 * 16;
+  constexpr int RB = HD_PAD * 2;
+  constexpr int KS = HD_PAD / 16;
+  constexpr int NO = HD_PAD / 8;
+  constexpr bool MMA_SUM = HD_PAD != HD;
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t qa[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) ldsm_x4(qa[ks], q_h + op_off<RB>(mt * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+  float s[8][4];
+  if constexpr (MASK) {
+    // closed-form SW-MSA mask (SUNet_detail.py:202-221, shift = 4): -100 where the wrapped halves differ, applied once
+    constexpr float NEG = -100.f * LOG2E;
+    const bool r0hi = (2 * mt) >= 4, r1hi = (2 * mt + 1) >= 4;
+    float cm[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cm[e] = (mcol && ((g >= 4) != ((2 * tq + e) >= 4))) ? NEG : 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float rm0 = (mrow && (r0hi != (nt >= 4))) ? NEG : 0.f;
+      const float rm1 = (mrow && (r1hi != (nt >= 4))) ? NEG : 0.f;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = tb[e][2 * MI + 0 - nt + 7] + fminf(rm0, cm[e]);
+        s[nt][2 + e] = tb[e][2 * MI + 1 - nt + 7] + fminf(rm1, cm[e]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = tb[e][2 * MI + 0 - nt + 7];
+        s[nt][2 + e] = tb[e][2 * MI + 1 - nt + 7];
+      }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; nt += 2) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t kb[4];   // (nt, k lo), (nt, k hi), (nt+1, k lo), (nt+1, k hi)
+      ldsm_x4(kb, k_h + op_off<RB>((nt + (lane >> 4)) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
+      mma_16816(s[nt], qa[ks], kb[0], kb[1]);
+      mma_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
+    }
+  }
+  // softmax over the 64 keys (a row lives in the 4 lanes of a quad); logits are already in the exp2 domain
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = ex2(s[nt][0] - m0);
+    s[nt][1] = ex2(s[nt][1] - m0);
+    s[nt][2] = ex2(s[nt][2] - m1);
+    s[nt][3] = ex2(s[nt][3] - m1);
+    if constexpr (!MMA_SUM) {
+      sum0 += s[nt][0] + s[nt][1];
+      sum1 += s[nt][2] + s[nt][3];
+    }
+  }
+  float o[NO][4];
+#pragma unroll
+  for (int n = 0; n < NO; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int n = 0; n < NO; n += 2) {
+      uint32_t vb[4];   // transposed 8x8 loads of V[key][d]: (keys lo, n), (keys hi, n), (keys lo, n+1), (keys hi, n+1)
+      ldsm_x4_t(vb, v_h + op_off<RB>(kk * 16 + (lane & 15), n + (lane >> 4)));
+      mma_16816(o[n], pa, vb[0], vb[1]);
+      mma_16816(o[n + 1], pa, vb[2], vb[3]);
+    }
+  }
+  if constexpr (MMA_SUM) {
+    constexpr int NS = HD / 8, CS = HD % 8;
+    const float c0 = (CS & 1) ? o[NS][1] : o[NS][0];
+    const float c1 = (CS & 1) ? o[NS][3] : o[NS][2];
+    const int src = (lane & ~3) | (CS >> 1);
+    sum0 = __shfl_sync(0xffffffffu, c0, src);
+    sum1 = __shfl_sync(0xffffffffu, c1, src);
+  } else {
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  }
+  const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
+  // normalise and park O in this tile's own q rows (already consumed into registers by every lane of this warp)
+  __syncwarp();
+  const int i0 = mt * 16 + g, i1 = i0 + 8;
+#pragma unroll
+  for (int n = 0; n < NO; ++n) {
+    if (n * 8 + 2 * tq < HD) {
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(q_h + op_off<RB>(i0, n) + 4 * tq), "r"(pack_half2(o[n][0] * inv0, o[n][1] * inv0)) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(q_h + op_off<RB>(i1, n) + 4 * tq), "r"(pack_half2(o[n][2] * inv1, o[n][3] * inv1)) : "memory");
+    }
+  }
+}
+
+template <int HD, int MT, bool MASK>
+__device__ __forceinline__ void attn_tiles(uint32_t q_h, uint32_t k_h, uint32_t v_h, int mbase, int lane, const float (&tb)[2][2 * MT + 7],
+                                           bool mrow, bool mcol) {
+  attn_tile<HD, MT, 0, MASK>(q_h, k_h, v_h, mbase + 0, lane, tb, mrow, mcol);
+  if constexpr (MT > 1) attn_tile<HD, MT, 1, MASK>(q_h, k_h, v_h, mbase + 1, lane, tb, mrow, mcol);
+  if constexpr (MT > 2) {
+    attn_tile<HD, MT, 2, MASK>(q_h, k_h, v_h, mbase + 2, lane, tb, mrow, mcol);
+    attn_tile<HD, MT, 3, MASK>(q_h, k_h, v_h, mbase + 3, lane, tb, mrow, mcol);
+  }
+}
+
+struct FParams {
+  const __half* x;
+  __half* out;
+  const float2* hconst;
+  const float* table;   // [225][heads]
+  int B, H, W, shift;
+};
+
+template <int C, int GH>
+__global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, const FParams p) {
+  using K = FCfg<C, GH>;
+  constexpr int RB = K::RB, HD = K::HD, MT = K::MT;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t w_full, mma_done;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sX = smem_u32(smem + K::OFF_X), sW = smem_u32(smem + K::OFF_W), sQKV = smem_u32(smem + K::OFF_QKV);
+  float* sTbl = reinterpret_cast<float*>(smem + K::OFF_TBL);
+  const float2* sHc = reinterpret_cast<const float2*>(smem + K::OFF_HC);
+  float2* sSt = reinterpret_cast<float2*>(smem + K::OFF_ST);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3;             // TMEM lane quadrant this warp may read
+  const int quarter = warp >> 2;       // column quarter of the drain / statistics pass
+  const int row = q4 * 32 + lane;      // token row of the tile owned in the drain
+
+  // ---------------------------------------------------------------- one-time setup
+  if (tid == 0) {
+    tma_prefetch_desc(&tmW);
+    mbar_init(&w_full, 1);
+    mbar_init(&mma_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_smem, K::TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < K::HEADS * 225; i += NTHREADS) {
+    const int e = i / K::HEADS, h = i - e * K::HEADS;
+    sTbl[h * TBL + e] = __ldg(p.table + i) * LOG2E;
+  }
+  for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float2*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
+  if constexpr (K::HD_PAD != HD) {
+    // pad columns of every operand tile: 0 for q / k, V column HD = 1.0 (softmax denominator through the MMA); the drain and
+    // the O store only ever write columns < HD, so this survives the whole kernel
+    constexpr int PADW = (K::HD_PAD - HD) / 2;   // 32-bit words per row
+    for (int i = tid; i < 3 * K::NU * 64 * PADW; i += NTHREADS) {
+      const int w = i % PADW, r = (i / PADW) & 63, unit = i / (PADW * 64);   // unit over [q|k|v][window][head]
+      const int d = HD + 2 * w;
+      const uint32_t addr = sQKV + unit * K::UNIT_BYTES + op_off<RB>(r, d >> 3) + (d & 7) * 2;
+      const uint32_t val = (unit / K::NU == 2 && w == 0) ? 0x00003C00u : 0u;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int nWc = p.W >> 3, nWr = p.H >> 3, nW = nWr * nWc;
+  const long long nwin = static_cast<long long>(p.B) * nW;
+  const long long tiles = (nwin + 1) >> 1;
+
+  // global token row of window token (wi, tt) of `tile`, or -1 past the last window
+  auto token_row = [&](long long tile, int t128) -> long long {
+    const long long win = tile * 2 + (t128 >> 6);
+    if (win >= nwin) return -1;
+    const int b = static_cast<int>(win / nW);
+    const int wimg = static_cast<int>(win - static_cast<long long>(b) * nW);
+    const int wr = wimg / nWc, wc = wimg - wr * nWc;
+    const int tt = t128 & 63;
+    int r = wr * 8 + (tt >> 3) + p.shift, c = wc * 8 + (tt & 7) + p.shift;
+    if (r >= p.H) r -= p.H;
+    if (c >= p.W) c -= p.W;
+    return (static_cast<long long>(b) * p.H + r) * p.W + c;
+  };
+  auto gather = [&](long long tile) {   // every thread: its share of the 128 x C/8 16-byte chunks
+#pragma unroll
+    for (int s = 0; s < (128 * K::CPR + NTHREADS - 1) / NTHREADS; ++s) {
+      const int i = tid + s * NTHREADS;
+      if (i < 128 * K::CPR) {
+        const int t = i / K::CPR, cg = i - t * K::CPR;
+        const int kb = cg >> 3, ch = cg & 7;
+        const uint32_t dst = sX + kb * 16384 + t * 128 + ((ch ^ (t & 7)) << 4);
+        const long long gr = token_row(tile, t);
+        if (gr >= 0) cp_async16(dst, p.x + gr * C + cg * 8);
+        else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+      }
+    }
+    cp_async_commit();
+  };
+  auto load_w = [&](int g) {   // thread 0: the folded qkv weights of head group g -> smem, [kb][sub-tile][NPM rows][64] SW128
+    mbar_arrive_expect_tx(&w_full, K::W_BYTES);
+#pragma unroll
+    for (int kb = 0; kb < K::KB; ++kb)
+#pragma unroll
+      for (int m = 0; m < K::NMMA; ++m)
+        tma_load_2d(smem + K::OFF_W + (kb * K::NMMA + m) * K::NPM * 128, &tmW, &w_full, kb * 64, g * K::NGC + m * K::NPM);
+  };
+
+  // this warp's (window, head) unit of the core pass
+  const int unit = warp % K::NU;
+  const int u_wi = unit / GH, u_hl = unit - u_wi * GH;
+  const int mbase = (warp / K::NU) * MT;
+  const int lg = lane >> 2, ltq = lane & 3;
+  float tb[2][2 * MT + 7];
+  int tb_head = -1;
+
+  uint32_t item = 0;
+  if (static_cast<long long>(blockIdx.x) < tiles) {
+    if (tid == 0) load_w(0);
+    gather(blockIdx.x);
+  }
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    float ln_a = 0.f, ln_b = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < K::NG; ++g, ++item) {
+      if (g == 0) {
+        cp_async_wait_all();
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      __syncthreads();   // (A) token tile landed; q/k/v operand tiles and the accumulator are free again
+      if (tid == 0) {
+        mbar_wait(&w_full, item & 1);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(128, K::NPM);
+#pragma unroll
+        for (int kb = 0; kb < K::KB; ++kb) {
+          const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
+          const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
+#pragma unroll
+          for (int k = 0; k < ksteps; ++k)
+#pragma unroll
+            for (int m = 0; m < K::NMMA; ++m) {
+              const uint64_t bdesc = umma_desc_sw128(sW + (kb * K::NMMA + m) * K::NPM * 128);
+              umma_f16_ss(tmem_base + m * K::NPM, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            }
+        }
+        tc_commit(&mma_done);
+      }
+      __syncwarp();
+      if (g == 0) {
+        // LayerNorm statistics of this thread's row (fp32, shifted one-pass variance), combined over the 4 column quarters
+        float s1 = 0.f, s2 = 0.f;
+        const uint32_t sw = static_cast<uint32_t>(row & 7);
+        const uint4 first = lds128(sX + row * 128 + (sw << 4));
+        const float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(first.x & 0xffffu)));
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) {
+          const int gi = quarter * K::QCH + i;
+          const uint4 v = lds128(sX + (gi >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4));
+          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h2[t]);
+            const float d0 = f.x - k0, d1 = f.y - k0;
+            s1 += d0 + d1;
+            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+          }
+        }
+        sSt[quarter * 128 + row] = make_float2(s1, s2);
+        __syncthreads();
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 v = sSt[t * 128 + row];
+          s1 += v.x; s2 += v.y;
+        }
+        const float ms = s1 * (1.0f / C);
+        const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        ln_a = rstd;
+        ln_b = -(k0 + ms) * rstd;
+      }
+      mbar_wait(&mma_done, item & 1);
+      tc_fence_after();
+      // the MMAs have read the weight buffer (and, for the last group, the token tile): refill both for the next item
+      {
+        const bool last_g = g == K::NG - 1;
+        const long long next = tile + gridDim.x;
+        if (tid == 0) {
+          if (!last_g) load_w(g + 1);
+          else if (next < tiles) load_w(0);
+        }
+        if (last_g && next < tiles) gather(next);
+      }
+      // ---- drain: qkv[row][n] = a * D + b * s_n + bf_n  -> fp16 operand tiles
+      {
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + quarter * K::QC;
+        const float2* hc = sHc + g * K::NGC + quarter * K::QC;
+        const int wi = row >> 6, t = row & 63;
+        auto put4 = [&](const uint32_t* v, int c0) {   // 4 consecutive accumulator columns starting at quarter-local c0
+          const int n = quarter * K::QC + c0;
+          const int m = n / K::BR;
+          const int j = n - m * K::BR;
+          const int hl = j / HD, d = j - hl * HD;
+          float f[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 cst = hc[c0 + e];
+            f[e] = fmaf(ln_a, __uint_as_float(v[e]), fmaf(ln_b, cst.x, cst.y));
+          }
+          const uint32_t dst = sQKV + (m * K::NU + wi * GH + hl) * K::UNIT_BYTES + op_off<RB>(t, d >> 3) + (d & 7) * 2;
+          sts64(dst, pack_half2(f[0], f[1]), pack_half2(f[2], f[3]));
+        };
+        int c0 = 0;
+#pragma unroll
+        for (; c0 + 8 <= K::QC; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(t_lane + c0, v);
+          tmem_ld_wait();
+          put4(v, c0);
+          put4(v + 4, c0 + 4);
+        }
+        if constexpr (K::QC % 8 != 0) {
+          uint32_t v[4];
+          tmem_ld4(t_lane + (K::QC / 8) * 8, v);
+          tmem_ld_wait();
+          put4(v, (K::QC / 8) * 8);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();   // (B) q/k/v operand tiles complete
+      // ---- core
+      {
+        const int head = g * GH + u_hl;
+        if (head != tb_head) {
+          const float* tbl = sTbl + head * TBL;
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (lg - 2 * ltq - e + 7)];
+          tb_head = head;
+        }
+        const long long win = tile * 2 + u_wi;
+        if (win < nwin) {
+          const int wimg = static_cast<int>(win % nW);
+          const int wr = wimg / nWc, wc = wimg - wr * nWc;
+          const bool mrow = p.shift > 0 && wr == nWr - 1;
+          const bool mcol = p.shift > 0 && wc == nWc - 1;
+          const uint32_t q_h = sQKV + (0 * K::NU + unit) * K::UNIT_BYTES;
+          const uint32_t k_h = sQKV + (1 * K::NU + unit) * K::UNIT_BYTES;
+          const uint32_t v_h = sQKV + (2 * K::NU + unit) * K::UNIT_BYTES;
+          if (mrow || mcol) attn_tiles<HD, MT, true>(q_h, k_h, v_h, mbase, lane, tb, mrow, mcol);
+          else attn_tiles<HD, MT, false>(q_h, k_h, v_h, mbase, lane, tb, false, false);
+        }
+      }
+      __syncthreads();   // (C) O rows of every unit parked in the q tiles
+      // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map)
+#pragma unroll
+      for (int s = 0; s < (128 * K::VPT + NTHREADS - 1) / NTHREADS; ++s) {
+        const int i = tid + s * NTHREADS;
+        if (i < 128 * K::VPT) {
+          const int t128 = i / K::VPT, vv = i - t128 * K::VPT;
+          const int hl = vv / K::VPH, v = vv - hl * K::VPH;
+          const int d0 = v * K::VEC;
+          const long long gr = token_row(tile, t128);
+          if (gr >= 0) {
+            const uint32_t src = sQKV + ((t128 >> 6) * GH + hl) * K::UNIT_BYTES + op_off<RB>(t128 & 63, d0 >> 3) + (d0 & 7) * 2;
+            __half* dst = p.out + gr * C + g * K::BR + vv * K::VEC;
+            if constexpr (K::VEC == 8) {
+              *reinterpret_cast<uint4*>(dst) = lds128(src);
+            } else {
+              uint2 o;
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(src) : "memory");
+              *reinterpret_cast<uint2*>(dst) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, K::TMEM_COLS);
+  }
+}
+
+// ---- pre-pack: permuted rows, W * gamma (q rows additionally * qscale), row sums of the rounded weights, folded bias
+__global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __restrict__ bqkv, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __half* __restrict__ wp, float2* __restrict__ hconst, int C, int HD,
+                                 int GH, float qscale) {
+  const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pr >= 3 * C) return;
+  const int BR = GH * HD, NGC = 3 * BR;
+  const int g = pr / NGC, within = pr - g * NGC;
+  const int m = within / BR, j = within - m * BR;
+  const int o = m * C + g * BR + j;   // original row: [q|k|v][head][d]
+  const float sc = m == 0 ? qscale : 1.f;
+  float s = 0.f, bb = 0.f;
+  for (int k = lane; k < C; k += 32) {
+    const float w = wqkv[static_cast<size_t>(o) * C + k];
+    const __half h = __float2half_rn(w * gamma[k] * sc);
+    wp[static_cast<size_t>(pr) * C + k] = h;
+    s += __half2float(h);
+    bb = fmaf(w, beta[k], bb);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    bb += __shfl_xor_sync(0xffffffffu, bb, off);
+  }
+  if (lane == 0) hconst[pr] = make_float2(s, (bb + (bqkv ? bqkv[o] : 0.f)) * sc);
+}
+
+template <int C, int GH>
+int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H, int W, int shift, cudaStream_t stream) {
+  using K = FCfg<C, GH>;
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    SUNET_CUDA(cudaFuncSetAttribute(attn_fused_kernel<C, GH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    configured = true;
+  }
+  FParams prm;
+  prm.x = x; prm.out = out;
+  prm.hconst = reinterpret_cast<const float2*>(p.hconst);
+  prm.table = p.table;
+  prm.B = B; prm.H = H; prm.W = W; prm.shift = shift;
+  const long long nwin = static_cast<long long>(B) * (H / 8) * (W / 8);
+  const long long tiles = (nwin + 1) / 2;
+  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
+  attn_fused_kernel<C, GH><<<grid, NTHREADS, K::SMEM, stream>>>(p.tmW, prm);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+
+constexpr int group_heads(int C) { return C == 96 ? 8 : 2; }
+
+}  // namespace
+
+bool attn_fused_supported(int C, int heads) { return heads == 8 && (C == 96 || C == 192); }
+
+int attn_fused_prepack(AttnFusedPack* p, int C, int heads, float qscale, const float* gamma, const float* beta, const float* wqkv,
+                       const float* bqkv, const float* table, cudaStream_t stream) {
+  if (!attn_fused_supported(C, heads)) return fail(SUNET_E_SHAPE, "fused attention: C=%d heads=%d not instantiated", C, heads);
+  if (!p->w || !p->hconst) return fail(SUNET_E_ARG, "fused attention: pack buffers not allocated");
+  p->C = C; p->heads = heads; p->table = table;
+  const int GH = group_heads(C), HD = C / heads;
+  attn_fold_kernel<<<(3 * C + 7) / 8, 256, 0, stream>>>(wqkv, bqkv, gamma, beta, p->w, reinterpret_cast<float2*>(p->hconst), C, HD, GH, qscale);
+  SUNET_CHECK_LAUNCH();
+  const int NGC = 3 * GH * HD;
+  const int NPM = NGC > 256 ? NGC / 3 : NGC;
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW, p->w, C, 3 * C, C, NPM));
+  return 0;
+}
+
+int attn_fused_launch(const AttnFusedPack& p, const __half* x, __half* out, int B, int H, int W, int shift, cudaStream_t stream) {
+  if (H % 8 || W % 8) return fail(SUNET_E_SHAPE, "fused attention: token grid %dx%d must be a multiple of the 8x8 window", H, W);
+  if (shift != 0 && shift != 4) return fail(SUNET_E_ARG, "fused attention: shift %d unsupported (0 or 4)", shift);
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "fused attention: x/out must be 16-byte aligned");
+  if (B <= 0) return fail(SUNET_E_SHAPE, "fused attention: batch %d", B);
+  switch (p.C) {
+    case 96: return launch_t<96, group_heads(96)>(p, x, out, B, H, W, shift, stream);
+    case 192: return launch_t<192, group_heads(192)>(p, x, out, B, H, W, shift, stream);
+    default: return fail(SUNET_E_SHAPE, "fused attention: C=%d not instantiated", p.C);
+  }
+}
+
+}  // namespace sunet

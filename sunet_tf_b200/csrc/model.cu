@@ -12,6 +12,7 @@
 
 #include "../../include/sunet_b200.h"
 #include "attn_core.cuh"
+#include "attn_fused.cuh"
 #include "elementwise.cuh"
 #include "error.h"
 #include "gemm.cuh"
@@ -67,7 +68,7 @@ struct ScratchMark {  // stack discipline
   ~ScratchMark() { s.off = saved; }
 };
 
-enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8, K_MLP_FUSED = 9 };
+enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8, K_MLP_FUSED = 9, K_ATTN_FUSED = 10 };
 
 struct ProfRec {
   int kind;
@@ -194,6 +195,8 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
   MlpPack mlp;
   MlpFusedPack mf;      // norm2 + mlp + residual as one kernel (dims with a fused instantiation)
   bool use_mf = false;
+  AttnFusedPack af;     // norm1 + shift/partition + qkv + attention core + reverse/un-shift as one kernel
+  bool use_af = false;
   int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, int heads_, int shift_, double qk_scale,
            cudaStream_t s) {
     dim = dim_; H = H_; W = W_; heads = heads_; shift = shift_;
@@ -205,6 +208,17 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     SUNET_TRY(copy_vec(ar, P, pre + "norm2.weight", dim, &g2, s));
     SUNET_TRY(copy_vec(ar, P, pre + "norm2.bias", dim, &b2, s));
     SUNET_TRY(attn.pack(ar, P, pre + "attn.", dim, heads, qk_scale, s));
+    use_af = attn_fused_supported(dim, heads) && getenv("SUNET_NO_FUSED_ATTN") == nullptr;
+    if (use_af) {
+      const float *gw, *gb, *wq, *bq = nullptr;
+      SUNET_TRY(P.get(pre + "norm1.weight", dim, &gw));
+      SUNET_TRY(P.get(pre + "norm1.bias", dim, &gb));
+      SUNET_TRY(P.get(pre + "attn.qkv.weight", static_cast<int64_t>(3) * dim * dim, &wq));
+      if (P.has(pre + "attn.qkv.bias")) SUNET_TRY(P.get(pre + "attn.qkv.bias", 3 * dim, &bq));
+      SUNET_TRY(ar.alloc_t(&af.w, static_cast<size_t>(3) * dim * dim));
+      SUNET_TRY(ar.alloc_t(&af.hconst, static_cast<size_t>(6) * dim));
+      SUNET_TRY(attn_fused_prepack(&af, dim, heads, attn.scale * 1.4426950408889634f, gw, gb, wq, bq, attn.table, s));
+    }
     use_mf = mlp_fused_supported(dim) && getenv("SUNET_NO_FUSED_MLP") == nullptr;
     if (use_mf) {
       const float *gw, *gb, *w1, *b1, *w2, *b2v;
@@ -229,16 +243,21 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     ScratchMark mk(c.sc);
     const int64_t M = static_cast<int64_t>(B) * H * W;
     __half *T, *QKV, *O, *Hd;
-    SUNET_TRY(c.sc.take_t(&T, M * dim));
-    SUNET_TRY(c.sc.take_t(&QKV, M * 3 * dim));
+    SUNET_TRY(c.sc.take_t(&T, (use_af && use_mf) ? 0 : M * dim));
+    SUNET_TRY(c.sc.take_t(&QKV, use_af ? 0 : M * 3 * dim));
     SUNET_TRY(c.sc.take_t(&O, M * dim));
     SUNET_TRY(c.sc.take_t(&Hd, use_mf ? 0 : M * 4 * dim));
-    RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                       // :233
-    SUNET_TRY(run_linear(c, attn.qkv, T, dim, M, QKV, 3 * dim));                               // :114
-    AttnCoreArgs a;
-    a.qkv = QKV; a.ld = 3 * dim; a.out = O; a.ldo = dim; a.B = B; a.H = H; a.W = W; a.C = dim; a.heads = heads;
-    a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
-    RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_launch(a, c.stream));               // :118-135, :236-257
+    if (use_af) {
+      RUN(c, K_ATTN_FUSED, 6.0 * M * dim * dim + 256.0 * M * dim, 4.0 * M * dim,
+          attn_fused_launch(af, x_in, O, B, H, W, shift, c.stream));                             // :233-257 minus proj
+    } else {
+      RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                     // :233
+      SUNET_TRY(run_linear(c, attn.qkv, T, dim, M, QKV, 3 * dim));                             // :114
+      AttnCoreArgs a;
+      a.qkv = QKV; a.ld = 3 * dim; a.out = O; a.ldo = dim; a.B = B; a.H = H; a.W = W; a.C = dim; a.heads = heads;
+      a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
+      RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_launch(a, c.stream));             // :118-135, :236-257
+    }
     SUNET_TRY(run_linear(c, attn.proj, O, dim, M, x_out, dim, ACT_NONE, nullptr, x_in, dim));   // :136, :261
     if (use_mf) {
       RUN(c, K_MLP_FUSED, 16.0 * M * dim * dim, 4.0 * M * dim, mlp_fused_launch(mf, x_out, x_out, M, c.stream));               // :262 (norm2, mlp, +res)
