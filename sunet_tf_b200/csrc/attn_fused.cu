@@ -82,7 +82,6 @@ struct FCfg {
   static constexpr int WPU = 16 / NU;            // warps per unit
   static constexpr int MT = 4 / WPU;             // 16-row query tiles per warp
   static constexpr int QC = NGC / 4;             // accumulator columns drained by one column-quarter
-  static constexpr int QCH = C / 32;             // 16-byte chunks of a token row per quarter (statistics pass)
   static constexpr int CPR = C / 8;              // 16-byte chunks per token row
   static constexpr int VEC = (HD % 8 == 0) ? 8 : 4;
   static constexpr int VPH = HD / VEC;
@@ -243,6 +242,38 @@ __device__ __forceinline__ void attn_tiles(uint32_t q_h, uint32_t k_h, uint32_t 
   }
 }
 
+// Drain of one column quarter Q of the accumulator for one token row: qkv = a * D + b * s_n + bf_n -> fp16, written as
+// 8-byte groups into the (q|k|v, window, head) operand tiles.  Everything that depends on the column is a compile-time
+// constant; TMEM loads are issued in batches of 24 / 36 columns per wait.
+template <typename K, int Q>
+__device__ __forceinline__ void drain_quarter(uint32_t t_lane, const float2* hc, uint32_t d_base, uint32_t d_sx, float a, float b) {
+  constexpr int QC = K::QC;
+  constexpr int BATCH = QC % 24 == 0 ? 24 : QC;   // columns per tcgen05.wait::ld
+  static_assert(BATCH % 4 == 0 && BATCH <= 40, "drain batch");
+#pragma unroll
+  for (int c0 = 0; c0 < QC; c0 += BATCH) {
+    uint32_t v[BATCH];
+#pragma unroll
+    for (int i = 0; i + 8 <= BATCH; i += 8) tmem_ld8(t_lane + Q * QC + c0 + i, *reinterpret_cast<uint32_t(*)[8]>(&v[i]));
+    if constexpr (BATCH % 8 != 0) tmem_ld4(t_lane + Q * QC + c0 + (BATCH / 8) * 8, *reinterpret_cast<uint32_t(*)[4]>(&v[(BATCH / 8) * 8]));
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < BATCH; i += 4) {
+      const int n = Q * QC + c0 + i;             // compile-time after unrolling
+      const int m = n / K::BR, j = n % K::BR;
+      const int hl = j / K::HD, d = j % K::HD;
+      const float4 c01 = *reinterpret_cast<const float4*>(hc + n);       // (s, bf) of columns n, n+1
+      const float4 c23 = *reinterpret_cast<const float4*>(hc + n + 2);
+      const float f0 = fmaf(a, __uint_as_float(v[i + 0]), fmaf(b, c01.x, c01.y));
+      const float f1 = fmaf(a, __uint_as_float(v[i + 1]), fmaf(b, c01.z, c01.w));
+      const float f2 = fmaf(a, __uint_as_float(v[i + 2]), fmaf(b, c23.x, c23.y));
+      const float f3 = fmaf(a, __uint_as_float(v[i + 3]), fmaf(b, c23.z, c23.w));
+      const uint32_t dst = d_base + (m * K::NU + hl) * K::UNIT_BYTES + (d & 7) * 2 + ((static_cast<uint32_t>(d >> 3) << 4) ^ d_sx);
+      sts64(dst, pack_half2(f0, f1), pack_half2(f2, f3));
+    }
+  }
+}
+
 struct FParams {
   const __half* x;
   __half* out;
@@ -306,33 +337,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   const long long nwin = static_cast<long long>(p.B) * nW;
   const long long tiles = (nwin + 1) >> 1;
 
-  // global token row of window token (wi, tt) of `tile`, or -1 past the last window
-  auto token_row = [&](long long tile, int t128) -> long long {
-    const long long win = tile * 2 + (t128 >> 6);
-    if (win >= nwin) return -1;
-    const int b = static_cast<int>(win / nW);
-    const int wimg = static_cast<int>(win - static_cast<long long>(b) * nW);
-    const int wr = wimg / nWc, wc = wimg - wr * nWc;
-    const int tt = t128 & 63;
-    int r = wr * 8 + (tt >> 3) + p.shift, c = wc * 8 + (tt & 7) + p.shift;
+  // Thread <-> token mapping of the gather / statistics / scatter passes: token tk = tid >> 2 of the tile (window
+  // wi = warp >> 3, the same window whose (window, head) units this warp runs in the core), 16-byte part tid & 3.
+  const int tk = tid >> 2, part = tid & 3;
+  const int wi = warp >> 3, tt = tk & 63;
+  // geometry of this thread's window of a tile: global row of token tk (or -1 past the last window) and the mask flags
+  struct Geo { int row; bool mrow, mcol; };
+  auto tile_geo = [&](long long tile) {
+    Geo gg;
+    const unsigned win = static_cast<unsigned>(tile) * 2u + wi;
+    const unsigned b = win / static_cast<unsigned>(nW);
+    const unsigned wimg = win - b * nW;
+    const unsigned wr = wimg / static_cast<unsigned>(nWc), wc = wimg - wr * nWc;
+    int r = static_cast<int>(wr) * 8 + p.shift + (tt >> 3), c = static_cast<int>(wc) * 8 + p.shift + (tt & 7);
     if (r >= p.H) r -= p.H;
     if (c >= p.W) c -= p.W;
-    return (static_cast<long long>(b) * p.H + r) * p.W + c;
+    gg.row = win < static_cast<unsigned>(nwin) ? (static_cast<int>(b) * p.H + r) * p.W + c : -1;
+    gg.mrow = p.shift > 0 && static_cast<int>(wr) == nWr - 1;
+    gg.mcol = p.shift > 0 && static_cast<int>(wc) == nWc - 1;
+    return gg;
   };
-  auto gather = [&](long long tile) {   // every thread: its share of the 128 x C/8 16-byte chunks
+  // 16-byte chunk cg = part + 4 j of token tk inside the SW128 token tile
+  auto x_chunk = [&](int j) -> uint32_t {
+    const int cg = part + 4 * j;
+    return sX + (cg >> 3) * 16384 + tk * 128 + ((static_cast<uint32_t>(cg & 7) ^ static_cast<uint32_t>(tk & 7)) << 4);
+  };
+  auto gather = [&](const Geo& gg) {
+    const __half* src = p.x + static_cast<long long>(gg.row) * C + part * 8;
 #pragma unroll
-    for (int s = 0; s < (128 * K::CPR + NTHREADS - 1) / NTHREADS; ++s) {
-      const int i = tid + s * NTHREADS;
-      if (i < 128 * K::CPR) {
-        const int t = i / K::CPR, cg = i - t * K::CPR;
-        const int kb = cg >> 3, ch = cg & 7;
-        const uint32_t dst = sX + kb * 16384 + t * 128 + ((ch ^ (t & 7)) << 4);
-        const long long gr = token_row(tile, t);
-        if (gr >= 0) cp_async16(dst, p.x + gr * C + cg * 8);
-        else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-      }
+    for (int j = 0; j < K::CPR / 4; ++j) {
+      if (gg.row >= 0) cp_async16(x_chunk(j), src + j * 32);
+      else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(x_chunk(j)), "r"(0u) : "memory");
     }
     cp_async_commit();
+  };
+  // LayerNorm statistics of token tk (fp32, shifted one-pass variance) -> (rstd, -mean * rstd) in sSt[tk]
+  auto stats = [&]() {
+    const uint4 first = lds128(sX + tk * 128 + (static_cast<uint32_t>(tk & 7) << 4));
+    const float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(first.x & 0xffffu)));
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < K::CPR / 4; ++j) {
+      const uint4 v = lds128(x_chunk(j));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h2[t]);
+        const float d0 = f.x - k0, d1 = f.y - k0;
+        s1 += d0 + d1;
+        s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+      }
+    }
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    if (part == 0) {
+      const float ms = s1 * (1.0f / C);
+      const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      sSt[tk] = make_float2(rstd, -(k0 + ms) * rstd);
+    }
   };
   auto load_w = [&](int g) {   // thread 0: the folded qkv weights of head group g -> smem, [kb][sub-tile][NPM rows][64] SW128
     mbar_arrive_expect_tx(&w_full, K::W_BYTES);
@@ -342,132 +407,87 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       for (int m = 0; m < K::NMMA; ++m)
         tma_load_2d(smem + K::OFF_W + (kb * K::NMMA + m) * K::NPM * 128, &tmW, &w_full, kb * 64, g * K::NGC + m * K::NPM);
   };
+  auto issue_mma = [&](uint32_t it) {   // thread 0: D[128 x NGC] = X * Wg^T for work item `it`
+    mbar_wait(&w_full, it & 1);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_f16(128, K::NPM);
+#pragma unroll
+    for (int kb = 0; kb < K::KB; ++kb) {
+      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
+      const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
+#pragma unroll
+      for (int k = 0; k < ksteps; ++k)
+#pragma unroll
+        for (int m = 0; m < K::NMMA; ++m) {
+          const uint64_t bdesc = umma_desc_sw128(sW + (kb * K::NMMA + m) * K::NPM * 128);
+          umma_f16_ss(tmem_base + m * K::NPM, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+        }
+    }
+    tc_commit(&mma_done);
+  };
 
   // this warp's (window, head) unit of the core pass
-  const int unit = warp % K::NU;
-  const int u_wi = unit / GH, u_hl = unit - u_wi * GH;
-  const int mbase = (warp / K::NU) * MT;
+  const int u_hl = (warp & 7) % GH;
+  const int unit = wi * GH + u_hl;
+  const int mbase = ((warp & 7) / GH) * MT;
   const int lg = lane >> 2, ltq = lane & 3;
   float tb[2][2 * MT + 7];
   int tb_head = -1;
+  // drain constants: token row `row` of the tile, column quarter `quarter`
+  const uint32_t d_base = sQKV + ((row >> 6) * GH) * K::UNIT_BYTES + (row & 63) * RB;
+  const uint32_t d_sx = (RB == 32 ? ((row >> 2) & 1) : ((row >> 1) & 3)) << 4;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
 
   uint32_t item = 0;
+  Geo geo = tile_geo(blockIdx.x);
   if (static_cast<long long>(blockIdx.x) < tiles) {
     if (tid == 0) load_w(0);
-    gather(blockIdx.x);
+    gather(geo);
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) issue_mma(0);
+    __syncwarp();
+    stats();
+    __syncthreads();
   }
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    float ln_a = 0.f, ln_b = 0.f;
+    const long long next_tile = tile + gridDim.x;
+    const bool has_next_tile = next_tile < tiles;
+    Geo geo_next = geo;
+    const float2 ln = sSt[row];   // (rstd, -mean * rstd) of this thread's drain row
 #pragma unroll 1
     for (int g = 0; g < K::NG; ++g, ++item) {
-      if (g == 0) {
+      const bool last_g = g == K::NG - 1;
+      const bool has_next = !last_g || has_next_tile;
+      mbar_wait(&mma_done, item & 1);
+      tc_fence_after();
+      // the MMAs of this item have read the weight buffer (and, for the last group, the token tile): refill them
+      if (tid == 0 && has_next) load_w(last_g ? 0 : g + 1);
+      if (last_g && has_next_tile) {
+        geo_next = tile_geo(next_tile);
+        gather(geo_next);
+      }
+      // ---- drain: qkv[row][n] = rstd * D - rstd * mean * s_n + bf_n  -> fp16 operand tiles
+      {
+        const float2* hc = sHc + g * K::NGC;
+        switch (quarter) {
+          case 0: drain_quarter<K, 0>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
+          case 1: drain_quarter<K, 1>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
+          case 2: drain_quarter<K, 2>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
+          default: drain_quarter<K, 3>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
+        }
+      }
+      if (last_g && has_next_tile) {
         cp_async_wait_all();
         fence_proxy_async_smem();
       }
       tc_fence_before();
-      __syncthreads();   // (A) token tile landed; q/k/v operand tiles and the accumulator are free again
-      if (tid == 0) {
-        mbar_wait(&w_full, item & 1);
-        tc_fence_after();
-        const uint32_t idesc = umma_idesc_f16(128, K::NPM);
-#pragma unroll
-        for (int kb = 0; kb < K::KB; ++kb) {
-          const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
-          const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
-#pragma unroll
-          for (int k = 0; k < ksteps; ++k)
-#pragma unroll
-            for (int m = 0; m < K::NMMA; ++m) {
-              const uint64_t bdesc = umma_desc_sw128(sW + (kb * K::NMMA + m) * K::NPM * 128);
-              umma_f16_ss(tmem_base + m * K::NPM, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-            }
-        }
-        tc_commit(&mma_done);
-      }
+      __syncthreads();   // (B) q/k/v operand tiles complete, accumulator drained, next token tile landed
+      if (tid == 0 && has_next) issue_mma(item + 1);   // runs on the tensor pipe while the core below runs on the CUDA cores
       __syncwarp();
-      if (g == 0) {
-        // LayerNorm statistics of this thread's row (fp32, shifted one-pass variance), combined over the 4 column quarters
-        float s1 = 0.f, s2 = 0.f;
-        const uint32_t sw = static_cast<uint32_t>(row & 7);
-        const uint4 first = lds128(sX + row * 128 + (sw << 4));
-        const float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(first.x & 0xffffu)));
-#pragma unroll
-        for (int i = 0; i < K::QCH; ++i) {
-          const int gi = quarter * K::QCH + i;
-          const uint4 v = lds128(sX + (gi >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4));
-          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 f = __half22float2(h2[t]);
-            const float d0 = f.x - k0, d1 = f.y - k0;
-            s1 += d0 + d1;
-            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-          }
-        }
-        sSt[quarter * 128 + row] = make_float2(s1, s2);
-        __syncthreads();
-        s1 = 0.f; s2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 v = sSt[t * 128 + row];
-          s1 += v.x; s2 += v.y;
-        }
-        const float ms = s1 * (1.0f / C);
-        const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
-        const float rstd = rsqrtf(var + 1e-5f);
-        ln_a = rstd;
-        ln_b = -(k0 + ms) * rstd;
-      }
-      mbar_wait(&mma_done, item & 1);
-      tc_fence_after();
-      // the MMAs have read the weight buffer (and, for the last group, the token tile): refill both for the next item
-      {
-        const bool last_g = g == K::NG - 1;
-        const long long next = tile + gridDim.x;
-        if (tid == 0) {
-          if (!last_g) load_w(g + 1);
-          else if (next < tiles) load_w(0);
-        }
-        if (last_g && next < tiles) gather(next);
-      }
-      // ---- drain: qkv[row][n] = a * D + b * s_n + bf_n  -> fp16 operand tiles
-      {
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + quarter * K::QC;
-        const float2* hc = sHc + g * K::NGC + quarter * K::QC;
-        const int wi = row >> 6, t = row & 63;
-        auto put4 = [&](const uint32_t* v, int c0) {   // 4 consecutive accumulator columns starting at quarter-local c0
-          const int n = quarter * K::QC + c0;
-          const int m = n / K::BR;
-          const int j = n - m * K::BR;
-          const int hl = j / HD, d = j - hl * HD;
-          float f[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 cst = hc[c0 + e];
-            f[e] = fmaf(ln_a, __uint_as_float(v[e]), fmaf(ln_b, cst.x, cst.y));
-          }
-          const uint32_t dst = sQKV + (m * K::NU + wi * GH + hl) * K::UNIT_BYTES + op_off<RB>(t, d >> 3) + (d & 7) * 2;
-          sts64(dst, pack_half2(f[0], f[1]), pack_half2(f[2], f[3]));
-        };
-        int c0 = 0;
-#pragma unroll
-        for (; c0 + 8 <= K::QC; c0 += 8) {
-          uint32_t v[8];
-          tmem_ld8(t_lane + c0, v);
-          tmem_ld_wait();
-          put4(v, c0);
-          put4(v + 4, c0 + 4);
-        }
-        if constexpr (K::QC % 8 != 0) {
-          uint32_t v[4];
-          tmem_ld4(t_lane + (K::QC / 8) * 8, v);
-          tmem_ld_wait();
-          put4(v, (K::QC / 8) * 8);
-        }
-      }
-      tc_fence_before();
-      __syncthreads();   // (B) q/k/v operand tiles complete
+      if (last_g && has_next_tile) stats();            // next tile's LayerNorm statistics (read after barrier (D))
       // ---- core
       {
         const int head = g * GH + u_hl;
@@ -479,45 +499,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
             for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (lg - 2 * ltq - e + 7)];
           tb_head = head;
         }
-        const long long win = tile * 2 + u_wi;
-        if (win < nwin) {
-          const int wimg = static_cast<int>(win % nW);
-          const int wr = wimg / nWc, wc = wimg - wr * nWc;
-          const bool mrow = p.shift > 0 && wr == nWr - 1;
-          const bool mcol = p.shift > 0 && wc == nWc - 1;
+        if (geo.row >= 0) {   // uniform per warp: all its tokens belong to one window
           const uint32_t q_h = sQKV + (0 * K::NU + unit) * K::UNIT_BYTES;
           const uint32_t k_h = sQKV + (1 * K::NU + unit) * K::UNIT_BYTES;
           const uint32_t v_h = sQKV + (2 * K::NU + unit) * K::UNIT_BYTES;
-          if (mrow || mcol) attn_tiles<HD, MT, true>(q_h, k_h, v_h, mbase, lane, tb, mrow, mcol);
+          if (geo.mrow || geo.mcol) attn_tiles<HD, MT, true>(q_h, k_h, v_h, mbase, lane, tb, geo.mrow, geo.mcol);
           else attn_tiles<HD, MT, false>(q_h, k_h, v_h, mbase, lane, tb, false, false);
         }
       }
       __syncthreads();   // (C) O rows of every unit parked in the q tiles
-      // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map)
+      // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map): the 4 threads
+      // of a token write consecutive vectors, so every store instruction covers whole 32-byte sectors
+      if (geo.row >= 0) {
+        __half* dst = p.out + static_cast<long long>(geo.row) * C + g * K::BR;
 #pragma unroll
-      for (int s = 0; s < (128 * K::VPT + NTHREADS - 1) / NTHREADS; ++s) {
-        const int i = tid + s * NTHREADS;
-        if (i < 128 * K::VPT) {
-          const int t128 = i / K::VPT, vv = i - t128 * K::VPT;
-          const int hl = vv / K::VPH, v = vv - hl * K::VPH;
-          const int d0 = v * K::VEC;
-          const long long gr = token_row(tile, t128);
-          if (gr >= 0) {
-            const uint32_t src = sQKV + ((t128 >> 6) * GH + hl) * K::UNIT_BYTES + op_off<RB>(t128 & 63, d0 >> 3) + (d0 & 7) * 2;
-            __half* dst = p.out + gr * C + g * K::BR + vv * K::VEC;
+        for (int j = 0; j < (K::VPT + 3) / 4; ++j) {
+          const int vv = part + 4 * j;
+          if (K::VPT % 4 == 0 || vv < K::VPT) {
+            const int hl = vv / K::VPH, d0 = (vv - hl * K::VPH) * K::VEC;
+            const uint32_t src = sQKV + (wi * GH + hl) * K::UNIT_BYTES + op_off<RB>(tt, d0 >> 3) + (d0 & 7) * 2;
             if constexpr (K::VEC == 8) {
-              *reinterpret_cast<uint4*>(dst) = lds128(src);
+              *reinterpret_cast<uint4*>(dst + vv * 8) = lds128(src);
             } else {
               uint2 o;
               asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(src) : "memory");
-              *reinterpret_cast<uint2*>(dst) = o;
+              *reinterpret_cast<uint2*>(dst + vv * 4) = o;
             }
           }
         }
       }
+      __syncthreads();   // (D) q tiles free for the next drain; next tile's statistics visible
     }
+    geo = geo_next;
   }
-  cp_async_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -571,6 +585,7 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   prm.table = p.table;
   prm.B = B; prm.H = H; prm.W = W; prm.shift = shift;
   const long long nwin = static_cast<long long>(B) * (H / 8) * (W / 8);
+  if (nwin > 0x3fffffffLL || static_cast<long long>(B) * H * W > 0x7fffffffLL) return fail(SUNET_E_SHAPE, "fused attention: too many tokens for 32-bit row indices");
   const long long tiles = (nwin + 1) / 2;
   const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
   attn_fused_kernel<C, GH><<<grid, NTHREADS, K::SMEM, stream>>>(p.tmW, prm);
