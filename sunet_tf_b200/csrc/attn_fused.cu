@@ -11,14 +11,17 @@
 //   gather : the 128 token rows are fetched through the roll+partition index map with 16-byte cp.async straight into
 //            the 128-byte-swizzled K-major layout tcgen05.mma reads (window_partition / torch.roll are address arithmetic)
 //   QKV    : D[128 x 3*GH*hd] = X[128 x C] * Wg^T on tcgen05 (fp16 in, fp32 accumulators in TMEM); the weights of the
-//            current head group arrive by TMA.  LayerNorm is folded: Wg = W * gamma (pre-pack), and
-//            qkv = rstd * D - rstd * mu * rowsum(Wg) + (b + W beta), applied when the accumulators are drained
+//            current head group arrive by TMA.  norm1 runs in place on the gathered tile (fp32 statistics, 4 threads per
+//            token); its affine part is folded into the weights at pre-pack: Wg = W * gamma, bias = b + W beta
 //   drain  : TMEM -> registers -> fp16 q/k/v operand tiles in shared memory (head_dim padded to 16/32, XOR-swizzled rows)
 //   core   : per (window, head): S = q k^T + bias (+ closed-form mask), exp2 softmax, O = P V on mma.sync.m16n8k16 with
 //            register-resident S/P (K = 12/24: a 64x64xhd problem per head is below any tcgen05 tile), O parked in the q rows
 //   scatter: O rows go back through the same index map (window_reverse + un-roll).
 // C = 96 handles all 8 heads per pass (288 accumulator columns); C = 192 walks 4 groups of 2 heads (144 columns).
 #include "attn_fused.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "error.h"
 #include "gemm.cuh"
@@ -49,7 +52,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float ex2(float x) {
+__device__ __forceinline__ float ex2(float x) {   // (ex2.approx.f16x2 becomes two MUFU.EX2.F16: same MUFU issue rate, measured)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
@@ -94,8 +97,7 @@ struct FCfg {
   static constexpr int OFF_QKV = OFF_W + W_BYTES;
   static constexpr int OFF_TBL = OFF_QKV + QKV_BYTES;
   static constexpr int OFF_HC = OFF_TBL + HEADS * TBL * 4;
-  static constexpr int OFF_ST = OFF_HC + 3 * C * 8;
-  static constexpr int SMEM = OFF_ST + 4 * 128 * 8 + 1024;
+  static constexpr int SMEM = OFF_HC + 3 * C * 4 + 1024;
   static constexpr uint32_t TMEM_COLS = NGC <= 256 ? 256 : 512;
   static_assert(C % 32 == 0 && HD % 4 == 0 && QC % 4 == 0, "column slices must be whole 4-column groups");
   static_assert((NPM * 128) % 1024 == 0 && NPM % 16 == 0 && NPM <= 256, "weight sub-tiles must be whole swizzle atoms");
@@ -176,15 +178,16 @@ __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float sum0 = 0.f, sum1 = 0.f;
+  uint32_t pk[8][2];   // fp16 probabilities: [nt][0] = row i0 (keys 2tq, 2tq+1 of key row nt), [nt][1] = row i1
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = ex2(s[nt][0] - m0);
-    s[nt][1] = ex2(s[nt][1] - m0);
-    s[nt][2] = ex2(s[nt][2] - m1);
-    s[nt][3] = ex2(s[nt][3] - m1);
+    pk[nt][0] = pack_half2(ex2(s[nt][0] - m0), ex2(s[nt][1] - m0));
+    pk[nt][1] = pack_half2(ex2(s[nt][2] - m1), ex2(s[nt][3] - m1));
     if constexpr (!MMA_SUM) {
-      sum0 += s[nt][0] + s[nt][1];
-      sum1 += s[nt][2] + s[nt][3];
+      const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&pk[nt][0]));
+      const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&pk[nt][1]));
+      sum0 += p0.x + p0.y;
+      sum1 += p1.x + p1.y;
     }
   }
   float o[NO][4];
@@ -192,11 +195,7 @@ __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v
   for (int n = 0; n < NO; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    uint32_t pa[4];
-    pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    const uint32_t pa[4] = {pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1]};
 #pragma unroll
     for (int n = 0; n < NO; n += 2) {
       uint32_t vb[4];   // transposed 8x8 loads of V[key][d]: (keys lo, n), (keys hi, n), (keys lo, n+1), (keys hi, n+1)
@@ -242,14 +241,14 @@ __device__ __forceinline__ void attn_tiles(uint32_t q_h, uint32_t k_h, uint32_t 
   }
 }
 
-// Drain of one column quarter Q of the accumulator for one token row: qkv = a * D + b * s_n + bf_n -> fp16, written as
-// 8-byte groups into the (q|k|v, window, head) operand tiles.  Everything that depends on the column is a compile-time
-// constant; TMEM loads are issued in batches of 24 / 36 columns per wait.
+// Drain of one column quarter Q of the accumulator for one token row: qkv = D + bias -> fp16, written as 8-byte groups
+// into the (q|k|v, window, head) operand tiles.  Everything that depends on the column is a compile-time constant; TMEM
+// loads are issued in batches of 24 / 36 columns per wait.
 template <typename K, int Q>
-__device__ __forceinline__ void drain_quarter(uint32_t t_lane, const float2* hc, uint32_t d_base, uint32_t d_sx, float a, float b) {
+__device__ __forceinline__ void drain_quarter(uint32_t t_lane, const float* bf, uint32_t d_base, uint32_t d_sx) {
   constexpr int QC = K::QC;
-  constexpr int BATCH = QC % 24 == 0 ? 24 : QC;   // columns per tcgen05.wait::ld
-  static_assert(BATCH % 4 == 0 && BATCH <= 40, "drain batch");
+  constexpr int BATCH = QC > 40 ? QC / 2 : QC;     // columns in flight per tcgen05.wait::ld (register budget)
+  static_assert(BATCH % 4 == 0 && QC % BATCH == 0 && BATCH <= 40, "drain batch");
 #pragma unroll
   for (int c0 = 0; c0 < QC; c0 += BATCH) {
     uint32_t v[BATCH];
@@ -262,14 +261,10 @@ __device__ __forceinline__ void drain_quarter(uint32_t t_lane, const float2* hc,
       const int n = Q * QC + c0 + i;             // compile-time after unrolling
       const int m = n / K::BR, j = n % K::BR;
       const int hl = j / K::HD, d = j % K::HD;
-      const float4 c01 = *reinterpret_cast<const float4*>(hc + n);       // (s, bf) of columns n, n+1
-      const float4 c23 = *reinterpret_cast<const float4*>(hc + n + 2);
-      const float f0 = fmaf(a, __uint_as_float(v[i + 0]), fmaf(b, c01.x, c01.y));
-      const float f1 = fmaf(a, __uint_as_float(v[i + 1]), fmaf(b, c01.z, c01.w));
-      const float f2 = fmaf(a, __uint_as_float(v[i + 2]), fmaf(b, c23.x, c23.y));
-      const float f3 = fmaf(a, __uint_as_float(v[i + 3]), fmaf(b, c23.z, c23.w));
+      const float4 b4 = *reinterpret_cast<const float4*>(bf + n);
       const uint32_t dst = d_base + (m * K::NU + hl) * K::UNIT_BYTES + (d & 7) * 2 + ((static_cast<uint32_t>(d >> 3) << 4) ^ d_sx);
-      sts64(dst, pack_half2(f0, f1), pack_half2(f2, f3));
+      sts64(dst, pack_half2(__uint_as_float(v[i + 0]) + b4.x, __uint_as_float(v[i + 1]) + b4.y),
+            pack_half2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w));
     }
   }
 }
@@ -277,9 +272,10 @@ __device__ __forceinline__ void drain_quarter(uint32_t t_lane, const float2* hc,
 struct FParams {
   const __half* x;
   __half* out;
-  const float2* hconst;
+  const float* hconst;  // folded qkv bias [3C], permuted row order
   const float* table;   // [225][heads]
   int B, H, W, shift;
+  long long* timing;    // optional [grid][8] phase cycle counters (SUNET_AF_TIMING bring-up aid), else null
 };
 
 template <int C, int GH>
@@ -287,14 +283,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   using K = FCfg<C, GH>;
   constexpr int RB = K::RB, HD = K::HD, MT = K::MT;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t w_full, mma_done;
+  __shared__ __align__(8) uint64_t w_full, mma_done, x_ready;
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sX = smem_u32(smem + K::OFF_X), sW = smem_u32(smem + K::OFF_W), sQKV = smem_u32(smem + K::OFF_QKV);
   float* sTbl = reinterpret_cast<float*>(smem + K::OFF_TBL);
-  const float2* sHc = reinterpret_cast<const float2*>(smem + K::OFF_HC);
-  float2* sSt = reinterpret_cast<float2*>(smem + K::OFF_ST);
+  const float* sBf = reinterpret_cast<const float*>(smem + K::OFF_HC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3;             // TMEM lane quadrant this warp may read
   const int quarter = warp >> 2;       // column quarter of the drain / statistics pass
@@ -305,6 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     tma_prefetch_desc(&tmW);
     mbar_init(&w_full, 1);
     mbar_init(&mma_done, 1);
+    mbar_init(&x_ready, NTHREADS);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -315,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     const int e = i / K::HEADS, h = i - e * K::HEADS;
     sTbl[h * TBL + e] = __ldg(p.table + i) * LOG2E;
   }
-  for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float2*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
+  for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
   if constexpr (K::HD_PAD != HD) {
     // pad columns of every operand tile: 0 for q / k, V column HD = 1.0 (softmax denominator through the MMA); the drain and
     // the O store only ever write columns < HD, so this survives the whole kernel
@@ -371,15 +367,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     }
     cp_async_commit();
   };
-  // LayerNorm statistics of token tk (fp32, shifted one-pass variance) -> (rstd, -mean * rstd) in sSt[tk]
-  auto stats = [&]() {
-    const uint4 first = lds128(sX + tk * 128 + (static_cast<uint32_t>(tk & 7) << 4));
-    const float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(first.x & 0xffffu)));
+  // LayerNorm of token tk in place (norm1 without its affine part, which is folded into the weights): every thread
+  // normalises the chunks it gathered itself; the 4 threads of a token combine their partial sums by shuffle.
+  // fp32 statistics with a shifted one-pass variance; then arrive on x_ready for the MMA issuer.
+  auto normalize = [&]() {
+    uint4 v[K::CPR / 4];
+#pragma unroll
+    for (int j = 0; j < K::CPR / 4; ++j) v[j] = lds128(x_chunk(j));
+    float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(v[0].x & 0xffffu)));
+    k0 = __shfl_sync(0xffffffffu, k0, lane & ~3);   // first element of the row (held by part 0)
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < K::CPR / 4; ++j) {
-      const uint4 v = lds128(x_chunk(j));
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[j]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __half22float2(h2[t]);
@@ -392,12 +392,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
     s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-    if (part == 0) {
-      const float ms = s1 * (1.0f / C);
-      const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
-      const float rstd = rsqrtf(var + 1e-5f);
-      sSt[tk] = make_float2(rstd, -(k0 + ms) * rstd);
+    const float ms = s1 * (1.0f / C);
+    const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
+    const float a = rsqrtf(var + 1e-5f);
+    const float b = -(k0 + ms) * a;
+#pragma unroll
+    for (int j = 0; j < K::CPR / 4; ++j) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[j]);
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h2[t]);
+        o2[t] = __floats2half2_rn(fmaf(f.x, a, b), fmaf(f.y, a, b));
+      }
+      sts128(x_chunk(j), o);
     }
+    fence_proxy_async_smem();
+    mbar_arrive(&x_ready);
   };
   auto load_w = [&](int g) {   // thread 0: the folded qkv weights of head group g -> smem, [kb][sub-tile][NPM rows][64] SW128
     mbar_arrive_expect_tx(&w_full, K::W_BYTES);
@@ -440,29 +452,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
 
   uint32_t item = 0;
+  long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   Geo geo = tile_geo(blockIdx.x);
   if (static_cast<long long>(blockIdx.x) < tiles) {
     if (tid == 0) load_w(0);
     gather(geo);
     cp_async_wait_all();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) issue_mma(0);
+    normalize();
+    if (tid == 0) {
+      mbar_wait(&x_ready, 0);
+      issue_mma(0);
+    }
     __syncwarp();
-    stats();
-    __syncthreads();
   }
+  uint32_t xph = 1;   // parity of the next x_ready phase
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long next_tile = tile + gridDim.x;
     const bool has_next_tile = next_tile < tiles;
     Geo geo_next = geo;
-    const float2 ln = sSt[row];   // (rstd, -mean * rstd) of this thread's drain row
 #pragma unroll 1
     for (int g = 0; g < K::NG; ++g, ++item) {
       const bool last_g = g == K::NG - 1;
       const bool has_next = !last_g || has_next_tile;
+      long long tq0 = 0, tq1 = 0;
+      if (p.timing) tq0 = clock64();
       mbar_wait(&mma_done, item & 1);
       tc_fence_after();
+      if (p.timing) { tq1 = clock64(); tacc[0] += tq1 - tq0; tq0 = tq1; }
       // the MMAs of this item have read the weight buffer (and, for the last group, the token tile): refill them
       if (tid == 0 && has_next) load_w(last_g ? 0 : g + 1);
       if (last_g && has_next_tile) {
@@ -471,23 +487,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       }
       // ---- drain: qkv[row][n] = rstd * D - rstd * mean * s_n + bf_n  -> fp16 operand tiles
       {
-        const float2* hc = sHc + g * K::NGC;
+        const float* bf = sBf + g * K::NGC;
         switch (quarter) {
-          case 0: drain_quarter<K, 0>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
-          case 1: drain_quarter<K, 1>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
-          case 2: drain_quarter<K, 2>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
-          default: drain_quarter<K, 3>(t_lane, hc, d_base, d_sx, ln.x, ln.y); break;
+          case 0: drain_quarter<K, 0>(t_lane, bf, d_base, d_sx); break;
+          case 1: drain_quarter<K, 1>(t_lane, bf, d_base, d_sx); break;
+          case 2: drain_quarter<K, 2>(t_lane, bf, d_base, d_sx); break;
+          default: drain_quarter<K, 3>(t_lane, bf, d_base, d_sx); break;
         }
       }
-      if (last_g && has_next_tile) {
-        cp_async_wait_all();
-        fence_proxy_async_smem();
-      }
+      if (p.timing) { tq1 = clock64(); tacc[1] += tq1 - tq0; tq0 = tq1; }
+      if (last_g && has_next_tile) cp_async_wait_all();
+      if (p.timing) { tq1 = clock64(); tacc[2] += tq1 - tq0; tq0 = tq1; }
       tc_fence_before();
-      __syncthreads();   // (B) q/k/v operand tiles complete, accumulator drained, next token tile landed
-      if (tid == 0 && has_next) issue_mma(item + 1);   // runs on the tensor pipe while the core below runs on the CUDA cores
+      __syncthreads();   // (B) q/k/v operand tiles complete, accumulator drained
+      if (p.timing) { tq1 = clock64(); tacc[3] += tq1 - tq0; tq0 = tq1; }
+      if (last_g && has_next_tile) normalize();        // next tile's LayerNorm, in place in the token tile
+      if (p.timing) { tq1 = clock64(); tacc[8] += tq1 - tq0; tq0 = tq1; }
+      if (tid == 0 && has_next) {                      // runs on the tensor pipe while the core below runs on the CUDA cores
+        if (last_g) { mbar_wait(&x_ready, xph & 1); }
+        issue_mma(item + 1);
+      }
+      if (last_g && has_next_tile) ++xph;
       __syncwarp();
-      if (last_g && has_next_tile) stats();            // next tile's LayerNorm statistics (read after barrier (D))
+      if (p.timing) { tq1 = clock64(); tacc[9] += tq1 - tq0; tq0 = tq1; }
       // ---- core
       {
         const int head = g * GH + u_hl;
@@ -507,7 +529,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
           else attn_tiles<HD, MT, false>(q_h, k_h, v_h, mbase, lane, tb, false, false);
         }
       }
+      if (p.timing) { tq1 = clock64(); tacc[4] += tq1 - tq0; tq0 = tq1; }
       __syncthreads();   // (C) O rows of every unit parked in the q tiles
+      if (p.timing) { tq1 = clock64(); tacc[5] += tq1 - tq0; tq0 = tq1; }
       // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map): the 4 threads
       // of a token write consecutive vectors, so every store instruction covers whole 32-byte sectors
       if (geo.row >= 0) {
@@ -528,9 +552,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
           }
         }
       }
-      __syncthreads();   // (D) q tiles free for the next drain; next tile's statistics visible
+      if (p.timing) { tq1 = clock64(); tacc[6] += tq1 - tq0; tq0 = tq1; }
+      __syncthreads();   // (D) q tiles free for the next drain
+      if (p.timing) { tq1 = clock64(); tacc[7] += tq1 - tq0; }
     }
     geo = geo_next;
+  }
+  if (p.timing && (tid & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) p.timing[(static_cast<long long>(blockIdx.x) * 16 + warp) * 10 + i] = tacc[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -542,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
 
 // ---- pre-pack: permuted rows, W * gamma (q rows additionally * qscale), row sums of the rounded weights, folded bias
 __global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __restrict__ bqkv, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __half* __restrict__ wp, float2* __restrict__ hconst, int C, int HD,
+                                 const float* __restrict__ beta, __half* __restrict__ wp, float* __restrict__ hconst, int C, int HD,
                                  int GH, float qscale) {
   const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -552,19 +582,14 @@ __global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __
   const int m = within / BR, j = within - m * BR;
   const int o = m * C + g * BR + j;   // original row: [q|k|v][head][d]
   const float sc = m == 0 ? qscale : 1.f;
-  float s = 0.f, bb = 0.f;
+  float bb = 0.f;
   for (int k = lane; k < C; k += 32) {
     const float w = wqkv[static_cast<size_t>(o) * C + k];
-    const __half h = __float2half_rn(w * gamma[k] * sc);
-    wp[static_cast<size_t>(pr) * C + k] = h;
-    s += __half2float(h);
+    wp[static_cast<size_t>(pr) * C + k] = __float2half_rn(w * gamma[k] * sc);
     bb = fmaf(w, beta[k], bb);
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, off);
-    bb += __shfl_xor_sync(0xffffffffu, bb, off);
-  }
-  if (lane == 0) hconst[pr] = make_float2(s, (bb + (bqkv ? bqkv[o] : 0.f)) * sc);
+  for (int off = 16; off > 0; off >>= 1) bb += __shfl_xor_sync(0xffffffffu, bb, off);
+  if (lane == 0) hconst[pr] = (bb + (bqkv ? bqkv[o] : 0.f)) * sc;
 }
 
 template <int C, int GH>
@@ -581,15 +606,36 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   }
   FParams prm;
   prm.x = x; prm.out = out;
-  prm.hconst = reinterpret_cast<const float2*>(p.hconst);
+  prm.hconst = p.hconst;
   prm.table = p.table;
   prm.B = B; prm.H = H; prm.W = W; prm.shift = shift;
+  prm.timing = nullptr;
+  static long long* timing_buf = nullptr;
+  const bool timing = getenv("SUNET_AF_TIMING") != nullptr;
+  if (timing) {
+    if (!timing_buf) SUNET_CUDA(cudaMalloc(&timing_buf, 148 * 16 * 10 * sizeof(long long)));
+    SUNET_CUDA(cudaMemsetAsync(timing_buf, 0, 148 * 16 * 10 * sizeof(long long), stream));
+    prm.timing = timing_buf;
+  }
   const long long nwin = static_cast<long long>(B) * (H / 8) * (W / 8);
   if (nwin > 0x3fffffffLL || static_cast<long long>(B) * H * W > 0x7fffffffLL) return fail(SUNET_E_SHAPE, "fused attention: too many tokens for 32-bit row indices");
   const long long tiles = (nwin + 1) / 2;
   const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
   attn_fused_kernel<C, GH><<<grid, NTHREADS, K::SMEM, stream>>>(p.tmW, prm);
   SUNET_CHECK_LAUNCH();
+  if (timing) {   // bring-up aid: per-phase cycles averaged over CTAs, for warp 0 (MMA issuer) and the mean of the other warps
+    SUNET_CUDA(cudaStreamSynchronize(stream));
+    static long long host[148 * 16 * 10];
+    SUNET_CUDA(cudaMemcpy(host, timing_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    static const char* names[10] = {"wait_mma", "drain", "cpwait", "barB", "core", "barC", "scatter", "barD", "normalize", "issue"};
+    double w0[10] = {0}, wr[10] = {0};
+    for (unsigned b = 0; b < grid; ++b)
+      for (int w = 0; w < 16; ++w)
+        for (int i = 0; i < 10; ++i) (w == 0 ? w0[i] : wr[i]) += static_cast<double>(host[(b * 16 + w) * 10 + i]);
+    fprintf(stderr, "attn_fused<%d> tiles=%lld grid=%u cycles per CTA:", C, tiles, grid);
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %.0f/%.0f", names[i], w0[i] / grid, wr[i] / grid / 15);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 
@@ -605,7 +651,7 @@ int attn_fused_prepack(AttnFusedPack* p, int C, int heads, float qscale, const f
   if (!p->w || !p->hconst) return fail(SUNET_E_ARG, "fused attention: pack buffers not allocated");
   p->C = C; p->heads = heads; p->table = table;
   const int GH = group_heads(C), HD = C / heads;
-  attn_fold_kernel<<<(3 * C + 7) / 8, 256, 0, stream>>>(wqkv, bqkv, gamma, beta, p->w, reinterpret_cast<float2*>(p->hconst), C, HD, GH, qscale);
+  attn_fold_kernel<<<(3 * C + 7) / 8, 256, 0, stream>>>(wqkv, bqkv, gamma, beta, p->w, p->hconst, C, HD, GH, qscale);
   SUNET_CHECK_LAUNCH();
   const int NGC = 3 * GH * HD;
   const int NPM = NGC > 256 ? NGC / 3 : NGC;

@@ -13,7 +13,7 @@ namespace sunet {
 struct AttnFusedPack {
   int C = 0, heads = 0;
   __half* w = nullptr;          // [3C][C] qkv weight: rows permuted to [head group][q|k|v][head][d], LN gamma folded, q rows scaled
-  float* hconst = nullptr;      // float2 [3C]: (row sum of the rounded weights, folded bias) in the same row order
+  float* hconst = nullptr;      // float [3C]: folded bias (b + W beta, q rows scaled) in the same row order
   const float* table = nullptr; // relative_position_bias_table fp32 [225][heads] (device)
   alignas(64) CUtensorMap tmW;
 };
