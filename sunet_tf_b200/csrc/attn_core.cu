@@ -15,6 +15,7 @@
 // The linear layers around it (>= 90% of the block FLOPs) run on tcgen05 (gemm_tcgen05.cu, mlp_fused.cu).
 #include "attn_core.cuh"
 #include "error.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace sunet {
@@ -246,6 +247,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) attn_core_kernel(const AttnCor
   const int nW = nWr * nWc;
   const int groups = p.heads / HPC;          // head groups per window
 
+  pdl_wait();
+  pdl_launch_dependents();
   // ---- one-time setup: bias table of every head, pad columns of both stages (cp.async never touches them)
   for (int i = tid; i < p.heads * 225; i += NT) {
     const int e = i / p.heads, h = i - e * p.heads;
@@ -386,8 +389,7 @@ int launch_core(const AttnCoreArgs& a, int64_t windows, cudaStream_t stream) {
   const int64_t units = windows * (a.heads / HPC);
   if (units > 0x7fffffff) return fail(SUNET_E_SHAPE, "attn: too many (window, head-group) units");
   const unsigned grid = static_cast<unsigned>(units < sms ? units : sms);
-  attn_core_kernel<HD, HPC, NWARPS><<<grid, K::NT, K::SMEM, stream>>>(a, static_cast<int>(units));
-  SUNET_CHECK_LAUNCH();
+  SUNET_CUDA(launch_pdl(attn_core_kernel<HD, HPC, NWARPS>, dim3(grid), dim3(K::NT), K::SMEM, stream, a, static_cast<int>(units)));
   return 0;
 }
 

@@ -25,11 +25,26 @@
 
 #include "error.h"
 #include "gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace sunet {
 
 namespace {
+
+// Phase cycle counters (SUNET_AF_TIMING=1 at run time): compiled in only with -DSUNET_KERNEL_TIMING=1, they cost ~25 registers
+#ifndef SUNET_KERNEL_TIMING
+#define SUNET_KERNEL_TIMING 0
+#endif
+#if SUNET_KERNEL_TIMING
+#define AF_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; } } while (0)
+#define AF_T_DECL long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define AF_T_START long long tq0 = p.timing ? clock64() : 0
+#else
+#define AF_T(i) do { } while (0)
+#define AF_T_DECL do { } while (0)
+#define AF_T_START do { } while (0)
+#endif
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int NTHREADS = 512;
@@ -44,7 +59,7 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -54,7 +69,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 __device__ __forceinline__ float ex2(float x) {   // (ex2.approx.f16x2 becomes two MUFU.EX2.F16: same MUFU issue rate, measured)
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -177,25 +192,29 @@ __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v
   m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  // Exponentials and P V interleaved per 16-key slab: the MUFU work of slab kk+1 is issued between the tensor-pipe work of
+  // slab kk instead of in one burst (the asm statements are volatile, so the order below is the issue order; with every
+  // warp of a scheduler in the same phase, a burst of 32 ex2 per lane leaves the FMA / tensor pipes idle and vice versa)
   float sum0 = 0.f, sum1 = 0.f;
-  uint32_t pk[8][2];   // fp16 probabilities: [nt][0] = row i0 (keys 2tq, 2tq+1 of key row nt), [nt][1] = row i1
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    pk[nt][0] = pack_half2(ex2(s[nt][0] - m0), ex2(s[nt][1] - m0));
-    pk[nt][1] = pack_half2(ex2(s[nt][2] - m1), ex2(s[nt][3] - m1));
-    if constexpr (!MMA_SUM) {
-      const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&pk[nt][0]));
-      const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&pk[nt][1]));
-      sum0 += p0.x + p0.y;
-      sum1 += p1.x + p1.y;
-    }
-  }
   float o[NO][4];
 #pragma unroll
   for (int n = 0; n < NO; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    const uint32_t pa[4] = {pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1]};
+    uint32_t pa[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int nt = 2 * kk + h;
+      const float e0 = ex2(s[nt][0] - m0), e1 = ex2(s[nt][1] - m0), e2 = ex2(s[nt][2] - m1), e3 = ex2(s[nt][3] - m1);
+      pa[2 * h] = pack_half2(e0, e1);       // row i0, keys 2tq, 2tq+1 of key row nt
+      pa[2 * h + 1] = pack_half2(e2, e3);   // row i1
+      if constexpr (!MMA_SUM) {
+        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&pa[2 * h]));
+        const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&pa[2 * h + 1]));
+        sum0 += p0.x + p0.y;
+        sum1 += p1.x + p1.y;
+      }
+    }
 #pragma unroll
     for (int n = 0; n < NO; n += 2) {
       uint32_t vb[4];   // transposed 8x8 loads of V[key][d]: (keys lo, n), (keys hi, n), (keys lo, n+1), (keys hi, n+1)
@@ -328,6 +347,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();   // everything above read only parameters (constant across the forward); the token stream is touched below
+  pdl_launch_dependents();
 
   const int nWc = p.W >> 3, nWr = p.H >> 3, nW = nWr * nWc;
   const long long nwin = static_cast<long long>(p.B) * nW;
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
 
   uint32_t item = 0;
-  long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  AF_T_DECL;
   Geo geo = tile_geo(blockIdx.x);
   if (static_cast<long long>(blockIdx.x) < tiles) {
     if (tid == 0) load_w(0);
@@ -474,11 +495,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     for (int g = 0; g < K::NG; ++g, ++item) {
       const bool last_g = g == K::NG - 1;
       const bool has_next = !last_g || has_next_tile;
-      long long tq0 = 0, tq1 = 0;
-      if (p.timing) tq0 = clock64();
+      AF_T_START;
       mbar_wait(&mma_done, item & 1);
       tc_fence_after();
-      if (p.timing) { tq1 = clock64(); tacc[0] += tq1 - tq0; tq0 = tq1; }
+      AF_T(0);
       // the MMAs of this item have read the weight buffer (and, for the last group, the token tile): refill them
       if (tid == 0 && has_next) load_w(last_g ? 0 : g + 1);
       if (last_g && has_next_tile) {
@@ -495,21 +515,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
           default: drain_quarter<K, 3>(t_lane, bf, d_base, d_sx); break;
         }
       }
-      if (p.timing) { tq1 = clock64(); tacc[1] += tq1 - tq0; tq0 = tq1; }
+      AF_T(1);
       if (last_g && has_next_tile) cp_async_wait_all();
-      if (p.timing) { tq1 = clock64(); tacc[2] += tq1 - tq0; tq0 = tq1; }
+      AF_T(2);
       tc_fence_before();
       __syncthreads();   // (B) q/k/v operand tiles complete, accumulator drained
-      if (p.timing) { tq1 = clock64(); tacc[3] += tq1 - tq0; tq0 = tq1; }
+      AF_T(3);
       if (last_g && has_next_tile) normalize();        // next tile's LayerNorm, in place in the token tile
-      if (p.timing) { tq1 = clock64(); tacc[8] += tq1 - tq0; tq0 = tq1; }
+      AF_T(8);
       if (tid == 0 && has_next) {                      // runs on the tensor pipe while the core below runs on the CUDA cores
         if (last_g) { mbar_wait(&x_ready, xph & 1); }
         issue_mma(item + 1);
       }
       if (last_g && has_next_tile) ++xph;
       __syncwarp();
-      if (p.timing) { tq1 = clock64(); tacc[9] += tq1 - tq0; tq0 = tq1; }
+      AF_T(9);
       // ---- core
       {
         const int head = g * GH + u_hl;
@@ -529,9 +549,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
           else attn_tiles<HD, MT, false>(q_h, k_h, v_h, mbase, lane, tb, false, false);
         }
       }
-      if (p.timing) { tq1 = clock64(); tacc[4] += tq1 - tq0; tq0 = tq1; }
+      AF_T(4);
       __syncthreads();   // (C) O rows of every unit parked in the q tiles
-      if (p.timing) { tq1 = clock64(); tacc[5] += tq1 - tq0; tq0 = tq1; }
+      AF_T(5);
       // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map): the 4 threads
       // of a token write consecutive vectors, so every store instruction covers whole 32-byte sectors
       if (geo.row >= 0) {
@@ -552,16 +572,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
           }
         }
       }
-      if (p.timing) { tq1 = clock64(); tacc[6] += tq1 - tq0; tq0 = tq1; }
+      AF_T(6);
       __syncthreads();   // (D) q tiles free for the next drain
-      if (p.timing) { tq1 = clock64(); tacc[7] += tq1 - tq0; }
+      AF_T(7);
     }
     geo = geo_next;
   }
+#if SUNET_KERNEL_TIMING
   if (p.timing && (tid & 31) == 0) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) p.timing[(static_cast<long long>(blockIdx.x) * 16 + warp) * 10 + i] = tacc[i];
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -611,7 +633,7 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   prm.B = B; prm.H = H; prm.W = W; prm.shift = shift;
   prm.timing = nullptr;
   static long long* timing_buf = nullptr;
-  const bool timing = getenv("SUNET_AF_TIMING") != nullptr;
+  const bool timing = SUNET_KERNEL_TIMING && getenv("SUNET_AF_TIMING") != nullptr;
   if (timing) {
     if (!timing_buf) SUNET_CUDA(cudaMalloc(&timing_buf, 148 * 16 * 10 * sizeof(long long)));
     SUNET_CUDA(cudaMemsetAsync(timing_buf, 0, 148 * 16 * 10 * sizeof(long long), stream));
@@ -621,8 +643,7 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   if (nwin > 0x3fffffffLL || static_cast<long long>(B) * H * W > 0x7fffffffLL) return fail(SUNET_E_SHAPE, "fused attention: too many tokens for 32-bit row indices");
   const long long tiles = (nwin + 1) / 2;
   const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
-  attn_fused_kernel<C, GH><<<grid, NTHREADS, K::SMEM, stream>>>(p.tmW, prm);
-  SUNET_CHECK_LAUNCH();
+  SUNET_CUDA(launch_pdl(attn_fused_kernel<C, GH>, dim3(grid), dim3(NTHREADS), K::SMEM, stream, p.tmW, prm));
   if (timing) {   // bring-up aid: per-phase cycles averaged over CTAs, for warp 0 (MMA issuer) and the mean of the other warps
     SUNET_CUDA(cudaStreamSynchronize(stream));
     static long long host[148 * 16 * 10];

@@ -3,6 +3,8 @@
 // consecutive lanes touch consecutive addresses.
 #include "elementwise.cuh"
 #include "error.h"
+#include "launch.cuh"
+#include "ptx.cuh"
 
 namespace sunet {
 
@@ -57,6 +59,8 @@ template <int LPR, int MAXV, bool MERGE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ in, int64_t ld_in, __half* __restrict__ out,
                                                         int64_t ld_out, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int64_t M, int C, int H, int W, int Csrc) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int sub = threadIdx.x % LPR;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
   const bool active = row < M;
@@ -143,15 +147,15 @@ static int launch_ln(const __half* in, int64_t ld_in, __half* out, int64_t ld_ou
     return fail(SUNET_E_ALIGN, "layernorm: 16-byte aligned rows / affine vectors required");
   const int nvec = C / 8;
   if (nvec <= 16) {
-    layernorm_kernel<16, 1, MERGE><<<blocks_for(M * 16, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+    SUNET_CUDA(launch_pdl(layernorm_kernel<16, 1, MERGE>, dim3(blocks_for(M * 16, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc));
   } else if (nvec <= 32) {
-    layernorm_kernel<32, 1, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+    SUNET_CUDA(launch_pdl(layernorm_kernel<32, 1, MERGE>, dim3(blocks_for(M * 32, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc));
   } else if (nvec <= 64) {
-    layernorm_kernel<32, 2, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+    SUNET_CUDA(launch_pdl(layernorm_kernel<32, 2, MERGE>, dim3(blocks_for(M * 32, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc));
   } else if (nvec <= 128) {
-    layernorm_kernel<32, 4, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+    SUNET_CUDA(launch_pdl(layernorm_kernel<32, 4, MERGE>, dim3(blocks_for(M * 32, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc));
   } else {
-    layernorm_kernel<32, 8, MERGE><<<blocks_for(M * 32, 256), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc);
+    SUNET_CUDA(launch_pdl(layernorm_kernel<32, 8, MERGE>, dim3(blocks_for(M * 32, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc));
   }
   SUNET_CHECK_LAUNCH();
   return 0;
@@ -179,6 +183,8 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
                                                           const float* __restrict__ wfold, const float* __restrict__ bfold,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           __half* __restrict__ out) {
+  pdl_wait();   // (the first kernel of a forward: orders it after the previous forward's readers of `out`)
+  pdl_launch_dependents();
   constexpr int E = EPL * 32;
   constexpr int PITCH = 35;
   extern __shared__ float sm[];
@@ -264,7 +270,7 @@ int patch_embed_fused(const float* img, int img_chans, int B, int Himg, int Wimg
 #define PE_LAUNCH(EPL)                                                                                          \
   {                                                                                                             \
     SUNET_CUDA(cudaFuncSetAttribute(patch_embed_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    patch_embed_kernel<EPL><<<grid, 256, smem, s>>>(img, img_chans, Himg, Wimg, wfold, bfold, gamma, beta, out);   \
+    SUNET_CUDA(launch_pdl(patch_embed_kernel<EPL>, dim3(grid), dim3(256), smem, s, img, img_chans, Himg, Wimg, wfold, bfold, gamma, beta, out));   \
   }
   switch (E / 32) {
     case 1: PE_LAUNCH(1); break;
@@ -310,6 +316,8 @@ __device__ __forceinline__ void bilinear_tap(int d, int r, int n, int& i0, int& 
 __global__ void __launch_bounds__(256) upsample_combine_kernel(const __half* __restrict__ Yp, const __half* __restrict__ Z,
                                                                void* __restrict__ out, int out_f32, int H, int W, int Co, int r,
                                                                int64_t total) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int nv = Co >> 3;
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(256) upsample_combine_kernel(const __half* __r
 int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, int B, int H, int W, int Co, int r, cudaStream_t s) {
   if (Co % 8) return fail(SUNET_E_SHAPE, "upsample: Co=%d must be a multiple of 8", Co);
   const int64_t total = static_cast<int64_t>(B) * H * r * W * r * (Co / 8);
-  upsample_combine_kernel<<<blocks_for(total, 256), 256, 0, s>>>(Yp, Z, out, out_f32, H, W, Co, r, total);
+  SUNET_CUDA(launch_pdl(upsample_combine_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, s, Yp, Z, out, out_f32, H, W, Co, r, total));
   SUNET_CHECK_LAUNCH();
   return 0;
 }
@@ -367,6 +375,8 @@ int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, 
 // ------------------------------------------------------------------------------------------------ folded tail stencil
 __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restrict__ Qp, const float* __restrict__ Rb,
                                                            float* __restrict__ out, int H, int W, int OC, int NT, int64_t total) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int OW = 4 * W, OH = 4 * H;
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restri
 int tail_stencil(const float* Qp, const float* Rb, float* out, int B, int H, int W, int OC, int NT, cudaStream_t s) {
   if (OC < 1 || OC > 3 || NT < OC * 9) return fail(SUNET_E_SHAPE, "tail: out_chans=%d (1..3) NT=%d", OC, NT);
   const int64_t total = static_cast<int64_t>(B) * 16 * H * W;
-  tail_stencil_kernel<<<blocks_for(total, 256), 256, 0, s>>>(Qp, Rb, out, H, W, OC, NT, total);
+  SUNET_CUDA(launch_pdl(tail_stencil_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, s, Qp, Rb, out, H, W, OC, NT, total));
   SUNET_CHECK_LAUNCH();
   return 0;
 }

@@ -34,6 +34,7 @@ struct GemmArgs {
   int out_f32 = 0;
   int force_block_n = 0;         // tuning / tests
   int pair_mode = 0;             // 0 auto, 1 single-CTA tiles, 2 CTA-pair (cta_group::2) 256-row tiles
+  int dbg = 0;                   // bring-up ablations (timing only, wrong results): 1 no epilogue, 2 no MMA, 4 no TMA loads
 };
 
 struct GemmEpi {
@@ -51,6 +52,7 @@ struct GemmEpi {
   int n_tiles;
   int64_t total_tiles;
   uint32_t acc_cols, tmem_cols;
+  int dbg;
 };
 
 struct GemmOp {

@@ -10,6 +10,7 @@
 #include "act.cuh"
 #include "error.h"
 #include "gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace sunet {
@@ -200,27 +201,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                 // the prologue above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter: the ring runs across tiles
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t ready = mbar_test(&empty_bar[0], 1);
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = static_cast<int>(tile % p.n_tiles) * block_n;
         const int m0 = static_cast<int>(tile / p.n_tiles) * BLOCK_M;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * stage_bytes;
+          mbar_wait_hint(&empty_bar[s], ph ^ 1, ready);
+          const int s_cur = s;
+          if (++s == stages) { s = 0; ph ^= 1; }
+          ready = mbar_test(&empty_bar[s], ph ^ 1);   // next slot's state, looked up under this slot's TMA issue
+          uint8_t* sa = smem + s_cur * stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          if (p.dbg & 4) { mbar_arrive(&full_bar[s_cur]); continue; }
+          mbar_arrive_expect_tx(&full_bar[s_cur], stage_bytes);
           if (kb < kb0) {
-            tma_load_2d(sa, &tmA0, &full_bar[s], kb * BLOCK_K, m0);
-            tma_load_2d(sb, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+            tma_load_2d(sa, &tmA0, &full_bar[s_cur], kb * BLOCK_K, m0);
+            tma_load_2d(sb, &tmW, &full_bar[s_cur], kb * BLOCK_K, n0);
           } else {
             const int j = kb - kb0;
-            tma_load_2d(sa, &tmA1, &full_bar[s], j * BLOCK_K, m0);
-            tma_load_2d(sb, &tmW, &full_bar[s], p.K0 + j * BLOCK_K, n0);
+            tma_load_2d(sa, &tmA1, &full_bar[s_cur], j * BLOCK_K, m0);
+            tma_load_2d(sb, &tmW, &full_bar[s_cur], p.K0 + j * BLOCK_K, n0);
           }
         }
       }
@@ -228,32 +236,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(BLOCK_M, block_n);
-      uint32_t it = 0;
       uint32_t local = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t ready = mbar_test(&full_bar[0], 0);
+      uint32_t acc_ready = mbar_test(&tmem_empty_bar[0], 1);
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const uint32_t as = local & 1;
         const uint32_t aph = (local >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aph ^ 1);   // epilogue has drained this accumulator stage
+        mbar_wait_hint(&tmem_empty_bar[as], aph ^ 1, acc_ready);   // epilogue has drained this accumulator stage
+        acc_ready = mbar_test(&tmem_empty_bar[as ^ 1], (((local + 1) >> 1) & 1) ^ 1);   // next tile's stage, looked up early
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * acc_cols;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&full_bar[s], ph);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_hint(&full_bar[s], ph, ready);
+          const int s_cur = s;
+          if (++s == stages) { s = 0; ph ^= 1; }
+          ready = mbar_test(&full_bar[s], ph);   // next slot's state, looked up under this slot's MMA issue
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sa = smem_u32(smem + s_cur * stage_bytes);
           const uint32_t sb = sa + A_TILE_BYTES;
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sb);
           // valid K elements in this block (a K0/K1 tail shorter than 64 is zero-filled by TMA but not multiplied)
           const int kvalid = kb < kb0 ? min(BLOCK_K, p.K0 - kb * BLOCK_K) : min(BLOCK_K, p.K1 - (kb - kb0) * BLOCK_K);
           const int ksteps = (kvalid + 15) >> 4;
-          for (int k = 0; k < ksteps; ++k) {
+          for (int k = 0; k < ksteps && !(p.dbg & 2); ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
             umma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          tc_commit(&empty_bar[s_cur]);  // frees the smem slot once these MMAs have read it
         }
         tc_commit(&tmem_full_bar[as]);  // accumulator of this tile complete
       }
@@ -280,7 +293,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const int64_t m_base = m - lane;
       const int rows_valid = static_cast<int>(min(static_cast<int64_t>(32), p.M - m_base));  // <= 0 for fully out-of-range warps
-      if (p.out_f32) epilogue_range<true>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
+      if (p.dbg & 1) { /* timing ablation: accumulator handed straight back */ }
+      else if (p.out_f32) epilogue_range<true>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
       else epilogue_range<false>(p, stg, taddr, c_begin, c_end, m_base, rows_valid, n0, lane, slope);
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -352,6 +366,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / peer TMA completion
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -540,6 +556,7 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   e.total_tiles = m_tiles * n_tiles;
   e.acc_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256));
   e.tmem_cols = 2 * e.acc_cols;
+  e.dbg = a.dbg;
   if (a.act == ACT_PRELU && a.prelu == nullptr) return fail(SUNET_E_ARG, "gemm: PReLU needs a slope pointer");
   if (a.out_f32 && a.R != nullptr) return fail(SUNET_E_ARG, "gemm: a residual with fp32 output is not supported");
   const int64_t tiles = m_tiles * n_tiles;
@@ -566,9 +583,8 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     SUNET_CUDA(cudaFuncSetAttribute(gemm_tn_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_MAX_DYN_SMEM));
     configured = true;
   }
-  if (op.pair) gemm_tn_f16_pair_kernel<<<op.grid, GEMM_THREADS, op.smem, stream>>>(op.tmA0, op.tmA1, op.tmW, op.epi);
-  else gemm_tn_f16_kernel<<<op.grid, GEMM_THREADS, op.smem, stream>>>(op.tmA0, op.tmA1, op.tmW, op.epi);
-  SUNET_CHECK_LAUNCH();
+  if (op.pair) SUNET_CUDA(launch_pdl(gemm_tn_f16_pair_kernel, dim3(op.grid), dim3(GEMM_THREADS), op.smem, stream, op.tmA0, op.tmA1, op.tmW, op.epi));
+  else SUNET_CUDA(launch_pdl(gemm_tn_f16_kernel, dim3(op.grid), dim3(GEMM_THREADS), op.smem, stream, op.tmA0, op.tmA1, op.tmW, op.epi));
   return 0;
 }
 

@@ -17,11 +17,13 @@
 // registers so the tile buffer can be refilled as soon as the last fc1 MMA of the tile has read it.
 #include "mlp_fused.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "act.cuh"
 #include "error.h"
 #include "gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace sunet {
@@ -69,7 +71,22 @@ struct Params {
   __half* out;
   int64_t M;
   int64_t tiles;
+  long long* timing;   // optional [grid][16 epilogue warps][8] phase cycle counters (SUNET_MLP_TIMING bring-up aid)
 };
+
+// Phase cycle counters of the epilogue warps: compiled in only with -DSUNET_KERNEL_TIMING=1 (they cost ~20 registers)
+#ifndef SUNET_KERNEL_TIMING
+#define SUNET_KERNEL_TIMING 0
+#endif
+#if SUNET_KERNEL_TIMING
+#define MLP_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; } } while (0)
+#define MLP_T_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define MLP_T_START long long tq0 = p.timing ? clock64() : 0
+#else
+#define MLP_T(i) do { } while (0)
+#define MLP_T_DECL do { } while (0)
+#define MLP_T_START do { } while (0)
+#endif
 
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -118,6 +135,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -234,11 +253,14 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t g = 0;
     int lt = 0;
+    MLP_T_DECL;
     for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
       const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
       const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
       // ---- row statistics + residual capture
+      MLP_T_START;
       mbar_wait(&x_full[xb], xuse & 1);
+      MLP_T(0);
       const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
       uint4 res[K::QCH];
       float s1 = 0.f, s2 = 0.f;
@@ -277,11 +299,13 @@ __global__ void __launch_bounds__(THREADS, 1)
         s2 = -(k0 + ms) * rstd;     // b
       }
       const float a = s1, b = s2;
+      MLP_T(1);
       // ---- GELU passes
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
         mbar_wait(&h_full[hb], ph);
         tc_fence_after();
+        MLP_T(2);
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         tmem_ld_wait();
@@ -295,7 +319,9 @@ __global__ void __launch_bounds__(THREADS, 1)
           const __half2 x2 = __floats2half2_rn(h0, h1);
           w[i] = gelu_fast_h2(*reinterpret_cast<const uint32_t*>(&x2));
         }
-        mbar_wait(&hs_empty[hb], ph ^ 1);   // fc2 of chunk g-2 has consumed this buffer
+        MLP_T(3);
+        mbar_wait(&hs_empty[hb], ph ^ 1);
+        MLP_T(4);   // fc2 of chunk g-2 has consumed this buffer
         const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -304,6 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gelu_done[hb]);
+        MLP_T(5);
       }
       // ---- output: Y + b2 + residual -> global
       {
@@ -311,6 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
         mbar_wait(&y_full[yb], yuse & 1);
         tc_fence_after();
+        MLP_T(6);
         const uint32_t ty = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
         uint32_t y[K::QC];
 #pragma unroll
@@ -337,8 +365,15 @@ __global__ void __launch_bounds__(THREADS, 1)
             *reinterpret_cast<uint4*>(orow + i * 8) = o;
           }
         }
+        MLP_T(7);
       }
     }
+#if SUNET_KERNEL_TIMING
+    if (p.timing && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -431,6 +466,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -528,10 +565,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t g = 0;
     int lt = 0;
+    MLP_T_DECL;
     for (int64_t pt = cluster_id; pt < p.tiles; pt += n_clusters, ++lt) {
       const int xb = lt & 1;
       const uint32_t xuse = lt >> 1;
+      MLP_T_START;
       mbar_wait(&x_full[xb], xuse & 1);
+      MLP_T(0);
       const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
       uint4 res[K::QCH];
       float s1 = 0.f, s2 = 0.f;
@@ -570,10 +610,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         s2 = -(k0 + ms) * rstd;
       }
       const float a = s1, b = s2;
+      MLP_T(1);
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
         mbar_wait(&h_full[hb], ph);
         tc_fence_after();
+        MLP_T(2);
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         tmem_ld_wait();
@@ -581,13 +623,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float4 c2 = hc4[i];
+          const float4 c2 = hc4[i];   // (s, b1f) of two consecutive hidden columns (warp-uniform address: broadcast)
           const float h0 = fmaf(a, __uint_as_float(v[2 * i]), fmaf(b, c2.x, c2.y));
           const float h1 = fmaf(a, __uint_as_float(v[2 * i + 1]), fmaf(b, c2.z, c2.w));
           const __half2 x2 = __floats2half2_rn(h0, h1);
           w[i] = gelu_fast_h2(*reinterpret_cast<const uint32_t*>(&x2));
         }
+        MLP_T(3);
         mbar_wait(&hs_empty[hb], ph ^ 1);
+        MLP_T(4);
         const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -596,12 +640,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&gelu_done[hb], 0);
+        MLP_T(5);
       }
       {
         const int yb = lt & 1;
         const uint32_t yuse = lt >> 1;
         mbar_wait(&y_full[yb], yuse & 1);
         tc_fence_after();
+        MLP_T(6);
         const uint32_t ty = tmem_base + lane_off + K::TM_Y + yb * 128 + quarter * K::QC;
         uint32_t y[K::QC];
 #pragma unroll
@@ -628,8 +674,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
             *reinterpret_cast<uint4*>(orow + i * 8) = o;
           }
         }
+        MLP_T(7);
       }
     }
+#if SUNET_KERNEL_TIMING
+    if (p.timing && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
+    }
+#endif
   }
   tc_fence_before();
   cluster_sync_all();
@@ -665,6 +718,28 @@ __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restric
     dst[i] = __float2half_rn(src[i]);
 }
 
+static long long* mlp_timing_buf(cudaStream_t stream) {
+  static long long* buf = nullptr;
+  if (!SUNET_KERNEL_TIMING || getenv("SUNET_MLP_TIMING") == nullptr) return nullptr;
+  if (!buf && cudaMalloc(&buf, 148 * EPI_WARPS * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(buf, 0, 148 * EPI_WARPS * 8 * sizeof(long long), stream);
+  return buf;
+}
+static void mlp_timing_report(const char* what, int C, unsigned grid, const long long* buf, cudaStream_t stream) {
+  if (!buf) return;
+  cudaStreamSynchronize(stream);
+  static long long host[148 * EPI_WARPS * 8];
+  cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
+  static const char* names[8] = {"wait_x", "stats", "wait_h", "gelu", "wait_hs", "store", "wait_y", "out"};
+  double acc[8] = {0};
+  for (unsigned b = 0; b < grid; ++b)
+    for (int w = 0; w < EPI_WARPS; ++w)
+      for (int i = 0; i < 8; ++i) acc[i] += static_cast<double>(host[(b * EPI_WARPS + w) * 8 + i]);
+  fprintf(stderr, "%s<%d> grid=%u cycles per epilogue warp:", what, C, grid);
+  for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %.0f", names[i], acc[i] / grid / EPI_WARPS);
+  fprintf(stderr, "\n");
+}
+
 template <int C>
 int launch_pair_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
   using K = PairCfg<C>;
@@ -686,8 +761,9 @@ int launch_pair_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const int64_t clusters = sms / 2;
   const unsigned grid = static_cast<unsigned>(2 * (prm.tiles < clusters ? prm.tiles : clusters));
-  mlp_pair_kernel<C><<<grid, THREADS, K::SMEM, stream>>>(tmX, p.tmW1p, p.tmW2p, prm);
-  SUNET_CHECK_LAUNCH();
+  prm.timing = mlp_timing_buf(stream);
+  SUNET_CUDA(launch_pdl(mlp_pair_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmX, p.tmW1p, p.tmW2p, prm));
+  mlp_timing_report("mlp_pair", C, grid, prm.timing, stream);
   return 0;
 }
 
@@ -711,8 +787,9 @@ int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cud
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
-  mlp_fused_kernel<C><<<grid, THREADS, K::SMEM, stream>>>(tmX, p.tmW1, p.tmW2, prm);
-  SUNET_CHECK_LAUNCH();
+  prm.timing = mlp_timing_buf(stream);
+  SUNET_CUDA(launch_pdl(mlp_fused_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmX, p.tmW1, p.tmW2, prm));
+  mlp_timing_report("mlp_fused", C, grid, prm.timing, stream);
   return 0;
 }
 

@@ -24,6 +24,10 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (see launch.cuh)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -55,6 +59,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test.  An mbarrier test / try_wait has ~170 clk latency on B200 even when the phase is already complete
+// (measured, csrc/tests/test_units.cu), so single-thread pipeline loops issue the test for the NEXT stage before doing the
+// current stage's work and only fall back to the blocking wait when that early test failed.
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug must surface as a trap (sticky CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // fast path: try_wait suspends the thread in hardware for a bounded time, so this loop is not a hot spin
@@ -68,6 +88,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// wait, skipping the round trip when an earlier mbar_test of the same phase already succeeded
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ready) {
+  if (!ready) mbar_wait(bar, parity);
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {

@@ -109,7 +109,7 @@ static void test_gemm(const Case& c, bool check, int time_iters) {
   a.A0 = dA0; a.lda0 = c.K0; a.K0 = c.K0; a.A1 = dA1; a.lda1 = c.K1; a.K1 = c.K1;
   a.W = dW; a.ldw = K; a.M = c.M; a.N = c.N;
   a.bias = c.bias ? dBias : nullptr; a.act = c.act; a.prelu = dSlope; a.R = dR; a.ldr = c.N;
-  a.C = dC; a.ldc = c.N; a.out_f32 = c.f32; a.force_block_n = c.bn; a.pair_mode = c.pair;
+  a.C = dC; a.ldc = c.N; a.out_f32 = c.f32; a.force_block_n = c.bn; a.pair_mode = c.pair; a.dbg = getenv("SUNET_GEMM_DBG") ? atoi(getenv("SUNET_GEMM_DBG")) : 0;
   GemmOp op;
   int rc = gemm_prepare(a, &op);
   if (rc) { printf("gemm prepare rc=%d: %s\n", rc, last_error_buf()); g_fail++; return; }
