@@ -436,6 +436,20 @@ int pack_weight_f16(const float* src, __half* dst, int N, int K, int scale_rows,
   SUNET_CHECK_LAUNCH();
   return 0;
 }
+// dst [N][K + N] = [ half(src) | I ]: the residual add of a square-ish projection becomes a second K segment of the GEMM
+// (y = A W^T + R I), so the residual tile is prefetched by the TMA ring instead of being loaded in the epilogue
+__global__ void pack_weight_residual_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int K) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int KK = K + N;
+  if (i >= static_cast<int64_t>(N) * KK) return;
+  const int n = static_cast<int>(i / KK), k = static_cast<int>(i % KK);
+  dst[i] = k < K ? __float2half_rn(src[static_cast<int64_t>(n) * K + k]) : __float2half_rn(k - K == n ? 1.f : 0.f);
+}
+int pack_weight_residual_f16(const float* src, __half* dst, int N, int K, cudaStream_t s) {
+  pack_weight_residual_kernel<<<blocks_for(static_cast<int64_t>(N) * (K + N), 256), 256, 0, s>>>(src, dst, N, K);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
 __global__ void pack_weight_shuffle_kernel(const float* __restrict__ src, __half* __restrict__ dst, int Cq, int rr, int K) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(Cq) * rr * K) return;

@@ -38,6 +38,8 @@ int tail_stencil(const float* Qp, const float* Rb, float* out, int B, int H, int
 // ---- pre-pack helpers (run once per weight load)
 // dst[n][k] = half(src[n][k] * (n < scale_rows ? scale : 1))
 int pack_weight_f16(const float* src, __half* dst, int N, int K, int scale_rows, float scale, cudaStream_t s);
+// dst [N][K + N] = [ half(src[N][K]) | identity ]  (residual folded into the GEMM as a second K segment)
+int pack_weight_residual_f16(const float* src, __half* dst, int N, int K, cudaStream_t s);
 // dst[perm(n)][k] = half(src[n][k]) with perm(c*rr + ij) = ij*Cq + c   (pixel-shuffle output reordering)
 int pack_weight_shuffle_f16(const float* src, __half* dst, int Cq, int rr, int K, cudaStream_t s);
 int scale_copy_f32(const float* src, float* dst, int n, int scale_n, float scale, cudaStream_t s);

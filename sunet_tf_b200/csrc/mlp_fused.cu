@@ -383,169 +383,195 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-// ================================================================================================ CTA-pair variant
-// Same dataflow on tcgen05 cta_group::2 (C = 96): the two CTAs of a cluster each own a 128-token tile and HALF of every
-// weight tile (fc1: 64 of the 128 rows of a hidden chunk, fc2: 48 of the 96 output rows), so the whole fc1 / fc2 weight
-// set (84 KB per CTA with the K padding of the swizzle atoms) stays RESIDENT in shared memory for the life of the
-// kernel: no weight bytes are re-streamed through L2 per tile and no MMA ever waits for a weight ring.  The leader's
-// MMA warp issues M = 256 instructions that read both CTAs' shared memory and write both CTAs' TMEM.
-// Barriers: h_full / hs_empty / x_empty / y_full exist in both CTAs and are signalled by multicast commits;
-// gelu_done / y_empty / xp_ready / w_full live in the leader and collect arrivals from both CTAs.
-template <int C>
-struct PairCfg {
-  static constexpr int HID = 4 * C;
-  static constexpr int NCH = HID / NC;
-  static constexpr int KB1 = (C + 63) / 64;
-  static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;
-  static constexpr int W1H_ROWS = NC / 2;                  // fc1 rows of a hidden chunk held by one CTA
-  static constexpr int W1H_KB = W1H_ROWS * 128;            // bytes of one [64 rows][64] k-block
-  static constexpr int W2H_ROWS = C / 2;                   // fc2 output rows held by one CTA
-  static constexpr int W2H_KB = W2H_ROWS * 128;            // bytes of one [48 rows][64] k-block
-  static constexpr int W1_BYTES = NCH * KB1 * W1H_KB;      // 48 KB
-  static constexpr int W2_BYTES = (HID / 64) * W2H_KB;     // 36 KB
-  static constexpr int QC = C / 4;
-  static constexpr int QCH = C / 32;
-  static constexpr int OFF_X = 0;                          // 2 token-tile buffers
-  static constexpr int OFF_HS = OFF_X + 2 * KB1 * KBYTES;
-  static constexpr int OFF_W1 = OFF_HS + 2 * 2 * KBYTES;
-  static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-  static constexpr int OFF_HC = OFF_W2 + W2_BYTES;
-  static constexpr int OFF_B2 = OFF_HC + HID * 8;
-  static constexpr int OFF_ST = OFF_B2 + C * 4;
-  static constexpr int SMEM = OFF_ST + 2 * 4 * 128 * 8 + 1024;
-  static constexpr uint32_t TM_Y = 0;                      // Y[b] at column b * 128
-  static constexpr uint32_t TM_H = 256;                    // H[b] at column 256 + 128 b
-  static_assert(C == 96, "the resident-weight pair kernel is sized for C = 96");
-  static_assert(W2H_ROWS % 8 == 0 && C % 32 == 0, "weight halves must be whole swizzle atoms");
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+// ================================================================================================ proj + shortcut + MLP
+// The back half of a Swin block in one kernel (SUNet_detail.py:136 proj, :261 first residual, :262 norm2 + Mlp + second
+// residual):   x1 = shortcut + attn_out Wp^T + bp ;   y = x1 + fc2(GELU(fc1(LN(x1))))
+// Same dataflow as mlp_fused_kernel with one more MMA in front:
+//   TMA  : attn_out tile [128][C] -> smem X ; Wp k-blocks ride the fc2 weight ring (same [C rows][64] shape)
+//   MMA0 : P = attn_out * Wp^T  (fp32, in the TMEM columns of this tile's fc2 accumulator, which is idle until fc2 starts)
+//   EPI0 : x1 = P + bp + shortcut (global, issued before the wait) -> fp16 -> written IN PLACE over the attn_out tile as
+//          the A operand of fc1 and kept in registers as the residual; LayerNorm statistics of x1 (per-quarter shifted
+//          sums merged with the parallel-variance formula, no cross-thread shift needed)
+//   then fc1 / GELU / fc2 / output exactly as in mlp_fused_kernel.
+struct ProjParams {
+  const float2* hconst;
+  const float* b2;
+  const float* bp;        // proj.bias [C]
+  const __half* shortcut; // block input x [M][C] (may alias out: each thread reads and later writes the same elements)
+  __half* out;
+  int64_t M;
+  int64_t tiles;
 };
 
 template <int C>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-    mlp_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                    const __grid_constant__ CUtensorMap tmW2, const Params p) {
-  using K = PairCfg<C>;
+__global__ void __launch_bounds__(THREADS, 1)
+    mlp_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWp,
+                          const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const ProjParams p) {
+  using K = Cfg<C>;
+  constexpr int OFF_BP = K::OFF_ST + 2 * 4 * 128 * 8;   // float [C] after the statistics exchange
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t x_full[2], x_empty[2], xp_ready[2], w_full;
+  __shared__ __align__(8) uint64_t x_full[2], x_empty[2], x1_ready[2], p_full[2];
+  __shared__ __align__(8) uint64_t r1_full[K::R1], r1_empty[K::R1], r2_full[K::R2], r2_empty[K::R2];
   __shared__ __align__(8) uint64_t h_full[2], gelu_done[2], hs_empty[2], y_full[2], y_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;   // p.tiles counts 256-token pair tiles
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWp);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 1);
-      mbar_init(&x_empty[i], 1 + EPI_WARPS);
-      mbar_init(&xp_ready[i], 1);
+      mbar_init(&x_empty[i], 1);
+      mbar_init(&x1_ready[i], EPI_WARPS);
+      mbar_init(&p_full[i], 1);
       mbar_init(&h_full[i], 1);
-      mbar_init(&gelu_done[i], 2 * EPI_WARPS);
+      mbar_init(&gelu_done[i], EPI_WARPS);
       mbar_init(&hs_empty[i], 1);
       mbar_init(&y_full[i], 1);
-      mbar_init(&y_empty[i], 2 * EPI_WARPS);
+      mbar_init(&y_empty[i], EPI_WARPS);
     }
-    mbar_init(&w_full, 1);
+    for (int i = 0; i < K::R1; ++i) { mbar_init(&r1_full[i], 1); mbar_init(&r1_empty[i], 1); }
+    for (int i = 0; i < K::R2; ++i) { mbar_init(&r2_full[i], 1); mbar_init(&r2_empty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc_pair(&tmem_base_smem, 512);
-    tmem_relinquish_pair();
+    tmem_alloc(&tmem_base_smem, 512);
+    tmem_relinquish();
   }
   {
     float2* hc = reinterpret_cast<float2*>(smem + K::OFF_HC);
     for (int i = threadIdx.x; i < K::HID; i += THREADS) hc[i] = __ldg(p.hconst + i);
     float* b2s = reinterpret_cast<float*>(smem + K::OFF_B2);
-    for (int i = threadIdx.x; i < C; i += THREADS) b2s[i] = __ldg(p.b2 + i);
+    float* bps = reinterpret_cast<float*>(smem + OFF_BP);
+    for (int i = threadIdx.x; i < C; i += THREADS) { b2s[i] = __ldg(p.b2 + i); bps[i] = __ldg(p.bp + i); }
   }
   tc_fence_before();
-  cluster_sync_all();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_wait();
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      // resident weights: this CTA's halves, counted on the leader's barrier
-      if (rank == 0) mbar_arrive_expect_tx(&w_full, 2 * (K::W1_BYTES + K::W2_BYTES));
-      for (int j = 0; j < K::NCH; ++j)
-        for (int kb = 0; kb < K::KB1; ++kb)
-          tma_load_2d_pair(smem + K::OFF_W1 + (j * K::KB1 + kb) * K::W1H_KB, &tmW1, &w_full, kb * 64,
-                           j * NC + static_cast<int>(rank) * K::W1H_ROWS);
-      for (int kb = 0; kb < K::HID / 64; ++kb)
-        tma_load_2d_pair(smem + K::OFF_W2 + kb * K::W2H_KB, &tmW2, &w_full, kb * 64, static_cast<int>(rank) * K::W2H_ROWS);
-      // token tiles, one tile ahead; the peer tells the leader's MMA warp when its tile has landed
+      uint32_t i1 = 0, i2 = 0;
       int lt = 0;
-      for (int64_t pt = cluster_id; pt < p.tiles; pt += n_clusters, ++lt) {
-        const int xb = lt & 1;
-        const uint32_t use = lt >> 1;
+      auto load_x = [&](int64_t tile, int ltile) {
+        const int xb = K::NXBUF == 2 ? (ltile & 1) : 0;
+        const uint32_t use = K::NXBUF == 2 ? (ltile >> 1) : ltile;
         mbar_wait(&x_empty[xb], (use & 1) ^ 1);
         mbar_arrive_expect_tx(&x_full[xb], K::KB1 * KBYTES);
         for (int kb = 0; kb < K::KB1; ++kb)
-          tma_load_2d(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES, &tmX, &x_full[xb], kb * 64,
-                      static_cast<int>(pt * (2 * TILE_M) + rank * TILE_M));
-        if (rank == 1) {
-          mbar_wait(&x_full[xb], use & 1);
-          mbar_arrive_cluster(&xp_ready[xb], 0);
+          tma_load_2d(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES, &tmX, &x_full[xb], kb * 64, static_cast<int>(tile * TILE_M));
+      };
+      auto load_r2 = [&](const CUtensorMap* tm, int col) {   // one [C rows][64] k-block of Wp or W2
+        const int s = i2 % K::R2;
+        mbar_wait(&r2_empty[s], ((i2 / K::R2) & 1) ^ 1);
+        mbar_arrive_expect_tx(&r2_full[s], K::R2BYTES);
+        tma_load_2d(smem + K::OFF_R2 + s * K::R2BYTES, tm, &r2_full[s], col, 0);
+        ++i2;
+      };
+      if (K::NXBUF == 2 && static_cast<int64_t>(blockIdx.x) < p.tiles) load_x(blockIdx.x, 0);
+      bool have_prev = false;
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        // fc2 ring order = MMA order: [fc2 weights of the previous tile's last chunk] [Wp] [fc2 chunk 0] ... [fc2 chunk NCH-2]
+        if (have_prev) { load_r2(&tmW2, (K::NCH - 1) * NC); load_r2(&tmW2, (K::NCH - 1) * NC + 64); }
+        if (K::NXBUF != 2) load_x(tile, lt);
+        for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
+        if (K::NXBUF == 2 && tile + gridDim.x < p.tiles) load_x(tile + gridDim.x, lt + 1);   // prefetch one tile ahead
+        for (int j = 0; j < K::NCH; ++j) {
+          for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
+            const int s = i1 % K::R1;
+            mbar_wait(&r1_empty[s], ((i1 / K::R1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&r1_full[s], KBYTES);
+            tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
+          }
+          if (j > 0) { load_r2(&tmW2, (j - 1) * NC); load_r2(&tmW2, (j - 1) * NC + 64); }
         }
+        have_prev = true;
       }
+      if (have_prev) { load_r2(&tmW2, (K::NCH - 1) * NC); load_r2(&tmW2, (K::NCH - 1) * NC + 64); }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader only)
-    if (lane == 0 && rank == 0) {
-      const uint32_t idesc1 = umma_idesc_f16(2 * TILE_M, NC);
-      const uint32_t idesc2 = umma_idesc_f16(2 * TILE_M, C);
-      uint32_t g = 0;
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_f16(TILE_M, NC);
+      const uint32_t idesc2 = umma_idesc_f16(TILE_M, C);
+      uint32_t i1 = 0, i2 = 0, g = 0;
       int lt = 0;
       bool pending = false;
       uint32_t pg = 0;
       int pj = 0, plt = 0;
-      mbar_wait(&w_full, 0);
-      tc_fence_after();
-      auto mma2 = [&]() {
+      auto mma2 = [&]() {   // Y[yb] (+)= G_pj * W2_pj^T
         const uint32_t hb = pg & 1;
-        const int yb = plt & 1;
-        const uint32_t yuse = plt >> 1;
+        const int yb = K::NYBUF == 2 ? (plt & 1) : 0;
         mbar_wait(&gelu_done[hb], (pg >> 1) & 1);
-        if (pj == 0) mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + K::TM_Y + yb * 128;
-        for (int kb = 0; kb < 2; ++kb) {
+        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+        for (int kb = 0; kb < 2; ++kb, ++i2) {
+          const int s = i2 % K::R2;
+          mbar_wait(&r2_full[s], (i2 / K::R2) & 1);
+          tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_HS + (hb * 2 + kb) * KBYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_W2 + (pj * 2 + kb) * K::W2H_KB));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_ss_pair(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
-                             (pj > 0 || kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
+                        (pj > 0 || kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r2_empty[s]);
         }
-        tc_commit_pair(&hs_empty[hb], 3);
-        if (pj == K::NCH - 1) tc_commit_pair(&y_full[yb], 3);
+        tc_commit(&hs_empty[hb]);
+        if (pj == K::NCH - 1) tc_commit(&y_full[yb]);
       };
-      for (int64_t pt = cluster_id; pt < p.tiles; pt += n_clusters, ++lt) {
-        const int xb = lt & 1;
-        const uint32_t xuse = lt >> 1;
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+        const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
+        const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
+        const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
+        if (pending) { mma2(); pending = false; }   // the previous tile's last fc2 chunk comes first in the weight ring
+        // ---- MMA0: P = attn_out * Wp^T into this tile's (idle) fc2 accumulator
         mbar_wait(&x_full[xb], xuse & 1);
-        mbar_wait(&xp_ready[xb], xuse & 1);
+        mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
+        tc_fence_after();
+        {
+          const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+          for (int kb = 0; kb < K::KB1; ++kb, ++i2) {
+            const int s = i2 % K::R2;
+            mbar_wait(&r2_full[s], (i2 / K::R2) & 1);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
+            const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r2_empty[s]);
+          }
+          tc_commit(&p_full[yb]);
+        }
+        // ---- fc1 / fc2 over the hidden chunks, on x1 (written over the attn_out tile by the epilogue warps)
+        mbar_wait(&x1_ready[xb], xuse & 1);
         tc_fence_after();
         for (int j = 0; j < K::NCH; ++j, ++g) {
           const uint32_t hb = g & 1;
           const uint32_t d = tmem_base + K::TM_H + hb * 128;
-          for (int kb = 0; kb < K::KB1; ++kb) {
+          for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
+            const int s = i1 % K::R1;
+            mbar_wait(&r1_full[s], (i1 / K::R1) & 1);
+            tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_W1 + (j * K::KB1 + kb) * K::W1H_KB));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
             const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
             for (int k = 0; k < ksteps; ++k)
-              umma_f16_ss_pair(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1,
-                               (kb > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r1_empty[s]);
           }
-          tc_commit_pair(&h_full[hb], 3);
-          if (j == K::NCH - 1) tc_commit_pair(&x_empty[xb], 3);
+          tc_commit(&h_full[hb]);
+          if (j == K::NCH - 1) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
           if (pending) mma2();
           pending = true; pg = g; pj = j; plt = lt;
         }
@@ -553,7 +579,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
       if (pending) mma2();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (both CTAs)
+    // ------------------------------------------------------------------ epilogue warps
     const int e = warp - 2;
     const int q = warp & 3;
     const int quarter = e >> 2;
@@ -561,61 +587,85 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float2* hc = reinterpret_cast<const float2*>(smem + K::OFF_HC);
     const float* b2s = reinterpret_cast<const float*>(smem + K::OFF_B2);
+    const float* bps = reinterpret_cast<const float*>(smem + OFF_BP);
     float2* stats = reinterpret_cast<float2*>(smem + K::OFF_ST);
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t g = 0;
     int lt = 0;
-    MLP_T_DECL;
-    for (int64_t pt = cluster_id; pt < p.tiles; pt += n_clusters, ++lt) {
-      const int xb = lt & 1;
-      const uint32_t xuse = lt >> 1;
-      MLP_T_START;
-      mbar_wait(&x_full[xb], xuse & 1);
-      MLP_T(0);
-      const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
+    for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+      const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+      const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
+      const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
+      const int64_t m = tile * TILE_M + row;
+      const bool valid = m < p.M;
+      // ---- EPI0: shortcut (global) issued first, then P from TMEM
       uint4 res[K::QCH];
-      float s1 = 0.f, s2 = 0.f;
       {
-        const uint4 first = lds128(xs + row * 128 + (sw << 4));
-        const float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(first.x & 0xffffu)));
+        const __half* srow = p.shortcut + (valid ? m : 0) * C + quarter * K::QC;
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) res[i] = valid ? __ldg(reinterpret_cast<const uint4*>(srow + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      mbar_wait(&p_full[yb], yuse & 1);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f, k0 = 0.f;
+      {
+        const uint32_t tp = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
+        uint32_t pv[K::QC];
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) tmem_ld8(tp + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&pv[i * 8]));
+        tmem_ld_wait();
+        const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) {
-          const int gi = quarter * K::QCH + i;
-          const int kb = gi >> 3, ch = gi & 7;
-          res[i] = lds128(xs + kb * KBYTES + row * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4));
-          const __half2* h2 = reinterpret_cast<const __half2*>(&res[i]);
+          const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
+          const float* bb = bps + quarter * K::QC + i * 8;
+          uint4 o;
+          __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 f = __half22float2(h2[t]);
+            const float2 r = __half22float2(r2[t]);
+            o2[t] = __floats2half2_rn(__uint_as_float(pv[i * 8 + 2 * t]) + bb[2 * t] + r.x, __uint_as_float(pv[i * 8 + 2 * t + 1]) + bb[2 * t + 1] + r.y);
+            const float2 f = __half22float2(o2[t]);   // statistics on the rounded stream values, as a separate LayerNorm pass would see them
+            if (i == 0 && t == 0) k0 = f.x;
             const float d0 = f.x - k0, d1 = f.y - k0;
             s1 += d0 + d1;
             s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
           }
+          res[i] = o;   // x1: residual of the second add, and the fc1 operand
+          const int gi = quarter * K::QCH + i;
+          sts128(xs + (gi >> 3) * KBYTES + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4), o);
         }
+        fence_proxy_async_smem();
+        // per-quarter (mean, M2) around the quarter's own shift, merged over the 4 quarters (parallel variance)
+        const float mq = k0 + s1 * (1.0f / K::QC);
+        const float m2q = s2 - s1 * s1 * (1.0f / K::QC);
         float2* st = stats + (lt & 1) * 4 * 128;
-        st[quarter * 128 + row] = make_float2(s1, s2);
+        st[quarter * 128 + row] = make_float2(mq, m2q);
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&x_empty[xb]);
+        if (lane == 0) mbar_arrive(&x1_ready[xb]);
         named_bar_sync(1, EPI_THREADS);
-        s1 = 0.f; s2 = 0.f;
+        float mean = 0.f, m2 = 0.f;
+        float mqs[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 v = st[t * 128 + row];
-          s1 += v.x; s2 += v.y;
+          mqs[t] = v.x; mean += v.x; m2 += v.y;
         }
-        const float ms = s1 * (1.0f / C);
-        const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
+        mean *= 0.25f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) m2 = fmaf(static_cast<float>(K::QC) * (mqs[t] - mean), mqs[t] - mean, m2);
+        const float var = fmaxf(m2 * (1.0f / C), 0.f);
         const float rstd = rsqrtf(var + 1e-5f);
         s1 = rstd;
-        s2 = -(k0 + ms) * rstd;
+        s2 = -mean * rstd;
       }
       const float a = s1, b = s2;
-      MLP_T(1);
+      // ---- GELU passes
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
         mbar_wait(&h_full[hb], ph);
         tc_fence_after();
-        MLP_T(2);
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         tmem_ld_wait();
@@ -623,15 +673,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float4 c2 = hc4[i];   // (s, b1f) of two consecutive hidden columns (warp-uniform address: broadcast)
+          const float4 c2 = hc4[i];
           const float h0 = fmaf(a, __uint_as_float(v[2 * i]), fmaf(b, c2.x, c2.y));
           const float h1 = fmaf(a, __uint_as_float(v[2 * i + 1]), fmaf(b, c2.z, c2.w));
           const __half2 x2 = __floats2half2_rn(h0, h1);
           w[i] = gelu_fast_h2(*reinterpret_cast<const uint32_t*>(&x2));
         }
-        MLP_T(3);
         mbar_wait(&hs_empty[hb], ph ^ 1);
-        MLP_T(4);
         const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -639,25 +687,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&gelu_done[hb], 0);
-        MLP_T(5);
+        if (lane == 0) mbar_arrive(&gelu_done[hb]);
       }
+      // ---- output: Y + b2 + x1 -> global
       {
-        const int yb = lt & 1;
-        const uint32_t yuse = lt >> 1;
         mbar_wait(&y_full[yb], yuse & 1);
         tc_fence_after();
-        MLP_T(6);
-        const uint32_t ty = tmem_base + lane_off + K::TM_Y + yb * 128 + quarter * K::QC;
+        const uint32_t ty = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
         uint32_t y[K::QC];
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) tmem_ld8(ty + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&y[i * 8]));
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&y_empty[yb], 0);
-        const int64_t m = pt * (2 * TILE_M) + rank * TILE_M + row;
-        if (m < p.M) {
+        if (lane == 0) mbar_arrive(&y_empty[yb]);
+        if (valid) {
           __half* orow = p.out + m * C + quarter * K::QC;
 #pragma unroll
           for (int i = 0; i < K::QCH; ++i) {
@@ -674,21 +718,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
             *reinterpret_cast<uint4*>(orow + i * 8) = o;
           }
         }
-        MLP_T(7);
       }
     }
-#if SUNET_KERNEL_TIMING
-    if (p.timing && lane == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
-    }
-#endif
   }
   tc_fence_before();
-  cluster_sync_all();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 512);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -741,33 +778,6 @@ static void mlp_timing_report(const char* what, int C, unsigned grid, const long
 }
 
 template <int C>
-int launch_pair_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
-  using K = PairCfg<C>;
-  static bool configured = false;
-  if (!configured) {
-    SUNET_CUDA(cudaFuncSetAttribute(mlp_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    configured = true;
-  }
-  alignas(64) CUtensorMap tmX;
-  SUNET_TRY(make_tmap_2d_f16(&tmX, x, C, M, C, TILE_M));
-  Params prm;
-  prm.hconst = reinterpret_cast<const float2*>(p.hconst);
-  prm.b2 = p.b2;
-  prm.out = out;
-  prm.M = M;
-  prm.tiles = (M + 2 * TILE_M - 1) / (2 * TILE_M);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  const int64_t clusters = sms / 2;
-  const unsigned grid = static_cast<unsigned>(2 * (prm.tiles < clusters ? prm.tiles : clusters));
-  prm.timing = mlp_timing_buf(stream);
-  SUNET_CUDA(launch_pdl(mlp_pair_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmX, p.tmW1p, p.tmW2p, prm));
-  mlp_timing_report("mlp_pair", C, grid, prm.timing, stream);
-  return 0;
-}
-
-template <int C>
 int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
   using K = Cfg<C>;
   static bool configured = false;
@@ -793,6 +803,34 @@ int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cud
   return 0;
 }
 
+template <int C>
+int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* shortcut, __half* out, int64_t M, cudaStream_t stream) {
+  using K = Cfg<C>;
+  constexpr int SMEM = K::SMEM + C * 4;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget (proj variant)");
+  static bool configured = false;
+  if (!configured) {
+    SUNET_CUDA(cudaFuncSetAttribute(mlp_proj_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  alignas(64) CUtensorMap tmX;
+  SUNET_TRY(make_tmap_2d_f16(&tmX, attn_out, C, M, C, TILE_M));
+  ProjParams prm;
+  prm.hconst = reinterpret_cast<const float2*>(p.hconst);
+  prm.b2 = p.b2;
+  prm.bp = p.bp;
+  prm.shortcut = shortcut;
+  prm.out = out;
+  prm.M = M;
+  prm.tiles = (M + TILE_M - 1) / TILE_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
+  SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(THREADS), SMEM, stream, tmX, p.tmWp, p.tmW1, p.tmW2, prm));
+  return 0;
+}
+
 }  // namespace
 
 bool mlp_fused_supported(int C) { return C == 96 || C == 192; }
@@ -811,18 +849,39 @@ int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* b
   else SUNET_CUDA(cudaMemsetAsync(p->b2, 0, C * sizeof(float), stream));
   SUNET_TRY(make_tmap_2d_f16(&p->tmW1, p->w1g, C, HID, C, NC));
   SUNET_TRY(make_tmap_2d_f16(&p->tmW2, p->w2, HID, C, HID, C));
-  // CTA-pair kernel: each CTA loads half of a hidden chunk's fc1 rows / half of the fc2 output rows per box
-  SUNET_TRY(make_tmap_2d_f16(&p->tmW1p, p->w1g, C, HID, C, NC / 2));
-  SUNET_TRY(make_tmap_2d_f16(&p->tmW2p, p->w2, HID, C, HID, C / 2));
-  p->pair = (C == 96 && getenv("SUNET_MLP_NO_PAIR") == nullptr) ? 1 : 0;
   return 0;
+}
+
+int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, cudaStream_t stream) {
+  if (!p->wp || !p->bp) return fail(SUNET_E_ARG, "fused mlp: proj pack buffers not allocated");
+  const int C = p->C;
+  cast_f16_kernel<<<148, 256, 0, stream>>>(wp, p->wp, static_cast<size_t>(C) * C);
+  SUNET_CHECK_LAUNCH();
+  if (bp) SUNET_CUDA(cudaMemcpyAsync(p->bp, bp, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  else SUNET_CUDA(cudaMemsetAsync(p->bp, 0, C * sizeof(float), stream));
+  SUNET_TRY(make_tmap_2d_f16(&p->tmWp, p->wp, C, C, C, C));
+  p->has_proj = 1;
+  return 0;
+}
+
+int mlp_proj_fused_launch(const MlpFusedPack& p, const __half* attn_out, const __half* shortcut, __half* out, int64_t M, cudaStream_t stream) {
+  if (!p.has_proj) return fail(SUNET_E_STATE, "fused mlp: proj weights not packed");
+  if (M <= 0 || M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "fused mlp: bad row count %lld", (long long)M);
+  if ((reinterpret_cast<uintptr_t>(attn_out) & 15) || (reinterpret_cast<uintptr_t>(shortcut) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(SUNET_E_ALIGN, "fused mlp: attn_out/shortcut/out must be 16-byte aligned");
+  if (attn_out == out) return fail(SUNET_E_ARG, "fused mlp: out must not alias attn_out (tiles of other CTAs are still being read)");
+  switch (p.C) {
+    case 96: return launch_proj_t<96>(p, attn_out, shortcut, out, M, stream);
+    case 192: return launch_proj_t<192>(p, attn_out, shortcut, out, M, stream);
+    default: return fail(SUNET_E_SHAPE, "fused mlp: C=%d not instantiated", p.C);
+  }
 }
 
 int mlp_fused_launch(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
   if (M <= 0 || M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "fused mlp: bad row count %lld", (long long)M);
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "fused mlp: x/out must be 16-byte aligned");
   switch (p.C) {
-    case 96: return p.pair ? launch_pair_t<96>(p, x, out, M, stream) : launch_t<96>(p, x, out, M, stream);
+    case 96: return launch_t<96>(p, x, out, M, stream);
     case 192: return launch_t<192>(p, x, out, M, stream);
     default: return fail(SUNET_E_SHAPE, "fused mlp: C=%d not instantiated", p.C);
   }

@@ -17,17 +17,22 @@ struct MlpFusedPack {
   __half* w2 = nullptr;      // [C][4C]  fp16( fc2.weight )
   float* hconst = nullptr;   // [4C][2]  (s_n = sum_k w1g[n,k],  b1f_n = fc1.bias[n] + sum_k fc1.weight[n,k] * beta[k])
   float* b2 = nullptr;       // [C]
+  __half* wp = nullptr;      // [C][C]   fp16( attn.proj.weight )   (proj + shortcut + MLP variant)
+  float* bp = nullptr;       // [C]      attn.proj.bias
+  int has_proj = 0;
   alignas(64) CUtensorMap tmW1;
   alignas(64) CUtensorMap tmW2;
-  alignas(64) CUtensorMap tmW1p;  // CTA-pair kernel: half-tile boxes
-  alignas(64) CUtensorMap tmW2p;
-  int pair = 0;                   // 1: run the cta_group::2 kernel with resident weights (C = 96)
+  alignas(64) CUtensorMap tmWp;
 };
 
 bool mlp_fused_supported(int C);
 // fp32 parameters (device) -> pack; w1g / w2 / hconst / b2 must already be allocated by the caller
 int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* beta, const float* w1, const float* b1,
                       const float* w2, const float* b2, cudaStream_t stream);
+// optional: attn.proj weights for the proj + shortcut + MLP kernel (wp / bp allocated by the caller)
+int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, cudaStream_t stream);
+// out = x1 + Mlp(LN(x1)),  x1 = shortcut + attn_out Wp^T + bp   (SUNet_detail.py:136, :261-262); out may alias shortcut, not attn_out
+int mlp_proj_fused_launch(const MlpFusedPack& p, const __half* attn_out, const __half* shortcut, __half* out, int64_t M, cudaStream_t stream);
 // x, out: [M][C] fp16 row-major (out may alias x)
 int mlp_fused_launch(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream);
 

@@ -113,6 +113,7 @@ struct Linear {
   __half* w = nullptr;
   float* b = nullptr;
   int N = 0, K = 0;
+  int res_fold = 0;   // 1: the last N columns of w are an identity block (residual folded in as a K segment)
 };
 
 static int pack_linear(Arena& ar, const Params& P, const std::string& wkey, const std::string& bkey, int N, int K, Linear* L,
@@ -146,8 +147,10 @@ static int run_linear(Ctx& c, const Linear& L, const __half* A, int64_t lda, int
   a.A1 = A1; a.lda1 = lda1; a.K1 = K1;
   a.W = L.w; a.ldw = L.K; a.M = M; a.N = L.N;
   a.bias = L.b; a.act = act; a.prelu = prelu; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.out_f32 = out_f32;
-  const double K = L.K;
-  const double bytes = 2.0 * M * K + 2.0 * L.N * K + (out_f32 ? 4.0 : 2.0) * M * L.N + (R ? 2.0 * M * L.N : 0.0);
+  if (L.res_fold) a.force_block_n = L.N;   // one N tile per row block: a row's shortcut columns are only read by the tile that writes them
+  // algorithmic figures: the identity block of a folded residual is not counted as FLOPs, its operand is the residual read
+  const double K = L.res_fold ? L.K - L.N : L.K;
+  const double bytes = 2.0 * M * K + 2.0 * L.N * K + (out_f32 ? 4.0 : 2.0) * M * L.N + ((R || L.res_fold) ? 2.0 * M * L.N : 0.0);
   RUN(c, K_GEMM, 2.0 * M * L.N * K, bytes, gemm_run(a, c.stream));
   return 0;
 }
@@ -163,6 +166,7 @@ struct AttnPack {  // WindowAttention parameters (SUNet_detail.py:83-105)
   int dim = 0, heads = 0;
   float scale = 1.f;
   Linear qkv, proj;
+  Linear proj_res;   // [proj.weight | I]: proj + shortcut as one two-segment GEMM (dims whose output is a single N tile)
   float* table = nullptr;
   int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int heads_, double qk_scale, cudaStream_t s) {
     dim = dim_; heads = heads_;
@@ -172,6 +176,13 @@ struct AttnPack {  // WindowAttention parameters (SUNet_detail.py:83-105)
     // attention core works in the exp2 domain (its bias table / mask are scaled the same way when staged)
     SUNET_TRY(pack_linear(ar, P, pre + "qkv.weight", pre + "qkv.bias", 3 * dim, dim, &qkv, s, dim, scale * 1.4426950408889634f));
     SUNET_TRY(pack_linear(ar, P, pre + "proj.weight", pre + "proj.bias", dim, dim, &proj, s));
+    if (dim <= 256 && dim % 16 == 0 && getenv("SUNET_NO_RESIDUAL_FOLD") == nullptr) {
+      const float* w;
+      SUNET_TRY(P.get(pre + "proj.weight", static_cast<int64_t>(dim) * dim, &w));
+      proj_res.N = dim; proj_res.K = 2 * dim; proj_res.b = proj.b; proj_res.res_fold = 1;
+      SUNET_TRY(ar.alloc_t(&proj_res.w, static_cast<size_t>(dim) * 2 * dim));
+      SUNET_TRY(pack_weight_residual_f16(w, proj_res.w, dim, dim, s));
+    }
     SUNET_TRY(copy_vec(ar, P, pre + "relative_position_bias_table", 225 * heads, &table, s));
     return 0;
   }
@@ -233,6 +244,14 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       SUNET_TRY(ar.alloc_t(&mf.hconst, static_cast<size_t>(8) * dim));
       SUNET_TRY(ar.alloc_t(&mf.b2, dim));
       SUNET_TRY(mlp_fused_prepack(&mf, dim, gw, gb, w1, b1, w2, b2v, s));
+      if (getenv("SUNET_NO_FUSED_PROJ") == nullptr) {   // attn.proj + first residual ride in front of the MLP kernel
+        const float *wp, *bp = nullptr;
+        SUNET_TRY(P.get(pre + "attn.proj.weight", static_cast<int64_t>(dim) * dim, &wp));
+        if (P.has(pre + "attn.proj.bias")) SUNET_TRY(P.get(pre + "attn.proj.bias", dim, &bp));
+        SUNET_TRY(ar.alloc_t(&mf.wp, static_cast<size_t>(dim) * dim));
+        SUNET_TRY(ar.alloc_t(&mf.bp, dim));
+        SUNET_TRY(mlp_fused_set_proj(&mf, wp, bp, s));
+      }
     } else {
       SUNET_TRY(mlp.pack(ar, P, pre + "mlp.", dim, 4 * dim, dim, s));
     }
@@ -258,7 +277,15 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
       RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_launch(a, c.stream));             // :118-135, :236-257
     }
-    SUNET_TRY(run_linear(c, attn.proj, O, dim, M, x_out, dim, ACT_NONE, nullptr, x_in, dim));   // :136, :261
+    if (use_mf && mf.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one kernel
+      RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim, mlp_proj_fused_launch(mf, O, x_in, x_out, M, c.stream));
+      return 0;
+    }
+    if (attn.proj_res.w) {   // :136, :261 - the shortcut rides the TMA ring as a second K segment against an identity block
+      SUNET_TRY(run_linear(c, attn.proj_res, O, dim, M, x_out, dim, ACT_NONE, nullptr, nullptr, 0, 0, x_in, dim, dim));
+    } else {
+      SUNET_TRY(run_linear(c, attn.proj, O, dim, M, x_out, dim, ACT_NONE, nullptr, x_in, dim));   // :136, :261
+    }
     if (use_mf) {
       RUN(c, K_MLP_FUSED, 16.0 * M * dim * dim, 4.0 * M * dim, mlp_fused_launch(mf, x_out, x_out, M, c.stream));               // :262 (norm2, mlp, +res)
       return 0;
