@@ -20,6 +20,17 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(h, th, h);
 }
 
+// GELU(x) from u = x / 2 (the caller pre-scales):  u + u * tanh(u * (2 c0 + 8 c1 u^2 + 32 c2 u^4)), same fit as gelu_fast;
+// 7 FMA-pipe instructions + one MUFU per element, all fp32.
+__device__ __forceinline__ float gelu_half_arg(float u) {
+  const float t = fminf(u * u, 12.25f);
+  float p = fmaf(t, -1.1248591167e-02f, 2.9604525738e-01f);
+  p = fmaf(t, p, 1.5950157421f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
+  return fmaf(u, th, u);
+}
+
 // Packed-half2 variant for the fc1 epilogue (the result is stored as fp16 anyway): 5 instructions per element.
 // t = min(u^2, 49) keeps the odd polynomial monotone for any |x| (tanh saturates to +-1 long before).
 __device__ __forceinline__ uint32_t gelu_fast_h2(uint32_t xbits) {

@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     __syncwarp();
   }
   uint32_t xph = 1;   // parity of the next x_ready phase
+  uint32_t md_ok = 0;  // early-test result for the current item's mma_done phase
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long next_tile = tile + gridDim.x;
     const bool has_next_tile = next_tile < tiles;
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       const bool last_g = g == K::NG - 1;
       const bool has_next = !last_g || has_next_tile;
       AF_T_START;
-      mbar_wait(&mma_done, item & 1);
+      mbar_wait_hint(&mma_done, item & 1, md_ok);
       tc_fence_after();
       AF_T(0);
       // the MMAs of this item have read the weight buffer (and, for the last group, the token tile): refill them
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
         }
       }
       AF_T(4);
+      const uint32_t md_next = has_next ? mbar_test(&mma_done, (item + 1) & 1) : 0u;   // looked up under the scatter (a test costs ~170 clk)
       __syncthreads();   // (C) O rows of every unit parked in the q tiles
       AF_T(5);
       // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map): the 4 threads
@@ -573,6 +575,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
         }
       }
       AF_T(6);
+      md_ok = md_next;
       __syncthreads();   // (D) q tiles free for the next drain
       AF_T(7);
     }

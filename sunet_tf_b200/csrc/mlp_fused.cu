@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 //          sums merged with the parallel-variance formula, no cross-thread shift needed)
 //   then fc1 / GELU / fc2 / output exactly as in mlp_fused_kernel.
 struct ProjParams {
-  const float2* hconst;
+  const float* hbias;     // 0.5 * (fc1.bias + fc1.weight beta) [4C]
   const float* b2;
   const float* bp;        // proj.bias [C]
   const __half* shortcut; // block input x [M][C] (may alias out: each thread reads and later writes the same elements)
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     tmem_relinquish();
   }
   {
-    float2* hc = reinterpret_cast<float2*>(smem + K::OFF_HC);
-    for (int i = threadIdx.x; i < K::HID; i += THREADS) hc[i] = __ldg(p.hconst + i);
+    float* hb = reinterpret_cast<float*>(smem + K::OFF_HC);
+    for (int i = threadIdx.x; i < K::HID; i += THREADS) hb[i] = __ldg(p.hbias + i);
     float* b2s = reinterpret_cast<float*>(smem + K::OFF_B2);
     float* bps = reinterpret_cast<float*>(smem + OFF_BP);
     for (int i = threadIdx.x; i < C; i += THREADS) { b2s[i] = __ldg(p.b2 + i); bps[i] = __ldg(p.bp + i); }
@@ -507,16 +507,33 @@ __global__ void __launch_bounds__(THREADS, 1)
       bool pending = false;
       uint32_t pg = 0;
       int pj = 0, plt = 0;
+      // ring-slot states are looked up one slot ahead (an mbarrier test costs ~170 clk even on a completed phase; this thread's
+      // serial latency sits on the GELU -> fc2 -> next fc1 critical path)
+      uint32_t r1_ok = mbar_test(&r1_full[0], 0), r2_ok = mbar_test(&r2_full[0], 0);
+      auto r1_acquire = [&]() -> int {
+        const int s = i1 % K::R1;
+        mbar_wait_hint(&r1_full[s], (i1 / K::R1) & 1, r1_ok);
+        ++i1;
+        r1_ok = mbar_test(&r1_full[i1 % K::R1], (i1 / K::R1) & 1);
+        tc_fence_after();
+        return s;
+      };
+      auto r2_acquire = [&]() -> int {
+        const int s = i2 % K::R2;
+        mbar_wait_hint(&r2_full[s], (i2 / K::R2) & 1, r2_ok);
+        ++i2;
+        r2_ok = mbar_test(&r2_full[i2 % K::R2], (i2 / K::R2) & 1);
+        tc_fence_after();
+        return s;
+      };
       auto mma2 = [&]() {   // Y[yb] (+)= G_pj * W2_pj^T
         const uint32_t hb = pg & 1;
         const int yb = K::NYBUF == 2 ? (plt & 1) : 0;
         mbar_wait(&gelu_done[hb], (pg >> 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
-        for (int kb = 0; kb < 2; ++kb, ++i2) {
-          const int s = i2 % K::R2;
-          mbar_wait(&r2_full[s], (i2 / K::R2) & 1);
-          tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          const int s = r2_acquire();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_HS + (hb * 2 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
 #pragma unroll
@@ -540,10 +557,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_after();
         {
           const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
-          for (int kb = 0; kb < K::KB1; ++kb, ++i2) {
-            const int s = i2 % K::R2;
-            mbar_wait(&r2_full[s], (i2 / K::R2) & 1);
-            tc_fence_after();
+          for (int kb = 0; kb < K::KB1; ++kb) {
+            const int s = r2_acquire();
             const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
             const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
@@ -559,10 +574,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int j = 0; j < K::NCH; ++j, ++g) {
           const uint32_t hb = g & 1;
           const uint32_t d = tmem_base + K::TM_H + hb * 128;
-          for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
-            const int s = i1 % K::R1;
-            mbar_wait(&r1_full[s], (i1 / K::R1) & 1);
-            tc_fence_after();
+          for (int kb = 0; kb < K::KB1; ++kb) {
+            const int s = r1_acquire();
             const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
             const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
@@ -585,36 +598,45 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int quarter = e >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const float2* hc = reinterpret_cast<const float2*>(smem + K::OFF_HC);
+    const float* hbv = reinterpret_cast<const float*>(smem + K::OFF_HC);
     const float* b2s = reinterpret_cast<const float*>(smem + K::OFF_B2);
     const float* bps = reinterpret_cast<const float*>(smem + OFF_BP);
     float2* stats = reinterpret_cast<float2*>(smem + K::OFF_ST);
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t g = 0;
     int lt = 0;
+    // the shortcut slice of this thread's row is fetched one tile ahead (global latency ~1-2 us against a ~5 us tile)
+    constexpr bool PREFETCH = C <= 96;   // wider rows do not have the registers for it (96-register cap at 576 threads)
+    uint4 nxt[K::QCH];
+    auto fetch_shortcut = [&](int64_t tile) {
+      const int64_t mm = tile * TILE_M + row;
+      const bool ok = tile < p.tiles && mm < p.M;
+      const __half* srow = p.shortcut + (ok ? mm : 0) * C + quarter * K::QC;
+#pragma unroll
+      for (int i = 0; i < K::QCH; ++i) nxt[i] = ok ? __ldg(reinterpret_cast<const uint4*>(srow + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    if (PREFETCH) fetch_shortcut(blockIdx.x);
+    uint32_t h_ok = 0;
     for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
       const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
       const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
       const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
       const int64_t m = tile * TILE_M + row;
       const bool valid = m < p.M;
-      // ---- EPI0: shortcut (global) issued first, then P from TMEM
+      // ---- EPI0: x1 = P + bp + shortcut
+      if (!PREFETCH) fetch_shortcut(tile);
       uint4 res[K::QCH];
-      {
-        const __half* srow = p.shortcut + (valid ? m : 0) * C + quarter * K::QC;
 #pragma unroll
-        for (int i = 0; i < K::QCH; ++i) res[i] = valid ? __ldg(reinterpret_cast<const uint4*>(srow + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int i = 0; i < K::QCH; ++i) res[i] = nxt[i];
       mbar_wait(&p_full[yb], yuse & 1);
       tc_fence_after();
-      float s1 = 0.f, s2 = 0.f, k0 = 0.f;
       {
         const uint32_t tp = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
         uint32_t pv[K::QC];
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) tmem_ld8(tp + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&pv[i * 8]));
         tmem_ld_wait();
-        const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
+        float s1 = 0.f, s2 = 0.f, k0 = 0.f;
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) {
           const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
@@ -631,19 +653,13 @@ __global__ void __launch_bounds__(THREADS, 1)
             s1 += d0 + d1;
             s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
           }
-          res[i] = o;   // x1: residual of the second add, and the fc1 operand
-          const int gi = quarter * K::QCH + i;
-          sts128(xs + (gi >> 3) * KBYTES + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4), o);
+          res[i] = o;   // x1 (fp16 stream value): residual of the second add
         }
-        fence_proxy_async_smem();
         // per-quarter (mean, M2) around the quarter's own shift, merged over the 4 quarters (parallel variance)
         const float mq = k0 + s1 * (1.0f / K::QC);
         const float m2q = s2 - s1 * s1 * (1.0f / K::QC);
         float2* st = stats + (lt & 1) * 4 * 128;
         st[quarter * 128 + row] = make_float2(mq, m2q);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&x1_ready[xb]);
         named_bar_sync(1, EPI_THREADS);
         float mean = 0.f, m2 = 0.f;
         float mqs[4];
@@ -655,31 +671,53 @@ __global__ void __launch_bounds__(THREADS, 1)
         mean *= 0.25f;
 #pragma unroll
         for (int t = 0; t < 4; ++t) m2 = fmaf(static_cast<float>(K::QC) * (mqs[t] - mean), mqs[t] - mean, m2);
-        const float var = fmaxf(m2 * (1.0f / C), 0.f);
-        const float rstd = rsqrtf(var + 1e-5f);
-        s1 = rstd;
-        s2 = -mean * rstd;
+        const float rstd = rsqrtf(fmaxf(m2 * (1.0f / C), 0.f) + 1e-5f);
+        const float nb = -mean * rstd;
+        // norm2 without its affine part (folded into fc1 at pre-pack), written over the attn_out tile as the fc1 operand
+        const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) {
+          const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
+          uint4 o;
+          __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(r2[t]);
+            o2[t] = __floats2half2_rn(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
+          }
+          const int gi = quarter * K::QCH + i;
+          sts128(xs + (gi >> 3) * KBYTES + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4), o);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x1_ready[xb]);
       }
-      const float a = s1, b = s2;
       // ---- GELU passes
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
-        mbar_wait(&h_full[hb], ph);
+        mbar_wait_hint(&h_full[hb], ph, h_ok);
         tc_fence_after();
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
+        const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);   // looked up under the TMEM load / GELU math
+        if (PREFETCH && j == K::NCH - 2) fetch_shortcut(tile + gridDim.x);   // next tile's shortcut, ~1.5 chunks ahead of its use
         tmem_ld_wait();
-        const float4* hc4 = reinterpret_cast<const float4*>(hc + j * NC + quarter * 32);
+        // u = 0.5 * fc1(LN(x1)) = D + hbias (fc1 weights and bias are pre-scaled by 0.5); GELU(2u) = u + u * tanh(u * P(u^2)), fp32 on
+        // the FMA pipe (7 FMA-pipe clocks per element against 8 MUFU clocks: HFMA2 issues at half rate, so packed-half math is no cheaper)
+        const float4* hb4 = reinterpret_cast<const float4*>(hbv + j * NC + quarter * 32);
         uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 c2 = hc4[i];
-          const float h0 = fmaf(a, __uint_as_float(v[2 * i]), fmaf(b, c2.x, c2.y));
-          const float h1 = fmaf(a, __uint_as_float(v[2 * i + 1]), fmaf(b, c2.z, c2.w));
-          const __half2 x2 = __floats2half2_rn(h0, h1);
-          w[i] = gelu_fast_h2(*reinterpret_cast<const uint32_t*>(&x2));
+        for (int i = 0; i < 8; ++i) {
+          const float4 bq = hb4[i];   // warp-uniform address: broadcast
+          const float g0 = gelu_half_arg(__uint_as_float(v[4 * i + 0]) + bq.x), g1 = gelu_half_arg(__uint_as_float(v[4 * i + 1]) + bq.y);
+          const float g2 = gelu_half_arg(__uint_as_float(v[4 * i + 2]) + bq.z), g3 = gelu_half_arg(__uint_as_float(v[4 * i + 3]) + bq.w);
+          const __half2 p0 = __floats2half2_rn(g0, g1), p1 = __floats2half2_rn(g2, g3);
+          w[2 * i] = *reinterpret_cast<const uint32_t*>(&p0);
+          w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&p1);
         }
-        mbar_wait(&hs_empty[hb], ph ^ 1);
+        mbar_wait_hint(&hs_empty[hb], ph ^ 1, hs_ok);
+        h_ok = j + 1 < K::NCH ? mbar_test(&h_full[hb ^ 1], ((g + 1) >> 1) & 1) : 0u;   // next chunk's accumulator, looked up under the stores
         const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -750,6 +788,22 @@ __global__ void mlp_fold_ln_kernel(const float* __restrict__ w1, const float* __
   if (lane == 0) hconst[n] = make_float2(s, bb + (b1 ? b1[n] : 0.f));
 }
 
+// proj variant: W1h = fp16(0.5 * W1 * gamma), hbias = 0.5 * (b1 + W1 beta)  (LayerNorm runs in the kernel, GELU takes u = x / 2)
+__global__ void mlp_fold_half_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, __half* __restrict__ w1h, float* __restrict__ hbias, int HID, int C) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= HID) return;
+  float bb = 0.f;
+  for (int k = lane; k < C; k += 32) {
+    const float w = w1[static_cast<size_t>(n) * C + k];
+    w1h[static_cast<size_t>(n) * C + k] = __float2half_rn(0.5f * w * gamma[k]);
+    bb = fmaf(w, beta[k], bb);
+  }
+  for (int o = 16; o > 0; o >>= 1) bb += __shfl_xor_sync(0xffffffffu, bb, o);
+  if (lane == 0) hbias[n] = 0.5f * (bb + (b1 ? b1[n] : 0.f));
+}
+
 __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = __float2half_rn(src[i]);
@@ -816,7 +870,7 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   alignas(64) CUtensorMap tmX;
   SUNET_TRY(make_tmap_2d_f16(&tmX, attn_out, C, M, C, TILE_M));
   ProjParams prm;
-  prm.hconst = reinterpret_cast<const float2*>(p.hconst);
+  prm.hbias = p.hbias;
   prm.b2 = p.b2;
   prm.bp = p.bp;
   prm.shortcut = shortcut;
@@ -827,7 +881,7 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
-  SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(THREADS), SMEM, stream, tmX, p.tmWp, p.tmW1, p.tmW2, prm));
+  SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(THREADS), SMEM, stream, tmX, p.tmWp, p.tmW1h, p.tmW2, prm));
   return 0;
 }
 
@@ -852,9 +906,13 @@ int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* b
   return 0;
 }
 
-int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, cudaStream_t stream) {
-  if (!p->wp || !p->bp) return fail(SUNET_E_ARG, "fused mlp: proj pack buffers not allocated");
+int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, const float* gamma, const float* beta, const float* w1,
+                       const float* b1, cudaStream_t stream) {
+  if (!p->wp || !p->bp || !p->w1h || !p->hbias) return fail(SUNET_E_ARG, "fused mlp: proj pack buffers not allocated");
   const int C = p->C;
+  mlp_fold_half_kernel<<<(4 * C + 7) / 8, 256, 0, stream>>>(w1, b1, gamma, beta, p->w1h, p->hbias, 4 * C, C);
+  SUNET_CHECK_LAUNCH();
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW1h, p->w1h, C, 4 * C, C, NC));
   cast_f16_kernel<<<148, 256, 0, stream>>>(wp, p->wp, static_cast<size_t>(C) * C);
   SUNET_CHECK_LAUNCH();
   if (bp) SUNET_CUDA(cudaMemcpyAsync(p->bp, bp, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));

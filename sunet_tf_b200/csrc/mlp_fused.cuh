@@ -19,18 +19,23 @@ struct MlpFusedPack {
   float* b2 = nullptr;       // [C]
   __half* wp = nullptr;      // [C][C]   fp16( attn.proj.weight )   (proj + shortcut + MLP variant)
   float* bp = nullptr;       // [C]      attn.proj.bias
+  __half* w1h = nullptr;     // [4C][C]  fp16( 0.5 * fc1.weight * gamma[k] )   (proj variant: LayerNorm runs in the kernel)
+  float* hbias = nullptr;    // [4C]     0.5 * (fc1.bias + fc1.weight beta)
   int has_proj = 0;
   alignas(64) CUtensorMap tmW1;
   alignas(64) CUtensorMap tmW2;
   alignas(64) CUtensorMap tmWp;
+  alignas(64) CUtensorMap tmW1h;
 };
 
 bool mlp_fused_supported(int C);
 // fp32 parameters (device) -> pack; w1g / w2 / hconst / b2 must already be allocated by the caller
 int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* beta, const float* w1, const float* b1,
                       const float* w2, const float* b2, cudaStream_t stream);
-// optional: attn.proj weights for the proj + shortcut + MLP kernel (wp / bp allocated by the caller)
-int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, cudaStream_t stream);
+// optional: attn.proj weights (+ the norm2 / fc1 parameters again, packed differently) for the proj + shortcut + MLP kernel;
+// wp / bp / w1h / hbias allocated by the caller
+int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, const float* gamma, const float* beta, const float* w1,
+                       const float* b1, cudaStream_t stream);
 // out = x1 + Mlp(LN(x1)),  x1 = shortcut + attn_out Wp^T + bp   (SUNet_detail.py:136, :261-262); out may alias shortcut, not attn_out
 int mlp_proj_fused_launch(const MlpFusedPack& p, const __half* attn_out, const __half* shortcut, __half* out, int64_t M, cudaStream_t stream);
 // x, out: [M][C] fp16 row-major (out may alias x)

@@ -219,13 +219,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of this cluster
+// arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of this cluster.  Relaxed: the release form compiles to
+// MEMBAR.ALL.GPU per call; every caller only hands back TMEM / smem that it has finished reading (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync precede the arrive, the waiter issues tcgen05.fence::after_thread_sync)
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");

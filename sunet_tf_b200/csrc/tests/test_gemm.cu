@@ -166,6 +166,7 @@ static void test_gemm(const Case& c, bool check, int time_iters) {
 int main(int argc, char** argv) {
   if (argc >= 10 && !strcmp(argv[1], "one")) {  // one M N K act res f32 bn iters
     Case c{atoll(argv[2]), atoi(argv[3]), atoi(argv[4]), 0, 1, atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8])};
+    if (getenv("SUNET_GEMM_PAIR")) c.pair = atoi(getenv("SUNET_GEMM_PAIR"));
     test_gemm(c, false, atoi(argv[9]));
     return 0;
   }
