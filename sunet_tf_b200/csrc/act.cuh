@@ -27,7 +27,11 @@ __device__ __forceinline__ float gelu_half_arg(float u) {
   float p = fmaf(t, -1.1248591167e-02f, 2.9604525738e-01f);
   p = fmaf(t, p, 1.5950157421f);
   float th;
+#if defined(SUNET_ABLATE_TANH)
+  th = u * p;   // timing ablation only
+#else
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
+#endif
   return fmaf(u, th, u);
 }
 

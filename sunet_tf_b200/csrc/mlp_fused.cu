@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 //   EPI0 : x1 = P + bp + shortcut (global, issued before the wait) -> fp16 -> written IN PLACE over the attn_out tile as
 //          the A operand of fc1 and kept in registers as the residual; LayerNorm statistics of x1 (per-quarter shifted
 //          sums merged with the parallel-variance formula, no cross-thread shift needed)
-//   then fc1 / GELU / fc2 / output exactly as in mlp_fused_kernel.
+//   then fc1 / GELU / fc2 / output as in mlp_fused_kernel, with fc1 issued two hidden chunks ahead of fc2.
 struct ProjParams {
   const float* hbias;     // 0.5 * (fc1.bias + fc1.weight beta) [4C]
   const float* b2;
@@ -401,6 +401,7 @@ struct ProjParams {
   __half* out;
   int64_t M;
   int64_t tiles;
+  long long* timing;   // see Params::timing
 };
 
 template <int C>
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t x_full[2], x_empty[2], x1_ready[2], p_full[2];
   __shared__ __align__(8) uint64_t r1_full[K::R1], r1_empty[K::R1], r2_full[K::R2], r2_empty[K::R2];
-  __shared__ __align__(8) uint64_t h_full[2], gelu_done[2], hs_empty[2], y_full[2], y_empty[2];
+  __shared__ __align__(8) uint64_t h_full[2], h_empty[2], gelu_done[2], hs_empty[2], y_full[2], y_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(&x1_ready[i], EPI_WARPS);
       mbar_init(&p_full[i], 1);
       mbar_init(&h_full[i], 1);
+      mbar_init(&h_empty[i], EPI_WARPS);
       mbar_init(&gelu_done[i], EPI_WARPS);
       mbar_init(&hs_empty[i], 1);
       mbar_init(&y_full[i], 1);
@@ -477,25 +479,27 @@ __global__ void __launch_bounds__(THREADS, 1)
         ++i2;
       };
       if (K::NXBUF == 2 && static_cast<int64_t>(blockIdx.x) < p.tiles) load_x(blockIdx.x, 0);
-      bool have_prev = false;
+      auto load_w1 = [&](int j) {
+        for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
+          const int s = i1 % K::R1;
+          mbar_wait(&r1_empty[s], ((i1 / K::R1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&r1_full[s], KBYTES);
+          tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
+        }
+      };
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-        // fc2 ring order = MMA order: [fc2 weights of the previous tile's last chunk] [Wp] [fc2 chunk 0] ... [fc2 chunk NCH-2]
-        if (have_prev) { load_r2(&tmW2, (K::NCH - 1) * NC); load_r2(&tmW2, (K::NCH - 1) * NC + 64); }
+        // same order as the MMA issuer consumes: Wp | fc1(0) fc1(1) | { fc1(j+2), fc2(j) } ...
         if (K::NXBUF != 2) load_x(tile, lt);
         for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
         if (K::NXBUF == 2 && tile + gridDim.x < p.tiles) load_x(tile + gridDim.x, lt + 1);   // prefetch one tile ahead
+        load_w1(0);
+        if (K::NCH > 1) load_w1(1);
         for (int j = 0; j < K::NCH; ++j) {
-          for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
-            const int s = i1 % K::R1;
-            mbar_wait(&r1_empty[s], ((i1 / K::R1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&r1_full[s], KBYTES);
-            tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
-          }
-          if (j > 0) { load_r2(&tmW2, (j - 1) * NC); load_r2(&tmW2, (j - 1) * NC + 64); }
+          if (j + 2 < K::NCH) load_w1(j + 2);
+          load_r2(&tmW2, j * NC);
+          load_r2(&tmW2, j * NC + 64);
         }
-        have_prev = true;
       }
-      if (have_prev) { load_r2(&tmW2, (K::NCH - 1) * NC); load_r2(&tmW2, (K::NCH - 1) * NC + 64); }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -504,9 +508,6 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint32_t idesc2 = umma_idesc_f16(TILE_M, C);
       uint32_t i1 = 0, i2 = 0, g = 0;
       int lt = 0;
-      bool pending = false;
-      uint32_t pg = 0;
-      int pj = 0, plt = 0;
       // ring-slot states are looked up one slot ahead (an mbarrier test costs ~170 clk even on a completed phase; this thread's
       // serial latency sits on the GELU -> fc2 -> next fc1 critical path)
       uint32_t r1_ok = mbar_test(&r1_full[0], 0), r2_ok = mbar_test(&r2_full[0], 0);
@@ -526,10 +527,27 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_after();
         return s;
       };
-      auto mma2 = [&]() {   // Y[yb] (+)= G_pj * W2_pj^T
-        const uint32_t hb = pg & 1;
-        const int yb = K::NYBUF == 2 ? (plt & 1) : 0;
-        mbar_wait(&gelu_done[hb], (pg >> 1) & 1);
+      auto fc1 = [&](int xb, uint32_t gg, int j, bool last) {   // H[gg & 1] = x1 * W1h_j^T   (gg: global chunk index)
+        const uint32_t hb = gg & 1, use = gg >> 1;
+        if (use > 0) mbar_wait(&h_empty[hb], (use - 1) & 1);   // the epilogue has loaded the previous contents of this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + K::TM_H + hb * 128;
+        for (int kb = 0; kb < K::KB1; ++kb) {
+          const int s = r1_acquire();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
+          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r1_empty[s]);
+        }
+        tc_commit(&h_full[hb]);
+        if (last) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
+        (void)j;
+      };
+      auto fc2 = [&](int yb, uint32_t gg, int j) {   // Y[yb] (+)= G_j * W2_j^T
+        const uint32_t hb = gg & 1;
+        mbar_wait(&gelu_done[hb], (gg >> 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
         for (int kb = 0; kb < 2; ++kb) {
@@ -539,18 +557,17 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
-                        (pj > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                        (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
           tc_commit(&r2_empty[s]);
         }
         tc_commit(&hs_empty[hb]);
-        if (pj == K::NCH - 1) tc_commit(&y_full[yb]);
+        if (j == K::NCH - 1) tc_commit(&y_full[yb]);
       };
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
         const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
         const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
         const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
         const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
-        if (pending) { mma2(); pending = false; }   // the previous tile's last fc2 chunk comes first in the weight ring
         // ---- MMA0: P = attn_out * Wp^T into this tile's (idle) fc2 accumulator
         mbar_wait(&x_full[xb], xuse & 1);
         mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
@@ -568,28 +585,18 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
           tc_commit(&p_full[yb]);
         }
-        // ---- fc1 / fc2 over the hidden chunks, on x1 (written over the attn_out tile by the epilogue warps)
+        // ---- fc1 runs two hidden chunks ahead of fc2: an fc1 accumulator is free again as soon as the epilogue has LOADED it
+        // (h_empty, early in its GELU pass), not only when the GELU output is back in shared memory (gelu_done)
         mbar_wait(&x1_ready[xb], xuse & 1);
         tc_fence_after();
-        for (int j = 0; j < K::NCH; ++j, ++g) {
-          const uint32_t hb = g & 1;
-          const uint32_t d = tmem_base + K::TM_H + hb * 128;
-          for (int kb = 0; kb < K::KB1; ++kb) {
-            const int s = r1_acquire();
-            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
-            const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(&r1_empty[s]);
-          }
-          tc_commit(&h_full[hb]);
-          if (j == K::NCH - 1) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
-          if (pending) mma2();
-          pending = true; pg = g; pj = j; plt = lt;
+        fc1(xb, g, 0, K::NCH == 1);
+        if (K::NCH > 1) fc1(xb, g + 1, 1, K::NCH == 2);
+        for (int j = 0; j < K::NCH; ++j) {
+          if (j + 2 < K::NCH) fc1(xb, g + j + 2, j + 2, j + 2 == K::NCH - 1);
+          fc2(yb, g + j, j);
         }
+        g += K::NCH;
       }
-      if (pending) mma2();
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -617,6 +624,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     };
     if (PREFETCH) fetch_shortcut(blockIdx.x);
     uint32_t h_ok = 0;
+    MLP_T_DECL;
     for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
       const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
       const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
@@ -624,12 +632,14 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int64_t m = tile * TILE_M + row;
       const bool valid = m < p.M;
       // ---- EPI0: x1 = P + bp + shortcut
+      MLP_T_START;
       if (!PREFETCH) fetch_shortcut(tile);
       uint4 res[K::QCH];
 #pragma unroll
       for (int i = 0; i < K::QCH; ++i) res[i] = nxt[i];
       mbar_wait(&p_full[yb], yuse & 1);
       tc_fence_after();
+      MLP_T(0);
       {
         const uint32_t tp = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
         uint32_t pv[K::QC];
@@ -693,16 +703,22 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&x1_ready[xb]);
       }
+      MLP_T(1);
       // ---- GELU passes
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
         mbar_wait_hint(&h_full[hb], ph, h_ok);
         tc_fence_after();
+        MLP_T(2);
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);   // looked up under the TMEM load / GELU math
         if (PREFETCH && j == K::NCH - 2) fetch_shortcut(tile + gridDim.x);   // next tile's shortcut, ~1.5 chunks ahead of its use
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_empty[hb]);   // the accumulator may be overwritten by the fc1 of chunk g + 2
+        MLP_T(4);   // (timing builds: slot 4 = TMEM load, slot 3 = GELU math; the hs_empty wait is folded into slot 5)
         // u = 0.5 * fc1(LN(x1)) = D + hbias (fc1 weights and bias are pre-scaled by 0.5); GELU(2u) = u + u * tanh(u * P(u^2)), fp32 on
         // the FMA pipe (7 FMA-pipe clocks per element against 8 MUFU clocks: HFMA2 issues at half rate, so packed-half math is no cheaper)
         const float4* hb4 = reinterpret_cast<const float4*>(hbv + j * NC + quarter * 32);
@@ -716,6 +732,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           w[2 * i] = *reinterpret_cast<const uint32_t*>(&p0);
           w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&p1);
         }
+        MLP_T(3);
         mbar_wait_hint(&hs_empty[hb], ph ^ 1, hs_ok);
         h_ok = j + 1 < K::NCH ? mbar_test(&h_full[hb ^ 1], ((g + 1) >> 1) & 1) : 0u;   // next chunk's accumulator, looked up under the stores
         const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
@@ -726,11 +743,13 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gelu_done[hb]);
+        MLP_T(5);
       }
       // ---- output: Y + b2 + x1 -> global
       {
         mbar_wait(&y_full[yb], yuse & 1);
         tc_fence_after();
+        MLP_T(6);
         const uint32_t ty = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
         uint32_t y[K::QC];
 #pragma unroll
@@ -756,8 +775,15 @@ __global__ void __launch_bounds__(THREADS, 1)
             *reinterpret_cast<uint4*>(orow + i * 8) = o;
           }
         }
+        MLP_T(7);
       }
     }
+#if SUNET_KERNEL_TIMING
+    if (p.timing && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -881,7 +907,9 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
+  prm.timing = mlp_timing_buf(stream);
   SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(THREADS), SMEM, stream, tmX, p.tmWp, p.tmW1h, p.tmW2, prm));
+  mlp_timing_report("mlp_proj_fused (wait_p, epi0, wait_h, gelu, wait_hs, store, wait_y, out)", C, grid, prm.timing, stream);
   return 0;
 }
 
