@@ -164,6 +164,26 @@ def test_swin_block_vs_live_oracle_larger_grids(dev, dim, grid, batch):
         report(f"block-live dim{dim} grid{grid} shift{shift}", blk(x.to(dev)), ref, MODULE_TOL)
 
 
+@pytest.mark.parametrize("dim,grid,batch,shift", [(96, 16, 3, 4), (96, 24, 1, 0), (192, 16, 2, 4), (192, 8, 1, 0)])
+def test_fused_block_kernels_agree_with_the_unfused_path(dev, dim, grid, batch, shift, monkeypatch):
+    """attn_fused + mlp_proj_fused (2 launches per block) against LN / GEMM / attn_core / GEMM / mlp (the pre-fusion sequence, selected
+    by the SUNET_NO_FUSED_* switches at pre-pack time) on identical weights and inputs: two independent CUDA implementations of the
+    same block must agree to fp16 rounding of the stream (odd window counts and a single-window grid included)."""
+    from sunet_tf_b200 import SwinTransformerBlock
+    sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, shift), seed=900 + dim + shift, style="stress")
+    x = module_input((batch, grid * grid, dim), seed=901 + dim).to(dev)
+    fused = load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+    y_fused = fused(x)
+    for var in ("SUNET_NO_FUSED_ATTN", "SUNET_NO_FUSED_PROJ", "SUNET_NO_FUSED_MLP", "SUNET_NO_RESIDUAL_FOLD"):
+        monkeypatch.setenv(var, "1")
+    plain = load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+    y_plain = plain(x)
+    ref = O.swin_block(sd, "", x.cpu(), grid, grid, 8, shift, 8)
+    report(f"fused-vs-oracle dim{dim} grid{grid} shift{shift}", y_fused, ref, MODULE_TOL)
+    report(f"plain-vs-oracle dim{dim} grid{grid} shift{shift}", y_plain, ref, MODULE_TOL)
+    report(f"fused-vs-plain dim{dim} grid{grid} shift{shift}", y_fused, y_plain.cpu(), MODULE_TOL)
+
+
 def test_swin_block_default_scale_and_rect_grid(dev):
     """qk_scale=None -> head_dim**-0.5 (SUNet_detail.py:80); rectangular token grid"""
     from sunet_tf_b200 import SwinTransformerBlock
