@@ -17,7 +17,8 @@
 //   core   : per (window, head): S = q k^T + bias (+ closed-form mask), exp2 softmax, O = P V on mma.sync.m16n8k16 with
 //            register-resident S/P (K = 12/24: a 64x64xhd problem per head is below any tcgen05 tile), O parked in the q rows
 //   scatter: O rows go back through the same index map (window_reverse + un-roll).
-// C = 96 handles all 8 heads per pass (288 accumulator columns); C = 192 walks 4 groups of 2 heads (144 columns).
+// C = 96 handles all 8 heads per pass (288 accumulator columns); C = 192 walks 4 groups of 2 heads (144 columns); C = 384 walks
+// 8 single heads, with the group weights streaming through a k-block ring because they no longer fit beside the 96 KB token tile.
 #include "attn_fused.cuh"
 
 #include <stdio.h>
@@ -87,7 +88,8 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
 
 template <int C_, int GH_>
 struct FCfg {
-  static constexpr int C = C_, HEADS = 8, HD = C / 8, HD_PAD = (HD + 15) / 16 * 16, GH = GH_, NG = HEADS / GH;
+  static constexpr int C = C_, HEADS = 8, HD = C / 8, GH = GH_, NG = HEADS / GH;
+  static constexpr int HD_PAD = HD <= 16 ? 16 : (HD <= 32 ? 32 : 64);   // operand rows of 32 / 64 / 128 bytes
   static constexpr int BR = GH * HD;             // rows of one of q / k / v in a head group
   static constexpr int NGC = 3 * BR;             // accumulator columns per head group
   static constexpr int NMMA = NGC > 256 ? 3 : 1; // tcgen05.mma instructions per k-step (N <= 256 each)
@@ -97,7 +99,7 @@ struct FCfg {
   static constexpr int RB = HD_PAD * 2;          // bytes per q/k/v operand row
   static constexpr int UNIT_BYTES = 64 * RB;     // one (q|k|v, window, head) operand tile
   static constexpr int NU = 2 * GH;              // (window, head) units per pass
-  static constexpr int WPU = 16 / NU;            // warps per unit
+  static constexpr int WPU = NU >= 4 ? 16 / NU : 4;   // warps per unit (a unit has 4 query tiles: with fewer than 4 units half the warps sit the core out)
   static constexpr int MT = 4 / WPU;             // 16-row query tiles per warp
   static constexpr int QC = NGC / 4;             // accumulator columns drained by one column-quarter
   static constexpr int CPR = C / 8;              // 16-byte chunks per token row
@@ -105,7 +107,11 @@ struct FCfg {
   static constexpr int VPH = HD / VEC;
   static constexpr int VPT = BR / VEC;           // output vectors per token per pass
   static constexpr int X_BYTES = KB * 16384;
-  static constexpr int W_BYTES = KB * NGC * 128;
+  // weights of a head group: one buffer loaded at once, or (RING: when that does not fit) a ring of 64-wide k-blocks
+  static constexpr bool RING = KB * NGC * 128 > 80 * 1024;
+  static constexpr int RSTAGES = 3;
+  static constexpr int WKB_BYTES = NGC * 128;    // one k-block of a group's weights
+  static constexpr int W_BYTES = RING ? RSTAGES * WKB_BYTES : KB * NGC * 128;
   static constexpr int QKV_BYTES = 3 * NU * UNIT_BYTES;
   static constexpr int OFF_X = 0;
   static constexpr int OFF_W = OFF_X + X_BYTES;
@@ -116,7 +122,8 @@ struct FCfg {
   static constexpr uint32_t TMEM_COLS = NGC <= 256 ? 256 : 512;
   static_assert(C % 32 == 0 && HD % 4 == 0 && QC % 4 == 0, "column slices must be whole 4-column groups");
   static_assert((NPM * 128) % 1024 == 0 && NPM % 16 == 0 && NPM <= 256, "weight sub-tiles must be whole swizzle atoms");
-  static_assert(WPU >= 1 && WPU <= 4 && WPU * NU == 16 && MT * WPU == 4, "warp / unit split");
+  static_assert(WPU >= 1 && WPU <= 4 && WPU * NU <= 16 && MT * WPU == 4, "warp / unit split");
+  static_assert(!RING || NMMA == 1, "the k-block ring carries one MMA-wide sub-tile per stage");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -126,7 +133,8 @@ struct FCfg {
 template <int RB>
 __device__ __forceinline__ uint32_t op_off(int row, int ch) {
   if constexpr (RB == 32) return static_cast<uint32_t>(row * 32 + ((ch ^ ((row >> 2) & 1)) << 4));
-  else return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+  else if constexpr (RB == 64) return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+  else return static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4));
 }
 
 // One 16-row query tile of one (window, head) unit; see attn_core.cu for the register-level scheme.  tb[e][k] holds this
@@ -135,7 +143,7 @@ __device__ __forceinline__ uint32_t op_off(int row, int ch) {
 template <int HD, int MT, int MI, bool MASK>
 __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v_h, int mt, int lane, const float (&tb)[2][2 * MT + 7],
                                           bool mrow, bool mcol) {
-  constexpr int HD_PAD = (HD + 15) / 16 * 16;
+  constexpr int HD_PAD = HD <= 16 ? 16 : (HD <= 32 ? 32 : 64);
   constexpr int RB = HD_PAD * 2;
   constexpr int KS = HD_PAD / 16;
   constexpr int NO = HD_PAD / 8;
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   constexpr int RB = K::RB, HD = K::HD, MT = K::MT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full, mma_done, x_ready;
+  __shared__ __align__(8) uint64_t rk_full[K::RSTAGES], rk_empty[K::RSTAGES];   // RING: k-block ring of the group weights
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     mbar_init(&w_full, 1);
     mbar_init(&mma_done, 1);
     mbar_init(&x_ready, NTHREADS);
+    for (int i = 0; i < K::RSTAGES; ++i) { mbar_init(&rk_full[i], 1); mbar_init(&rk_empty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -392,15 +402,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   // normalises the chunks it gathered itself; the 4 threads of a token combine their partial sums by shuffle.
   // fp32 statistics with a shifted one-pass variance; then arrive on x_ready for the MMA issuer.
   auto normalize = [&]() {
-    uint4 v[K::CPR / 4];
-#pragma unroll
-    for (int j = 0; j < K::CPR / 4; ++j) v[j] = lds128(x_chunk(j));
-    float k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(v[0].x & 0xffffu)));
-    k0 = __shfl_sync(0xffffffffu, k0, lane & ~3);   // first element of the row (held by part 0)
+    constexpr int NJ = K::CPR / 4;
+    constexpr bool KEEP = NJ <= 6;     // narrow rows stay in registers between the two passes; wide ones are re-read from smem
+    uint4 v[KEEP ? NJ : 1];
+    float k0 = 0.f;
+    {
+      const uint4 f0 = lds128(x_chunk(0));
+      k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(f0.x & 0xffffu)));
+      k0 = __shfl_sync(0xffffffffu, k0, lane & ~3);   // first element of the row (held by part 0)
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < K::CPR / 4; ++j) {
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v[j]);
+    for (int j = 0; j < NJ; ++j) {
+      const uint4 u = lds128(x_chunk(j));
+      if constexpr (KEEP) v[j] = u;
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __half22float2(h2[t]);
@@ -418,8 +434,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     const float a = rsqrtf(var + 1e-5f);
     const float b = -(k0 + ms) * a;
 #pragma unroll
-    for (int j = 0; j < K::CPR / 4; ++j) {
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v[j]);
+    for (int j = 0; j < NJ; ++j) {
+      uint4 u;
+      if constexpr (KEEP) u = v[j]; else u = lds128(x_chunk(j));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
       uint4 o;
       __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
@@ -460,29 +478,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     tc_commit(&mma_done);
   };
 
+  // RING mode (wide rows): the weights of a head group do not fit next to the token tile, so they stream through a ring of
+  // 64-wide k-blocks.  One thread of a warp that sits the core out is both TMA producer and MMA issuer; the ring runs ahead
+  // across items (the weight sequence does not depend on the tile), refilling a slot one k-block after its MMAs were issued.
+  uint32_t rk_loaded = 0;      // k-blocks whose TMA has been issued (sequence number over items)
+  const uint32_t rk_total = K::RING ? static_cast<uint32_t>(((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * K::NG * K::KB) : 0u;
+  auto ring_load = [&]() {     // issue the TMA of k-block rk_loaded (its slot must be free)
+    const uint32_t c = rk_loaded, slot = c % K::RSTAGES;
+    if (c >= K::RSTAGES) mbar_wait(&rk_empty[slot], ((c / K::RSTAGES) - 1) & 1);
+    const int g = static_cast<int>((c / K::KB) % K::NG), kb = static_cast<int>(c % K::KB);
+    mbar_arrive_expect_tx(&rk_full[slot], K::WKB_BYTES);
+    tma_load_2d(smem + K::OFF_W + slot * K::WKB_BYTES, &tmW, &rk_full[slot], kb * 64, g * K::NGC);
+    ++rk_loaded;
+  };
+  auto ring_mma = [&](uint32_t it) {   // D[128 x NGC] = X * Wg^T for work item `it`, k-block by k-block
+    const uint32_t idesc = umma_idesc_f16(128, K::NPM);
+#pragma unroll 1
+    for (int kb = 0; kb < K::KB; ++kb) {
+      const uint32_t c = it * K::KB + kb, slot = c % K::RSTAGES;
+      while (rk_loaded <= c) ring_load();
+      mbar_wait(&rk_full[slot], (c / K::RSTAGES) & 1);
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
+      const uint64_t bdesc = umma_desc_sw128(sW + slot * K::WKB_BYTES);
+      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
+      for (int k = 0; k < ksteps; ++k)
+        umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&rk_empty[slot]);
+      // refill the slot used one k-block ago (its MMAs have had a k-block's time to finish)
+      if (c >= 1 && rk_loaded < rk_total && rk_loaded < c + K::RSTAGES) ring_load();
+    }
+    tc_commit(&mma_done);
+    while (rk_loaded < rk_total && rk_loaded < it * K::KB + K::KB + K::RSTAGES) ring_load();   // prefetch the next item's first k-blocks
+  };
+  // the thread that issues TMA + MMA: lane 0 of warp 0, or in RING mode of a warp without a query tile in the core
+  constexpr int ISSUER_WARP = K::RING ? K::WPU * K::GH : 0;
+  static_assert(!K::RING || (K::NU * K::WPU < 16 && ISSUER_WARP < 8), "RING mode needs an idle warp for the issuer");
+  const bool is_issuer = tid == ISSUER_WARP * 32;
+
   // this warp's (window, head) unit of the core pass
   const int u_hl = (warp & 7) % GH;
   const int unit = wi * GH + u_hl;
   const int mbase = ((warp & 7) / GH) * MT;
+  const bool core_warp = mbase < 4;   // with fewer than 4 units per pass some warps have no query tile
   const int lg = lane >> 2, ltq = lane & 3;
   float tb[2][2 * MT + 7];
   int tb_head = -1;
   // drain constants: token row `row` of the tile, column quarter `quarter`
   const uint32_t d_base = sQKV + ((row >> 6) * GH) * K::UNIT_BYTES + (row & 63) * RB;
-  const uint32_t d_sx = (RB == 32 ? ((row >> 2) & 1) : ((row >> 1) & 3)) << 4;
+  const uint32_t d_sx = (RB == 32 ? ((row >> 2) & 1) : (RB == 64 ? ((row >> 1) & 3) : (row & 7))) << 4;
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
 
   uint32_t item = 0;
   AF_T_DECL;
   Geo geo = tile_geo(blockIdx.x);
   if (static_cast<long long>(blockIdx.x) < tiles) {
-    if (tid == 0) load_w(0);
+    if (!K::RING && tid == 0) load_w(0);
     gather(geo);
     cp_async_wait_all();
     normalize();
-    if (tid == 0) {
+    if (is_issuer) {
       mbar_wait(&x_ready, 0);
-      issue_mma(0);
+      if (K::RING) ring_mma(0); else issue_mma(0);
     }
     __syncwarp();
   }
@@ -501,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       tc_fence_after();
       AF_T(0);
       // the MMAs of this item have read the weight buffer (and, for the last group, the token tile): refill them
-      if (tid == 0 && has_next) load_w(last_g ? 0 : g + 1);
+      if (!K::RING && tid == 0 && has_next) load_w(last_g ? 0 : g + 1);
       if (last_g && has_next_tile) {
         geo_next = tile_geo(next_tile);
         gather(geo_next);
@@ -524,9 +581,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       AF_T(3);
       if (last_g && has_next_tile) normalize();        // next tile's LayerNorm, in place in the token tile
       AF_T(8);
-      if (tid == 0 && has_next) {                      // runs on the tensor pipe while the core below runs on the CUDA cores
+      if (is_issuer && has_next) {                     // runs on the tensor pipe while the core below runs on the CUDA cores
         if (last_g) { mbar_wait(&x_ready, xph & 1); }
-        issue_mma(item + 1);
+        if (K::RING) ring_mma(item + 1); else issue_mma(item + 1);
       }
       if (last_g && has_next_tile) ++xph;
       __syncwarp();
@@ -534,7 +591,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       // ---- core
       {
         const int head = g * GH + u_hl;
-        if (head != tb_head) {
+        if (head != tb_head && core_warp) {
           const float* tbl = sTbl + head * TBL;
 #pragma unroll
           for (int e = 0; e < 2; ++e)
@@ -542,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
             for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (lg - 2 * ltq - e + 7)];
           tb_head = head;
         }
-        if (geo.row >= 0) {   // uniform per warp: all its tokens belong to one window
+        if (geo.row >= 0 && core_warp) {   // uniform per warp: all its tokens belong to one window
           const uint32_t q_h = sQKV + (0 * K::NU + unit) * K::UNIT_BYTES;
           const uint32_t k_h = sQKV + (1 * K::NU + unit) * K::UNIT_BYTES;
           const uint32_t v_h = sQKV + (2 * K::NU + unit) * K::UNIT_BYTES;
@@ -663,11 +720,11 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   return 0;
 }
 
-constexpr int group_heads(int C) { return C == 96 ? 8 : 2; }
+constexpr int group_heads(int C) { return C == 96 ? 8 : (C == 192 ? 2 : 1); }
 
 }  // namespace
 
-bool attn_fused_supported(int C, int heads) { return heads == 8 && (C == 96 || C == 192); }
+bool attn_fused_supported(int C, int heads) { return heads == 8 && (C == 96 || C == 192 || C == 384); }
 
 int attn_fused_prepack(AttnFusedPack* p, int C, int heads, float qscale, const float* gamma, const float* beta, const float* wqkv,
                        const float* bqkv, const float* table, cudaStream_t stream) {
@@ -691,6 +748,7 @@ int attn_fused_launch(const AttnFusedPack& p, const __half* x, __half* out, int 
   switch (p.C) {
     case 96: return launch_t<96, group_heads(96)>(p, x, out, B, H, W, shift, stream);
     case 192: return launch_t<192, group_heads(192)>(p, x, out, B, H, W, shift, stream);
+    case 384: return launch_t<384, group_heads(384)>(p, x, out, B, H, W, shift, stream);
     default: return fail(SUNET_E_SHAPE, "fused attention: C=%d not instantiated", p.C);
   }
 }
