@@ -109,7 +109,7 @@ struct FCfg {
   static constexpr int X_BYTES = KB * 16384;
   // weights of a head group: one buffer loaded at once, or (RING: when that does not fit) a ring of 64-wide k-blocks
   static constexpr bool RING = KB * NGC * 128 > 80 * 1024;
-  static constexpr int RSTAGES = 3;
+  static constexpr int RSTAGES = 4;
   static constexpr int WKB_BYTES = NGC * 128;    // one k-block of a group's weights
   static constexpr int W_BYTES = RING ? RSTAGES * WKB_BYTES : KB * NGC * 128;
   static constexpr int QKV_BYTES = 3 * NU * UNIT_BYTES;
@@ -117,7 +117,8 @@ struct FCfg {
   static constexpr int OFF_W = OFF_X + X_BYTES;
   static constexpr int OFF_QKV = OFF_W + W_BYTES;
   static constexpr int OFF_TBL = OFF_QKV + QKV_BYTES;
-  static constexpr int OFF_HC = OFF_TBL + HEADS * TBL * 4;
+  static constexpr bool TBL_SMEM = !RING;        // RING configs need the space for a 4th ring stage: the bias slice comes from global
+  static constexpr int OFF_HC = OFF_TBL + (TBL_SMEM ? HEADS * TBL * 4 : 0);
   static constexpr int SMEM = OFF_HC + 3 * C * 4 + 1024;
   static constexpr uint32_t TMEM_COLS = NGC <= 256 ? 256 : 512;
   static_assert(C % 32 == 0 && HD % 4 == 0 && QC % 4 == 0, "column slices must be whole 4-column groups");
@@ -336,9 +337,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     tmem_alloc(&tmem_base_smem, K::TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = tid; i < K::HEADS * 225; i += NTHREADS) {
-    const int e = i / K::HEADS, h = i - e * K::HEADS;
-    sTbl[h * TBL + e] = __ldg(p.table + i) * LOG2E;
+  if constexpr (K::TBL_SMEM) {
+    for (int i = tid; i < K::HEADS * 225; i += NTHREADS) {
+      const int e = i / K::HEADS, h = i - e * K::HEADS;
+      sTbl[h * TBL + e] = __ldg(p.table + i) * LOG2E;
+    }
   }
   for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
   if constexpr (K::HD_PAD != HD) {
@@ -483,9 +486,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   // across items (the weight sequence does not depend on the tile), refilling a slot one k-block after its MMAs were issued.
   uint32_t rk_loaded = 0;      // k-blocks whose TMA has been issued (sequence number over items)
   const uint32_t rk_total = K::RING ? static_cast<uint32_t>(((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * K::NG * K::KB) : 0u;
-  auto ring_load = [&]() {     // issue the TMA of k-block rk_loaded (its slot must be free)
+  auto ring_load = [&](uint32_t empty_ok) {   // issue the TMA of k-block rk_loaded (its slot must be free; empty_ok: an earlier test said so)
     const uint32_t c = rk_loaded, slot = c % K::RSTAGES;
-    if (c >= K::RSTAGES) mbar_wait(&rk_empty[slot], ((c / K::RSTAGES) - 1) & 1);
+    if (c >= K::RSTAGES) mbar_wait_hint(&rk_empty[slot], ((c / K::RSTAGES) - 1) & 1, empty_ok);
     const int g = static_cast<int>((c / K::KB) % K::NG), kb = static_cast<int>(c % K::KB);
     mbar_arrive_expect_tx(&rk_full[slot], K::WKB_BYTES);
     tma_load_2d(smem + K::OFF_W + slot * K::WKB_BYTES, &tmW, &rk_full[slot], kb * 64, g * K::NGC);
@@ -493,11 +496,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   };
   auto ring_mma = [&](uint32_t it) {   // D[128 x NGC] = X * Wg^T for work item `it`, k-block by k-block
     const uint32_t idesc = umma_idesc_f16(128, K::NPM);
+    const uint32_t c0 = it * K::KB;
+    while (rk_loaded <= c0) ring_load(0u);
+    uint32_t full_ok = mbar_test(&rk_full[c0 % K::RSTAGES], (c0 / K::RSTAGES) & 1);
 #pragma unroll 1
     for (int kb = 0; kb < K::KB; ++kb) {
-      const uint32_t c = it * K::KB + kb, slot = c % K::RSTAGES;
-      while (rk_loaded <= c) ring_load();
-      mbar_wait(&rk_full[slot], (c / K::RSTAGES) & 1);
+      const uint32_t c = c0 + kb, slot = c % K::RSTAGES;
+      while (rk_loaded <= c) ring_load(0u);
+      mbar_wait_hint(&rk_full[slot], (c / K::RSTAGES) & 1, full_ok);
+      // barrier states needed next are looked up now, under the MMA issue (a test costs ~170 clk even on a completed phase):
+      // the next k-block's full flag, and the empty flag of the slot the refill below will reuse
+      const uint32_t cn = c + 1;
+      full_ok = (kb + 1 < K::KB && rk_loaded > cn) ? mbar_test(&rk_full[cn % K::RSTAGES], (cn / K::RSTAGES) & 1) : 0u;
+      const bool refill = c >= 1 && rk_loaded < rk_total && rk_loaded < c + K::RSTAGES;
+      const uint32_t empty_ok = (refill && rk_loaded >= K::RSTAGES) ? mbar_test(&rk_empty[rk_loaded % K::RSTAGES], ((rk_loaded / K::RSTAGES) - 1) & 1) : 0u;
       tc_fence_after();
       const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
       const uint64_t bdesc = umma_desc_sw128(sW + slot * K::WKB_BYTES);
@@ -506,10 +518,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
         umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
       tc_commit(&rk_empty[slot]);
       // refill the slot used one k-block ago (its MMAs have had a k-block's time to finish)
-      if (c >= 1 && rk_loaded < rk_total && rk_loaded < c + K::RSTAGES) ring_load();
+      if (refill) ring_load(empty_ok);
     }
     tc_commit(&mma_done);
-    while (rk_loaded < rk_total && rk_loaded < it * K::KB + K::KB + K::RSTAGES) ring_load();   // prefetch the next item's first k-blocks
+    while (rk_loaded < rk_total && rk_loaded < c0 + K::KB + K::RSTAGES - 1) ring_load(0u);   // prefetch the next item's first k-blocks
   };
   // the thread that issues TMA + MMA: lane 0 of warp 0, or in RING mode of a warp without a query tile in the core
   constexpr int ISSUER_WARP = K::RING ? K::WPU * K::GH : 0;
@@ -592,11 +604,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       {
         const int head = g * GH + u_hl;
         if (head != tb_head && core_warp) {
-          const float* tbl = sTbl + head * TBL;
 #pragma unroll
           for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = tbl[(k + 2 * mbase) * 15 + (lg - 2 * ltq - e + 7)];
+            for (int k = 0; k < 2 * MT + 7; ++k) {
+              const int idx = (k + 2 * mbase) * 15 + (lg - 2 * ltq - e + 7);
+              tb[e][k] = K::TBL_SMEM ? sTbl[head * TBL + idx] : __ldg(p.table + idx * K::HEADS + head) * LOG2E;
+            }
           tb_head = head;
         }
         if (geo.row >= 0 && core_warp) {   // uniform per warp: all its tokens belong to one window

@@ -14,7 +14,7 @@ from sunet_tf_b200 import SwinTransformerBlock  # noqa: E402
 dev = torch.device("cuda:0")
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 shift = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-for dim, grid in ((96, 64), (192, 32)):
+for dim, grid in ((96, 64), (192, 32), (384, 16)):
     sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, shift), seed=dim, style="init")
     blk = SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8)
     blk.load_state_dict(sd, strict=True)
