@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   using K = FCfg<C, GH>;
   constexpr int RB = K::RB, HD = K::HD, MT = K::MT;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t w_full, mma_done, x_ready;
+  __shared__ __align__(8) uint64_t w_full, mma_done;
   __shared__ __align__(8) uint64_t rk_full[K::RSTAGES], rk_empty[K::RSTAGES];   // RING: k-block ring of the group weights
   __shared__ uint32_t tmem_base_smem;
 
@@ -329,7 +329,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     tma_prefetch_desc(&tmW);
     mbar_init(&w_full, 1);
     mbar_init(&mma_done, 1);
-    mbar_init(&x_ready, NTHREADS);
     for (int i = 0; i < K::RSTAGES; ++i) { mbar_init(&rk_full[i], 1); mbar_init(&rk_empty[i], 1); }
     fence_mbar_init();
   }
@@ -403,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   };
   // LayerNorm of token tk in place (norm1 without its affine part, which is folded into the weights): every thread
   // normalises the chunks it gathered itself; the 4 threads of a token combine their partial sums by shuffle.
-  // fp32 statistics with a shifted one-pass variance; then arrive on x_ready for the MMA issuer.
+  // fp32 statistics with a shifted one-pass variance.
   auto normalize = [&]() {
     constexpr int NJ = K::CPR / 4;
     constexpr bool KEEP = NJ <= 6;     // narrow rows stay in registers between the two passes; wide ones are re-read from smem
@@ -450,8 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       }
       sts128(x_chunk(j), o);
     }
-    fence_proxy_async_smem();
-    mbar_arrive(&x_ready);
+    fence_proxy_async_smem();   // the MMA issuer reads the tile through the async proxy after the next block barrier
   };
   auto load_w = [&](int g) {   // thread 0: the folded qkv weights of head group g -> smem, [kb][sub-tile][NPM rows][64] SW128
     mbar_arrive_expect_tx(&w_full, K::W_BYTES);
@@ -549,13 +547,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     gather(geo);
     cp_async_wait_all();
     normalize();
+    tc_fence_before();
+    __syncthreads();
     if (is_issuer) {
-      mbar_wait(&x_ready, 0);
+      tc_fence_after();
       if (K::RING) ring_mma(0); else issue_mma(0);
     }
     __syncwarp();
   }
-  uint32_t xph = 1;   // parity of the next x_ready phase
   uint32_t md_ok = 0;  // early-test result for the current item's mma_done phase
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long next_tile = tile + gridDim.x;
@@ -586,18 +585,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
         }
       }
       AF_T(1);
-      if (last_g && has_next_tile) cp_async_wait_all();
+      if (last_g && has_next_tile) {   // next tile's LayerNorm, in place in the token tile; barrier (B) below publishes it to the issuer
+        cp_async_wait_all();
+        normalize();
+      }
       AF_T(2);
       tc_fence_before();
       __syncthreads();   // (B) q/k/v operand tiles complete, accumulator drained
       AF_T(3);
-      if (last_g && has_next_tile) normalize();        // next tile's LayerNorm, in place in the token tile
       AF_T(8);
       if (is_issuer && has_next) {                     // runs on the tensor pipe while the core below runs on the CUDA cores
-        if (last_g) { mbar_wait(&x_ready, xph & 1); }
         if (K::RING) ring_mma(item + 1); else issue_mma(item + 1);
       }
-      if (last_g && has_next_tile) ++xph;
       __syncwarp();
       AF_T(9);
       // ---- core
