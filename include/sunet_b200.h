@@ -75,7 +75,7 @@ int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int
 /* Same forward with every kernel launch bracketed by CUDA events on `stream` (synchronises before returning).
  * recs[i] = {kind, device ms, algorithmic FLOPs, algorithmic bytes} in launch order; kind: 0 tcgen05 GEMM, 1 attention core,
  * 2 LayerNorm, 3 merge-gather+LN, 4 patch-embed conv, 5 up-sample combine, 6 tail stencil, 7 cast, 8 im2col, 9 fused LN+MLP+residual,
- * 10 fused LN+shift/partition+QKV+window attention. */
+ * 10 fused LN+shift/partition+QKV+window attention, 11 fused x4 pixel-shuffle branch + folded output taps. */
 typedef struct sunet_prof_rec { int kind; float ms; double flops; double bytes; } sunet_prof_rec;
 int sunet_forward_profile(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
                           size_t workspace_bytes, void* stream, sunet_prof_rec* recs, int max_recs, int* n_recs);

@@ -20,7 +20,7 @@ class ProfRec(ctypes.Structure):
 
 
 KERNEL_KINDS = ("gemm_tcgen05", "attn_core", "layernorm", "merge_gather_ln", "patch_embed_conv", "upsample_combine", "tail_stencil",
-                "cast", "im2col", "mlp_fused", "attn_fused")
+                "cast", "im2col", "mlp_fused", "attn_fused", "tail_up_fused")
 
 _SIGNATURES = {
     "sunet_abi_version": (ctypes.c_int, []),

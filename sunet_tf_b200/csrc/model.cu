@@ -17,6 +17,7 @@
 #include "error.h"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
+#include "tail_fused.cuh"
 
 namespace sunet {
 
@@ -68,7 +69,7 @@ struct ScratchMark {  // stack discipline
   ~ScratchMark() { s.off = saved; }
 };
 
-enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8, K_MLP_FUSED = 9, K_ATTN_FUSED = 10 };
+enum KernelKind { K_GEMM = 0, K_ATTN = 1, K_LAYERNORM = 2, K_MERGE_LN = 3, K_PATCH_EMBED = 4, K_UP_COMBINE = 5, K_TAIL = 6, K_CAST = 7, K_IM2COL = 8, K_MLP_FUSED = 9, K_ATTN_FUSED = 10, K_TAIL_FUSED = 11 };
 
 struct ProfRec {
   int kind;
@@ -402,12 +403,18 @@ struct TailPack {
     const int64_t M = static_cast<int64_t>(B) * H * W;
     __half *Pb, *Bb;
     float *Qp, *Rb;
-    SUNET_TRY(c.sc.take_t(&Pb, M * 16 * E));
+    const bool fused = tail_up_fused_supported(E, NT) && getenv("SUNET_NO_FUSED_TAIL") == nullptr;
+    SUNET_TRY(c.sc.take_t(&Pb, fused ? 0 : M * 16 * E));
     SUNET_TRY(c.sc.take_t(&Qp, M * 16 * NT));
     SUNET_TRY(c.sc.take_t(&Bb, M * E));
     SUNET_TRY(c.sc.take_t(&Rb, M * NT));
-    SUNET_TRY(run_linear(c, up.p0, x, E, M, Pb, 16 * E, ACT_PRELU, up.slope_p));
-    SUNET_TRY(run_linear(c, gp, Pb, E, M * 16, Qp, NT, ACT_NONE, nullptr, nullptr, 0, 1));
+    if (fused) {   // up_p[0..1] and the folded taps in one kernel: the [M][16 * 96] activation stays on the SM
+      RUN(c, K_TAIL_FUSED, 2.0 * M * 16 * E * E + 2.0 * M * 16 * NT * E, 2.0 * M * E + 4.0 * M * 16 * NT,
+          tail_up_fused_launch(x, up.p0.w, gp.w, up.slope_p, Qp, M, c.stream));
+    } else {
+      SUNET_TRY(run_linear(c, up.p0, x, E, M, Pb, 16 * E, ACT_PRELU, up.slope_p));
+      SUNET_TRY(run_linear(c, gp, Pb, E, M * 16, Qp, NT, ACT_NONE, nullptr, nullptr, 0, 1));
+    }
     SUNET_TRY(run_linear(c, up.b0, x, E, M, Bb, E, ACT_PRELU, up.slope_b));
     SUNET_TRY(run_linear(c, gb, Bb, E, M, Rb, NT, ACT_NONE, nullptr, nullptr, 0, 1));
     RUN(c, K_TAIL, 0.0, 4.0 * M * NT * 17 + 4.0 * M * 16 * OC, tail_stencil(Qp, Rb, out, B, H, W, OC, NT, c.stream));
