@@ -629,8 +629,6 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
       const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
       const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
-      const int64_t m = tile * TILE_M + row;
-      const bool valid = m < p.M;
       // ---- EPI0: x1 = P + bp + shortcut
       MLP_T_START;
       if (!PREFETCH) fetch_shortcut(tile);
@@ -758,21 +756,34 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&y_empty[yb]);
-        if (valid) {
-          __half* orow = p.out + m * C + quarter * K::QC;
+        // Stage the 32 x C fp16 block of this row quadrant through the (now idle) GELU buffers so that global stores cover whole
+        // rows: a thread-per-row store touches 32 different 128-byte lines per instruction and is LSU-bound (measured).
+        constexpr int PITCH = C * 2 + 16;   // bytes; the 16-byte pad makes 8 consecutive rows hit 8 distinct bank groups
+        const uint32_t stg = smem_u32(smem + K::OFF_HS) + static_cast<uint32_t>(q) * (32 * PITCH);
 #pragma unroll
-          for (int i = 0; i < K::QCH; ++i) {
-            const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
-            const float* bb = b2s + quarter * K::QC + i * 8;
-            uint4 o;
-            __half2* o2 = reinterpret_cast<__half2*>(&o);
+        for (int i = 0; i < K::QCH; ++i) {
+          const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
+          const float* bb = b2s + quarter * K::QC + i * 8;
+          uint4 o;
+          __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 r = __half22float2(r2[t]);
-              o2[t] = __floats2half2_rn(__uint_as_float(y[i * 8 + 2 * t]) + bb[2 * t] + r.x,
-                                        __uint_as_float(y[i * 8 + 2 * t + 1]) + bb[2 * t + 1] + r.y);
-            }
-            *reinterpret_cast<uint4*>(orow + i * 8) = o;
+          for (int t = 0; t < 4; ++t) {
+            const float2 r = __half22float2(r2[t]);
+            o2[t] = __floats2half2_rn(__uint_as_float(y[i * 8 + 2 * t]) + bb[2 * t] + r.x,
+                                      __uint_as_float(y[i * 8 + 2 * t + 1]) + bb[2 * t + 1] + r.y);
+          }
+          sts128(stg + lane * PITCH + (quarter * K::QCH + i) * 16, o);
+        }
+        named_bar_sync(2 + q, 128);   // the 4 column-quarter warps of this row quadrant
+        {
+          constexpr int CPR = C / 8;   // 16-byte chunks per row
+          const int64_t m0 = tile * TILE_M + q * 32 + quarter * 8;   // this warp writes 8 of the quadrant's 32 rows
+#pragma unroll
+          for (int kk = 0; kk < (8 * CPR + 31) / 32; ++kk) {
+            const int idx = kk * 32 + lane;
+            const int r = idx / CPR, ch = idx - r * CPR;
+            if (idx < 8 * CPR && m0 + r < p.M)
+              *reinterpret_cast<uint4*>(p.out + (m0 + r) * C + ch * 8) = lds128(stg + (quarter * 8 + r) * PITCH + ch * 16);
           }
         }
         MLP_T(7);

@@ -12,6 +12,9 @@
 // and after the 16 sub-pixels the 128 x 256 fp32 tile goes out with 16-byte stores (1 KB contiguous per token).
 #include "tail_fused.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "error.h"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -39,7 +42,17 @@ constexpr uint32_t TM_Y = 0;            // Q tile: 256 columns
 constexpr uint32_t TM_H = 256;          // H[b] at 256 + 128 b
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 
+#ifndef SUNET_KERNEL_TIMING
+#define SUNET_KERNEL_TIMING 0
+#endif
+#if SUNET_KERNEL_TIMING
+#define TF_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; } } while (0)
+#else
+#define TF_T(i) do { } while (0)
+#endif
+
 struct Params {
+  long long* timing;    // SUNET_KERNEL_TIMING builds: [grid][16 warps][8] phase cycles
   const float* slope;   // PReLU slope (device scalar)
   float* out;           // [M * 16][16] fp32 == [M][256]
   int64_t M;
@@ -184,16 +197,23 @@ __global__ void __launch_bounds__(THREADS, 1)
     uint32_t g = 0;
     int lt = 0;
     uint32_t h_ok = 0;
+#if SUNET_KERNEL_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tq0 = clock64();
+#endif
     for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
       for (int j = 0; j < SUB; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
+        TF_T(7);
         mbar_wait_hint(&h_full[hb], ph, h_ok);
         tc_fence_after();
+        TF_T(0);
         uint32_t v[24];
 #pragma unroll
         for (int i = 0; i < 3; ++i) tmem_ld8(tmem_base + lane_off + TM_H + hb * 128 + quarter * 24 + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[i * 8]));
         const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);
         tmem_ld_wait();
+        TF_T(1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_empty[hb]);   // the accumulator may be overwritten by the fc1 of sub-pixel g + 2
@@ -207,7 +227,9 @@ __global__ void __launch_bounds__(THREADS, 1)
             o2[t] = __floats2half2_rn(a >= 0.f ? a : slope * a, b >= 0.f ? b : slope * b);   // PReLU, one shared slope (:356)
           }
         }
+        TF_T(2);
         mbar_wait_hint(&hs_empty[hb], ph ^ 1, hs_ok);
+        TF_T(3);
         h_ok = mbar_test(&h_full[hb ^ 1], ((g + 1) >> 1) & 1);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -218,10 +240,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&g_done[hb]);
+        TF_T(4);
       }
       // ---- output: Q tile columns [64 quarter, +64) of this row = sub-pixels 4 quarter .. 4 quarter + 3, 16 taps each
       mbar_wait(&y_full, lt & 1);
       tc_fence_after();
+      TF_T(5);
       const int64_t m = tile * TILE_M + row;
       float* orow = p.out + m * (SUB * NT) + quarter * 64;
 #pragma unroll
@@ -238,7 +262,12 @@ __global__ void __launch_bounds__(THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&y_empty);
+      TF_T(6);
     }
+#if SUNET_KERNEL_TIMING
+    if (p.timing && lane == 0)
+      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -269,12 +298,36 @@ int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p,
   SUNET_TRY(make_tmap_2d_f16(&tmW1, w_p0, E, SUB * E, E, E));
   SUNET_TRY(make_tmap_2d_f16(&tmGp, g_p, E, NT, E, NT));
   Params prm;
+  prm.timing = nullptr;
+#if SUNET_KERNEL_TIMING
+  static long long* tbuf = nullptr;
+  if (getenv("SUNET_TAIL_TIMING")) {
+    if (!tbuf) SUNET_CUDA(cudaMalloc(&tbuf, 148 * EPI_WARPS * 8 * sizeof(long long)));
+    SUNET_CUDA(cudaMemsetAsync(tbuf, 0, 148 * EPI_WARPS * 8 * sizeof(long long), stream));
+    prm.timing = tbuf;
+  }
+#endif
   prm.slope = slope;
   prm.out = out;
   prm.M = M;
   prm.tiles = (M + TILE_M - 1) / TILE_M;
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   SUNET_CUDA(launch_pdl(tail_up_fused_kernel, dim3(grid), dim3(THREADS), SMEM, stream, tmX, tmW1, tmGp, prm));
+#if SUNET_KERNEL_TIMING
+  if (prm.timing) {
+    SUNET_CUDA(cudaStreamSynchronize(stream));
+    static long long host[148 * EPI_WARPS * 8];
+    SUNET_CUDA(cudaMemcpy(host, prm.timing, sizeof(host), cudaMemcpyDeviceToHost));
+    static const char* names[8] = {"wait_h", "tmem_ld", "prelu", "wait_hs", "store", "wait_y", "out", "loop"};
+    double acc[8] = {0};
+    for (unsigned b = 0; b < grid; ++b)
+      for (int w = 0; w < EPI_WARPS; ++w)
+        for (int i = 0; i < 8; ++i) acc[i] += static_cast<double>(host[(b * EPI_WARPS + w) * 8 + i]);
+    fprintf(stderr, "tail_up_fused grid=%u cycles per epilogue warp:", grid);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %.0f", names[i], acc[i] / grid / EPI_WARPS);
+    fprintf(stderr, "\n");
+  }
+#endif
   return 0;
 }
 
