@@ -246,22 +246,32 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_wait(&y_full, lt & 1);
       tc_fence_after();
       TF_T(5);
-      const int64_t m = tile * TILE_M + row;
-      float* orow = p.out + m * (SUB * NT) + quarter * 64;
+      // staged through this warp's 4 KB slice of the (idle) G buffers, 32 columns per pass: the warp then writes 4 whole 128-byte
+      // row segments per instruction instead of 32 different lines (a thread-per-row store is LSU-bound, measured)
+      const uint32_t stg = smem_u32(smem + OFF_HS) + static_cast<uint32_t>(e) * 4096;
+      const int64_t m_warp = tile * TILE_M + q * 32;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t y[32];
         tmem_ld32(tmem_base + lane_off + TM_Y + quarter * 64 + c, y);
         tmem_ld_wait();
-        if (m < p.M) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(orow + c + i * 4) = make_uint4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)
+          sts128(stg + lane * 128 + ((static_cast<uint32_t>(i) ^ static_cast<uint32_t>(lane & 7)) << 4), make_uint4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int r = kk * 4 + (lane >> 3), ch = lane & 7;
+          if (m_warp + r < p.M)
+            *reinterpret_cast<uint4*>(p.out + (m_warp + r) * (SUB * NT) + quarter * 64 + c + ch * 4) =
+                lds128(stg + r * 128 + ((static_cast<uint32_t>(ch) ^ static_cast<uint32_t>(r & 7)) << 4));
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&y_empty);
+      named_bar_sync(1, EPI_WARPS * 32);   // every warp is done with its staging slice before the next tile's G stores reuse the buffers
       TF_T(6);
     }
 #if SUNET_KERNEL_TIMING
