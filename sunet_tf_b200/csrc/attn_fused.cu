@@ -272,28 +272,52 @@ __device__ __forceinline__ void attn_tiles(uint32_t q_h, uint32_t k_h, uint32_t 
 // Drain of one column quarter Q of the accumulator for one token row: qkv = D + bias -> fp16, written as 8-byte groups
 // into the (q|k|v, window, head) operand tiles.  Everything that depends on the column is a compile-time constant; TMEM
 // loads are issued in batches of 24 / 36 columns per wait.
+template <typename K, int Q, int BATCH>
+__device__ __forceinline__ void drain_load(uint32_t t_lane, int c0, uint32_t (&v)[BATCH]) {
+#pragma unroll
+  for (int i = 0; i + 8 <= BATCH; i += 8) tmem_ld8(t_lane + Q * K::QC + c0 + i, *reinterpret_cast<uint32_t(*)[8]>(&v[i]));
+  if constexpr (BATCH % 8 != 0) tmem_ld4(t_lane + Q * K::QC + c0 + (BATCH / 8) * 8, *reinterpret_cast<uint32_t(*)[4]>(&v[(BATCH / 8) * 8]));
+}
+template <typename K, int Q, int BATCH>
+__device__ __forceinline__ void drain_store(const uint32_t (&v)[BATCH], int c0, const float* bf, uint32_t d_base, uint32_t d_sx) {
+#pragma unroll
+  for (int i = 0; i < BATCH; i += 4) {
+    const int n = Q * K::QC + c0 + i;             // compile-time after unrolling
+    const int m = n / K::BR, j = n % K::BR;
+    const int hl = j / K::HD, d = j % K::HD;
+    const float4 b4 = *reinterpret_cast<const float4*>(bf + n);
+    const uint32_t dst = d_base + (m * K::NU + hl) * K::UNIT_BYTES + (d & 7) * 2 + ((static_cast<uint32_t>(d >> 3) << 4) ^ d_sx);
+    sts64(dst, pack_half2(__uint_as_float(v[i + 0]) + b4.x, __uint_as_float(v[i + 1]) + b4.y),
+          pack_half2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w));
+  }
+}
 template <typename K, int Q>
 __device__ __forceinline__ void drain_quarter(uint32_t t_lane, const float* bf, uint32_t d_base, uint32_t d_sx) {
   constexpr int QC = K::QC;
-  constexpr int BATCH = QC > 40 ? QC / 2 : QC;     // columns in flight per tcgen05.wait::ld (register budget)
-  static_assert(BATCH % 4 == 0 && QC % BATCH == 0 && BATCH <= 40, "drain batch");
-#pragma unroll
-  for (int c0 = 0; c0 < QC; c0 += BATCH) {
-    uint32_t v[BATCH];
-#pragma unroll
-    for (int i = 0; i + 8 <= BATCH; i += 8) tmem_ld8(t_lane + Q * QC + c0 + i, *reinterpret_cast<uint32_t(*)[8]>(&v[i]));
-    if constexpr (BATCH % 8 != 0) tmem_ld4(t_lane + Q * QC + c0 + (BATCH / 8) * 8, *reinterpret_cast<uint32_t(*)[4]>(&v[(BATCH / 8) * 8]));
+  if constexpr (QC % 24 == 0 && QC > 24) {
+    // three batches of 24 columns, software-pipelined: the TMEM loads of batch b + 1 are in flight while batch b is converted and
+    // stored (tcgen05.wait::ld covers everything issued so far; the drain is latency-, not bandwidth-bound)
+    constexpr int NB = QC / 24;
+    uint32_t va[24], vb[24];
+    drain_load<K, Q, 24>(t_lane, 0, va);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < BATCH; i += 4) {
-      const int n = Q * QC + c0 + i;             // compile-time after unrolling
-      const int m = n / K::BR, j = n % K::BR;
-      const int hl = j / K::HD, d = j % K::HD;
-      const float4 b4 = *reinterpret_cast<const float4*>(bf + n);
-      const uint32_t dst = d_base + (m * K::NU + hl) * K::UNIT_BYTES + (d & 7) * 2 + ((static_cast<uint32_t>(d >> 3) << 4) ^ d_sx);
-      sts64(dst, pack_half2(__uint_as_float(v[i + 0]) + b4.x, __uint_as_float(v[i + 1]) + b4.y),
-            pack_half2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w));
+    for (int bi = 0; bi < NB; ++bi) {
+      if (bi & 1) {
+        if (bi + 1 < NB) drain_load<K, Q, 24>(t_lane, (bi + 1) * 24, va);
+        drain_store<K, Q, 24>(vb, bi * 24, bf, d_base, d_sx);
+      } else {
+        if (bi + 1 < NB) drain_load<K, Q, 24>(t_lane, (bi + 1) * 24, vb);
+        drain_store<K, Q, 24>(va, bi * 24, bf, d_base, d_sx);
+      }
+      if (bi + 1 < NB) tmem_ld_wait();
     }
+  } else {
+    static_assert(QC % 4 == 0 && QC <= 40, "drain batch");
+    uint32_t v[QC];
+    drain_load<K, Q, QC>(t_lane, 0, v);
+    tmem_ld_wait();
+    drain_store<K, Q, QC>(v, 0, bf, d_base, d_sx);
   }
 }
 
