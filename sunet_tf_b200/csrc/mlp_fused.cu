@@ -82,10 +82,12 @@ struct Params {
 #define MLP_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; } } while (0)
 #define MLP_T_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define MLP_T_START long long tq0 = p.timing ? clock64() : 0
+#define MLP_T_RESTART do { if (p.timing) tq0 = clock64(); } while (0)
 #else
 #define MLP_T(i) do { } while (0)
 #define MLP_T_DECL do { } while (0)
 #define MLP_T_START do { } while (0)
+#define MLP_T_RESTART do { } while (0)
 #endif
 
 template <int C>
@@ -487,15 +489,21 @@ __global__ void __launch_bounds__(THREADS, 1)
           tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
         }
       };
-      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-        // same order as the MMA issuer consumes: Wp | fc1(0) fc1(1) | { fc1(j+2), fc2(j) } ...
-        if (K::NXBUF != 2) load_x(tile, lt);
+      constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;
+      if (EARLY && static_cast<int64_t>(blockIdx.x) < p.tiles)
         for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        // same order as the MMA issuer consumes: [Wp] fc1(0) fc1(1) { fc1(j+2), fc2(j) } ... ; EARLY: the next tile's Wp before the last fc2
+        if (K::NXBUF != 2) load_x(tile, lt);
+        if (!EARLY)
+          for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
         if (K::NXBUF == 2 && tile + gridDim.x < p.tiles) load_x(tile + gridDim.x, lt + 1);   // prefetch one tile ahead
         load_w1(0);
         if (K::NCH > 1) load_w1(1);
         for (int j = 0; j < K::NCH; ++j) {
           if (j + 2 < K::NCH) load_w1(j + 2);
+          if (EARLY && j == K::NCH - 1 && tile + gridDim.x < p.tiles)
+            for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
           load_r2(&tmW2, j * NC);
           load_r2(&tmW2, j * NC + 64);
         }
@@ -563,28 +571,33 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_commit(&hs_empty[hb]);
         if (j == K::NCH - 1) tc_commit(&y_full[yb]);
       };
+      auto mma0 = [&](int lt2) {   // P = attn_out * Wp^T into the (idle) fc2 accumulator of local tile lt2
+        const int xb = K::NXBUF == 2 ? (lt2 & 1) : 0;
+        const uint32_t xuse = K::NXBUF == 2 ? (lt2 >> 1) : lt2;
+        const int yb = K::NYBUF == 2 ? (lt2 & 1) : 0;
+        const uint32_t yuse = K::NYBUF == 2 ? (lt2 >> 1) : lt2;
+        mbar_wait(&x_full[xb], xuse & 1);
+        mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+        for (int kb = 0; kb < K::KB1; ++kb) {
+          const int s = r2_acquire();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
+          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r2_empty[s]);
+        }
+        tc_commit(&p_full[yb]);
+      };
+      constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;   // see the epilogue: the next tile's proj is issued before this tile's last fc2
+      if (EARLY && static_cast<int64_t>(blockIdx.x) < p.tiles) mma0(0);
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
         const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
         const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
         const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
-        const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
-        // ---- MMA0: P = attn_out * Wp^T into this tile's (idle) fc2 accumulator
-        mbar_wait(&x_full[xb], xuse & 1);
-        mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
-        tc_fence_after();
-        {
-          const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
-          for (int kb = 0; kb < K::KB1; ++kb) {
-            const int s = r2_acquire();
-            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
-            const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(&r2_empty[s]);
-          }
-          tc_commit(&p_full[yb]);
-        }
+        if (!EARLY) mma0(lt);
         // ---- fc1 runs two hidden chunks ahead of fc2: an fc1 accumulator is free again as soon as the epilogue has LOADED it
         // (h_empty, early in its GELU pass), not only when the GELU output is back in shared memory (gelu_done)
         mbar_wait(&x1_ready[xb], xuse & 1);
@@ -593,6 +606,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (K::NCH > 1) fc1(xb, g + 1, 1, K::NCH == 2);
         for (int j = 0; j < K::NCH; ++j) {
           if (j + 2 < K::NCH) fc1(xb, g + j + 2, j + 2, j + 2 == K::NCH - 1);
+          if (EARLY && j == K::NCH - 1 && tile + gridDim.x < p.tiles) mma0(lt + 1);
           fc2(yb, g + j, j);
         }
         g += K::NCH;
@@ -613,6 +627,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     uint32_t g = 0;
     int lt = 0;
     // the shortcut slice of this thread's row is fetched one tile ahead (global latency ~1-2 us against a ~5 us tile)
+    constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;
     constexpr bool PREFETCH = C <= 96;   // wider rows do not have the registers for it (96-register cap at 576 threads)
     uint4 nxt[K::QCH];
     auto fetch_shortcut = [&](int64_t tile) {
@@ -625,14 +640,18 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (PREFETCH) fetch_shortcut(blockIdx.x);
     uint32_t h_ok = 0;
     MLP_T_DECL;
-    for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+    MLP_T_START;
+    // EARLY (two token-tile buffers and two fc2 accumulators, i.e. C <= 96): x1 of the NEXT tile is built before the output of the
+    // current one, so the last fc2 of this tile, the proj of the next and its first fc1 chunks run on the tensor pipe under epilogue
+    // work instead of being waited for (those three waits were ~20% of the epilogue warps' time).
+    auto epi0 = [&](int64_t tile, int lt, uint4 (&res)[K::QCH]) {
       const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
       const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
       const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
+      (void)xb; (void)yb; (void)yuse;
       // ---- EPI0: x1 = P + bp + shortcut
-      MLP_T_START;
+      MLP_T_RESTART;
       if (!PREFETCH) fetch_shortcut(tile);
-      uint4 res[K::QCH];
 #pragma unroll
       for (int i = 0; i < K::QCH; ++i) res[i] = nxt[i];
       mbar_wait(&p_full[yb], yuse & 1);
@@ -702,6 +721,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (lane == 0) mbar_arrive(&x1_ready[xb]);
       }
       MLP_T(1);
+    };
+    auto gelu_passes = [&](int64_t tile, int lt) {
+      const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+      const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
+      const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
+      (void)xb; (void)yb; (void)yuse;
       // ---- GELU passes
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
@@ -711,7 +736,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);   // looked up under the TMEM load / GELU math
-        if (PREFETCH && j == K::NCH - 2) fetch_shortcut(tile + gridDim.x);   // next tile's shortcut, ~1.5 chunks ahead of its use
+        if (PREFETCH && j == (EARLY ? 0 : K::NCH - 2)) fetch_shortcut(tile + gridDim.x);   // next tile's shortcut, well ahead of its use
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -743,6 +768,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (lane == 0) mbar_arrive(&gelu_done[hb]);
         MLP_T(5);
       }
+    };
+    auto output = [&](int64_t tile, int lt, const uint4 (&res)[K::QCH]) {
+      const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+      const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
+      const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
+      (void)xb; (void)yb; (void)yuse;
       // ---- output: Y + b2 + x1 -> global
       {
         mbar_wait(&y_full[yb], yuse & 1);
@@ -786,7 +817,28 @@ __global__ void __launch_bounds__(THREADS, 1)
               *reinterpret_cast<uint4*>(p.out + (m0 + r) * C + ch * 8) = lds128(stg + (quarter * 8 + r) * PITCH + ch * 16);
           }
         }
+        // EARLY: no other block-wide barrier separates these staging reads from the next tile's GELU stores into the same buffers
+        if constexpr (EARLY) named_bar_sync(1, EPI_THREADS);
         MLP_T(7);
+      }
+        };
+    if constexpr (EARLY) {
+      uint4 res_cur[K::QCH], res_nxt[K::QCH];
+      if (static_cast<int64_t>(blockIdx.x) < p.tiles) epi0(blockIdx.x, 0, res_cur);
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        gelu_passes(tile, lt);
+        const bool more = tile + gridDim.x < p.tiles;
+        if (more) epi0(tile + gridDim.x, lt + 1, res_nxt);
+        output(tile, lt, res_cur);
+#pragma unroll
+        for (int i = 0; i < K::QCH; ++i) res_cur[i] = res_nxt[i];
+      }
+    } else {
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        uint4 res[K::QCH];
+        epi0(tile, lt, res);
+        gelu_passes(tile, lt);
+        output(tile, lt, res);
       }
     }
 #if SUNET_KERNEL_TIMING
