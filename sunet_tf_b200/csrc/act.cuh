@@ -27,11 +27,7 @@ __device__ __forceinline__ float gelu_half_arg(float u) {
   float p = fmaf(t, -1.1248591167e-02f, 2.9604525738e-01f);
   p = fmaf(t, p, 1.5950157421f);
   float th;
-#if defined(SUNET_ABLATE_TANH)
-  th = u * p;   // timing ablation only
-#else
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
-#endif
   return fmaf(u, th, u);
 }
 
@@ -48,31 +44,6 @@ __device__ __forceinline__ uint32_t gelu_fast_h2(uint32_t xbits) {
   const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
   const __half2 g = __hfma2(h, *reinterpret_cast<const __half2*>(&th), h);
   return *reinterpret_cast<const uint32_t*>(&g);
-}
-
-// The same evaluation split into three stages whose asm statements are volatile, so that a caller can software-pipeline a
-// run of elements: stage B (the two MUFU.TANH) of element i is issued between stage A (FMA pipe) of element i+2 and stage C
-// of element i-1.  Every warp of a scheduler reaches the GELU pass at the same time (they wait on the same MMA); without
-// the explicit interleave ptxas clusters the MUFU ops at the end of the block and the MUFU and FMA pipes take turns idling.
-__device__ __forceinline__ void gelu_h2_stage_a(uint32_t xbits, uint32_t& z, uint32_t& hx) {
-  const __half2 x = *reinterpret_cast<const __half2*>(&xbits);
-  const __half2 t = __hmin2(__hmul2(x, x), __float2half2_rn(49.0f));
-  __half2 p = __hfma2(t, __float2half2_rn(-3.5151847398e-04f), __float2half2_rn(3.7005657172e-02f));
-  p = __hfma2(t, p, __float2half2_rn(7.9750787105e-01f));
-  const uint32_t pb = *reinterpret_cast<const uint32_t*>(&p);
-  asm volatile("mul.f16x2 %0, %1, %2;" : "=r"(z) : "r"(xbits), "r"(pb));
-  const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
-  hx = *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ uint32_t gelu_h2_stage_b(uint32_t z) {
-  uint32_t th;
-  asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(z));
-  return th;
-}
-__device__ __forceinline__ uint32_t gelu_h2_stage_c(uint32_t hx, uint32_t th) {
-  uint32_t g;
-  asm volatile("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(g) : "r"(hx), "r"(th));
-  return g;
 }
 
 }  // namespace sunet

@@ -40,7 +40,9 @@ def init_process_group(backend=None):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(local)
-    dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+        dist.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend=backend, rank=rank, world_size=ws)
     return rank, ws, local
 
 
