@@ -18,11 +18,10 @@ i = 0
 while i < len(recs):
     kind, ms, flops, nbytes = recs[i]
     if kind == "attn_fused":
-        M = nbytes / 4.0                      # algorithmic bytes = 4 M C
-        C = 96 if abs(flops - (6.0 * (M / 96) * 96 * 96 + 256.0 * M)) < abs(flops - (6.0 * (M / 192) * 192 * 192 + 256.0 * M)) else 192
+        C = min((96, 192, 384), key=lambda c: abs((flops / nbytes - 64.0) / 1.5 - c))   # flops / bytes = (6 C^2 + 256 C) / (4 C)
         out[C]["blocks"] += 1
         out[C]["ms"] += ms                    # proj rides in the following mlp_fused launch (not counted here)
-        out[C]["launches_per_block"] = "1 (proj fused into the MLP kernel)"
+        out[C]["launches_per_block"] = "1 (proj fused into the MLP kernel)" if C < 384 else "1 + proj GEMM (not counted)"
         i += 1
     elif kind == "attn_core" and i >= 2 and recs[i - 1][0] == "gemm_tcgen05" and recs[i - 2][0] == "layernorm":
         C = 384 if recs[i][3] / 8.0 / B > 256 * 384 - 1 and recs[i][3] / 8.0 / B < 256 * 384 + 1 else 768
@@ -38,7 +37,7 @@ for C, L in stages:
     if not o["blocks"]:
         continue
     per_block_ms = o["ms"] / o["blocks"]
-    with_proj = C >= 384
+    with_proj = C >= 768
     flops = B * ((8.0 if with_proj else 6.0) * L * C * C + 256.0 * L * C)
     res.append({"C": C, "head_dim": C // 8, "tokens_per_image": L, "windows": B * L // 64, "blocks": o["blocks"], "launches_per_block": o["launches_per_block"],
                 "ms_per_block": per_block_ms, "algorithmic_gflop_per_block": flops / 1e9, "tflops": flops / per_block_ms * 1e-9,
