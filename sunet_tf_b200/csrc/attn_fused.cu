@@ -389,6 +389,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   const int nWc = p.W >> 3, nWr = p.H >> 3, nW = nWr * nWc;
   const long long nwin = static_cast<long long>(p.B) * nW;
   const long long tiles = (nwin + 1) >> 1;
+  // Work items are (tile, head group) pairs in tile-major order, split into contiguous, equally long runs over the CTAs: with 3.5
+  // tiles per SM (C = 192 at B = 64) whole-tile scheduling loses 13% to the last partial wave.  A CTA that starts or ends inside a
+  // tile gathers and normalises that tile itself (the other CTA sharing it does the same; they write disjoint output columns).
+  const long long total_items = tiles * K::NG;
+  const long long it_begin = total_items * blockIdx.x / gridDim.x;
+  const long long it_end = total_items * (blockIdx.x + 1) / gridDim.x;
+  const int g_first = static_cast<int>(it_begin % K::NG);
 
   // Thread <-> token mapping of the gather / statistics / scatter passes: token tk = tid >> 2 of the tile (window
   // wi = warp >> 3, the same window whose (window, head) units this warp runs in the core), 16-byte part tid & 3.
@@ -507,11 +514,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   // 64-wide k-blocks.  One thread of a warp that sits the core out is both TMA producer and MMA issuer; the ring runs ahead
   // across items (the weight sequence does not depend on the tile), refilling a slot one k-block after its MMAs were issued.
   uint32_t rk_loaded = 0;      // k-blocks whose TMA has been issued (sequence number over items)
-  const uint32_t rk_total = K::RING ? static_cast<uint32_t>(((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * K::NG * K::KB) : 0u;
+  const uint32_t rk_total = K::RING ? static_cast<uint32_t>((it_end - it_begin) * K::KB) : 0u;
   auto ring_load = [&](uint32_t empty_ok) {   // issue the TMA of k-block rk_loaded (its slot must be free; empty_ok: an earlier test said so)
     const uint32_t c = rk_loaded, slot = c % K::RSTAGES;
     if (c >= K::RSTAGES) mbar_wait_hint(&rk_empty[slot], ((c / K::RSTAGES) - 1) & 1, empty_ok);
-    const int g = static_cast<int>((c / K::KB) % K::NG), kb = static_cast<int>(c % K::KB);
+    const int g = static_cast<int>((g_first + c / K::KB) % K::NG), kb = static_cast<int>(c % K::KB);
     mbar_arrive_expect_tx(&rk_full[slot], K::WKB_BYTES);
     tma_load_2d(smem + K::OFF_W + slot * K::WKB_BYTES, &tmW, &rk_full[slot], kb * 64, g * K::NGC);
     ++rk_loaded;
@@ -565,9 +572,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
 
   uint32_t item = 0;
   AF_T_DECL;
-  Geo geo = tile_geo(blockIdx.x);
-  if (static_cast<long long>(blockIdx.x) < tiles) {
-    if (!K::RING && tid == 0) load_w(0);
+  Geo geo = tile_geo(it_begin / K::NG);
+  if (it_begin < it_end) {
+    if (!K::RING && tid == 0) load_w(g_first);
     gather(geo);
     cp_async_wait_all();
     normalize();
@@ -580,14 +587,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     __syncwarp();
   }
   uint32_t md_ok = 0;  // early-test result for the current item's mma_done phase
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long next_tile = tile + gridDim.x;
-    const bool has_next_tile = next_tile < tiles;
-    Geo geo_next = geo;
+  Geo geo_next = geo;
+  {
 #pragma unroll 1
-    for (int g = 0; g < K::NG; ++g, ++item) {
+    for (long long it = it_begin; it < it_end; ++it, ++item) {
+      const long long tile = it / K::NG;
+      const int g = static_cast<int>(it - tile * K::NG);
       const bool last_g = g == K::NG - 1;
-      const bool has_next = !last_g || has_next_tile;
+      const bool has_next = it + 1 < it_end;
+      const bool has_next_tile = has_next && last_g;   // the next item opens a new tile
+      const long long next_tile = tile + 1;
       AF_T_START;
       mbar_wait_hint(&mma_done, item & 1, md_ok);
       tc_fence_after();
@@ -672,8 +681,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       md_ok = md_next;
       __syncthreads();   // (D) q tiles free for the next drain
       AF_T(7);
+      if (last_g) geo = geo_next;
     }
-    geo = geo_next;
   }
 #if SUNET_KERNEL_TIMING
   if (p.timing && (tid & 31) == 0) {
@@ -739,7 +748,8 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   const long long nwin = static_cast<long long>(B) * (H / 8) * (W / 8);
   if (nwin > 0x3fffffffLL || static_cast<long long>(B) * H * W > 0x7fffffffLL) return fail(SUNET_E_SHAPE, "fused attention: too many tokens for 32-bit row indices");
   const long long tiles = (nwin + 1) / 2;
-  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);
+  const long long items = tiles * K::NG;
+  const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
   SUNET_CUDA(launch_pdl(attn_fused_kernel<C, GH>, dim3(grid), dim3(NTHREADS), K::SMEM, stream, p.tmW, prm));
   if (timing) {   // bring-up aid: per-phase cycles averaged over CTAs, for warp 0 (MMA issuer) and the mean of the other warps
     SUNET_CUDA(cudaStreamSynchronize(stream));
