@@ -72,6 +72,21 @@ int sunet_patch_embed_fwd(sunet_handle_t h, const float* x, int batch, int himg,
 size_t sunet_workspace_bytes(sunet_handle_t h, int batch, int max_chunk);
 int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,
                   size_t workspace_bytes, void* stream);
+/* The demo.py I/O edge (demo.py:70-79: PIL RGB -> TF.to_tensor -> model -> torch.clamp(0,1) -> img_as_ubyte) in one call:
+ * x (B, img, img, in_chans) uint8 interleaved as PIL / cv2 hold it -> out (B, img, img, out_chans) uint8 =
+ * rint(clamp(model(x / 255), 0, 1) * 255).  The /255 is applied as the first kernel loads the image, clamp + quantisation
+ * as the last kernel stores it; host<->device traffic is 1 byte per sample instead of 4. */
+int sunet_forward_u8(sunet_handle_t h, const uint8_t* x, int in_chans, int batch, int max_chunk, uint8_t* out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* The validation-loop forward (train.py:432-443): logits = model(x); prob = sigmoid(logits); se = (logits - target)^2,
+ * reduced inside the last kernel.  target (B, target_chans, img, img) fp32 with target_chans == out_chans, or 3 with
+ * out_chans == 1 (reduced to luminance 0.2989 R + 0.5870 G + 0.1140 B, :437-438); weight (B, 1, img, img) fp32 or NULL
+ * (the per-pixel map of make_weights_from_numpy, :226-249, computed by the caller as in the reference); prob may be NULL.
+ * sums (device, 5 doubles, overwritten): sum se, sum se*w, sum w, sum sqrt((logits-target)^2 + eps^2)*w, element count, so that
+ * se.mean() = s0/s4 (:442), weighted MSE = s1/max(1e-8, s2) (:445), charbonnier_loss = s3/max(1e-8, s2) (:187-192, :447). */
+int sunet_forward_eval(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, const float* target, int target_chans,
+                       const float* weight, float eps, float* logits, float* prob, double* sums, void* workspace,
+                       size_t workspace_bytes, void* stream);
 /* Same forward with every kernel launch bracketed by CUDA events on `stream` (synchronises before returning).
  * recs[i] = {kind, device ms, algorithmic FLOPs, algorithmic bytes} in launch order; kind: 0 tcgen05 GEMM, 1 attention core,
  * 2 LayerNorm, 3 merge-gather+LN, 4 patch-embed conv, 5 up-sample combine, 6 tail stencil, 7 cast, 8 im2col, 9 fused LN+MLP+residual,

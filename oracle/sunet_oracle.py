@@ -317,3 +317,44 @@ def fold_tiles(tiles, X, h, w, kernel=256, stride=128):
     acc = acc / cnt
     oy, ox = (X - h) // 2, (X - w) // 2
     return torch.clamp(acc[:, :, oy:oy + h, ox:ox + w], 0, 1)
+
+
+# ----------------------------------------------------------------------------- demo.py image edge (§8f-3)
+def to_tensor_u8(img_u8):
+    """demo.py:70-71 `TF.to_tensor(PIL RGB)`: uint8 (B, H, W, C) -> float32 (B, C, H, W) / 255."""
+    return img_u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
+
+
+def to_ubyte(restored):
+    """demo.py:76-79: clamp(restored, 0, 1) -> NHWC -> skimage.img_as_ubyte, which for float input is
+    rint(x * 255) clipped to [0, 255] (skimage.util.dtype._convert: multiply by imax_out, np.rint, np.clip; skimage is not
+    installed here - np.rint and torch.round both round half to even)."""
+    x = torch.clamp(restored, 0, 1).permute(0, 2, 3, 1)
+    return torch.clamp(torch.round(x * 255.0), 0, 255).to(torch.uint8)
+
+
+def demo_restore_u8(sd, img_u8, arch=None):
+    """demo.py:69-79 for a batch of 8-bit images: (B, H, W, 3) uint8 -> (B, H, W, 1) uint8."""
+    return to_ubyte(sunet_model_forward(sd, to_tensor_u8(img_u8), arch))
+
+
+# ----------------------------------------------------------------------------- train.py validation reductions (§8f-4)
+def charbonnier_loss(pred, target, weight=None, eps=1e-3):
+    """train.py:187-192."""
+    diff = pred - target
+    l = torch.sqrt(diff * diff + eps * eps)
+    if weight is None:
+        return l.mean()
+    return (l * weight).sum() / weight.sum().clamp(min=1e-8)
+
+
+def validation_batch(logits, target, weight=None, eps=1e-3):
+    """train.py:437-448 for one batch, given the model output: luminance target, prob = sigmoid(logits), mean squared error,
+    weighted squared error and weighted Charbonnier loss (weight None = the unit map).  Returns (prob, dict)."""
+    if target.shape[1] == 3:
+        target = 0.2989 * target[:, 0:1] + 0.5870 * target[:, 1:2] + 0.1140 * target[:, 2:3]
+    prob = torch.sigmoid(logits)
+    se = (logits - target) ** 2
+    w = weight if weight is not None else torch.ones_like(target)
+    return prob, {"mse": se.mean().item(), "mse_weighted": (se * w).sum().item() / max(1e-8, w.sum().item()),
+                  "charbonnier": charbonnier_loss(logits, target, weight=w, eps=eps).item()}

@@ -178,8 +178,8 @@ int merge_gather_ln_f16(const __half* in, __half* out, const float* gamma, const
 // ------------------------------------------------------------------------------------------------ folded PatchEmbed
 // CTA = 8x8 tokens; warp = one token row (8 tokens); lane = EPL output channels {lane, lane+32, ...}.
 // Per tap: EPL conflict-free weight reads + 8 broadcast input reads feed 8*EPL FMAs.
-template <int EPL>
-__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, int img_chans, int Himg, int Wimg,
+template <int EPL, bool U8>
+__global__ void __launch_bounds__(256) patch_embed_kernel(const void* __restrict__ img_v, int img_chans, int Himg, int Wimg,
                                                           const float* __restrict__ wfold, const float* __restrict__ bfold,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           __half* __restrict__ out) {
@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
     float v = 0.f;
     if (y >= 0 && y < Himg && x >= 0 && x < Wimg) {
       const int cs = img_chans == 1 ? 0 : c;   // grey input is repeated to 3 channels (model/SUNet.py:27-28)
-      v = __ldg(img + ((static_cast<int64_t>(b) * img_chans + cs) * Himg + y) * Wimg + x);
+      if (U8)   // PIL layout (B, H, W, chans); to_tensor's division by 255 (demo.py:71)
+        v = static_cast<float>(__ldg(static_cast<const uint8_t*>(img_v) + ((static_cast<int64_t>(b) * Himg + y) * Wimg + x) * img_chans + cs)) / 255.f;
+      else
+        v = __ldg(static_cast<const float*>(img_v) + ((static_cast<int64_t>(b) * img_chans + cs) * Himg + y) * Wimg + x);
     }
     s_in[(c * 34 + r) * PITCH + col] = v;
   }
@@ -260,18 +263,20 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   }
 }
 
-int patch_embed_fused(const float* img, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
+int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
                       const float* gamma, const float* beta, int E, __half* out, cudaStream_t s) {
   if (img_chans != 1 && img_chans != 3) return fail(SUNET_E_SHAPE, "patch embed: input must have 1 or 3 channels, got %d", img_chans);
   if (Himg % 32 || Wimg % 32) return fail(SUNET_E_SHAPE, "patch embed: image %dx%d must be a multiple of 32", Himg, Wimg);
   if (E % 32 || E > 128) return fail(SUNET_E_SHAPE, "patch embed: embed_dim %d must be a multiple of 32 and <= 128", E);
   const unsigned grid = static_cast<unsigned>(B) * (Himg / 32) * (Wimg / 32);
   const int smem = (3 * 34 * 35 + 108 * E) * 4;
-#define PE_LAUNCH(EPL)                                                                                          \
+#define PE_LAUNCH_T(EPL, U8)                                                                                    \
   {                                                                                                             \
-    SUNET_CUDA(cudaFuncSetAttribute(patch_embed_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    SUNET_CUDA(launch_pdl(patch_embed_kernel<EPL>, dim3(grid), dim3(256), smem, s, img, img_chans, Himg, Wimg, wfold, bfold, gamma, beta, out));   \
+    SUNET_CUDA(cudaFuncSetAttribute(patch_embed_kernel<EPL, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    SUNET_CUDA(launch_pdl(patch_embed_kernel<EPL, U8>, dim3(grid), dim3(256), smem, s, img, img_chans, Himg, Wimg, wfold, bfold, gamma, beta, out));   \
   }
+#define PE_LAUNCH(EPL)                                                                                          \
+  if (img_fmt == IMG_U8_NHWC) PE_LAUNCH_T(EPL, true) else PE_LAUNCH_T(EPL, false)
   switch (E / 32) {
     case 1: PE_LAUNCH(1); break;
     case 2: PE_LAUNCH(2); break;
@@ -373,53 +378,121 @@ int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, 
 }
 
 // ------------------------------------------------------------------------------------------------ folded tail stencil
+// MODE 0: fp32 NCHW; 1: 8-bit NHWC, rint(clamp(v, 0, 1) * 255); 2: fp32 NCHW + validation epilogue (EvalEpilogue)
+template <int MODE>
 __global__ void __launch_bounds__(256) tail_stencil_kernel(const float* __restrict__ Qp, const float* __restrict__ Rb,
-                                                           float* __restrict__ out, int H, int W, int OC, int NT, int64_t total) {
+                                                           void* __restrict__ out_v, EvalEpilogue ev, int H, int W, int OC, int NT,
+                                                           int64_t total) {
   pdl_wait();
   pdl_launch_dependents();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  const bool live = i < total;
+  if (MODE != 2 && !live) return;
   const int OW = 4 * W, OH = 4 * H;
-  const int x = static_cast<int>(i % OW), y = static_cast<int>((i / OW) % OH);
-  const int64_t b = i / (static_cast<int64_t>(OW) * OH);
-  int yy0[3], yy1[3], xx0[3], xx1[3];
-  float ly[3], lx[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    bilinear_tap(min(max(y + d - 1, 0), OH - 1), 4, H, yy0[d], yy1[d], ly[d]);
-    bilinear_tap(min(max(x + d - 1, 0), OW - 1), 4, W, xx0[d], xx1[d], lx[d]);
-  }
   float acc[3] = {0.f, 0.f, 0.f};
-  const float* rb = Rb + b * H * W * NT;
+  int x = 0, y = 0;
+  int64_t b = 0;
+  if (live) {
+    x = static_cast<int>(i % OW);
+    y = static_cast<int>((i / OW) % OH);
+    b = i / (static_cast<int64_t>(OW) * OH);
+    int yy0[3], yy1[3], xx0[3], xx1[3];
+    float ly[3], lx[3];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int ny = y + dy - 1;
-    if (ny < 0 || ny >= OH) continue;
+    for (int d = 0; d < 3; ++d) {
+      bilinear_tap(min(max(y + d - 1, 0), OH - 1), 4, H, yy0[d], yy1[d], ly[d]);
+      bilinear_tap(min(max(x + d - 1, 0), OW - 1), 4, W, xx0[d], xx1[d], lx[d]);
+    }
+    const float* rb = Rb + b * H * W * NT;
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int nx = x + dx - 1;
-      if (nx < 0 || nx >= OW) continue;
-      const int t = dy * 3 + dx;
-      const float* q = Qp + ((((b * H + (ny >> 2)) * W + (nx >> 2)) << 4) + ((ny & 3) << 2) + (nx & 3)) * NT;
-      const float* r00 = rb + (static_cast<int64_t>(yy0[dy]) * W + xx0[dx]) * NT;
-      const float* r01 = rb + (static_cast<int64_t>(yy0[dy]) * W + xx1[dx]) * NT;
-      const float* r10 = rb + (static_cast<int64_t>(yy1[dy]) * W + xx0[dx]) * NT;
-      const float* r11 = rb + (static_cast<int64_t>(yy1[dy]) * W + xx1[dx]) * NT;
-      for (int oc = 0; oc < OC; ++oc) {
-        const int col = oc * 9 + t;
-        const float top = __ldg(r00 + col) * (1.f - ly[dy]) + __ldg(r10 + col) * ly[dy];
-        const float bot = __ldg(r01 + col) * (1.f - ly[dy]) + __ldg(r11 + col) * ly[dy];
-        acc[oc] += __ldg(q + col) + top * (1.f - lx[dx]) + bot * lx[dx];
+    for (int dy = 0; dy < 3; ++dy) {
+      const int ny = y + dy - 1;
+      if (ny < 0 || ny >= OH) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int nx = x + dx - 1;
+        if (nx < 0 || nx >= OW) continue;
+        const int t = dy * 3 + dx;
+        const float* q = Qp + ((((b * H + (ny >> 2)) * W + (nx >> 2)) << 4) + ((ny & 3) << 2) + (nx & 3)) * NT;
+        const float* r00 = rb + (static_cast<int64_t>(yy0[dy]) * W + xx0[dx]) * NT;
+        const float* r01 = rb + (static_cast<int64_t>(yy0[dy]) * W + xx1[dx]) * NT;
+        const float* r10 = rb + (static_cast<int64_t>(yy1[dy]) * W + xx0[dx]) * NT;
+        const float* r11 = rb + (static_cast<int64_t>(yy1[dy]) * W + xx1[dx]) * NT;
+        for (int oc = 0; oc < OC; ++oc) {
+          const int col = oc * 9 + t;
+          const float top = __ldg(r00 + col) * (1.f - ly[dy]) + __ldg(r10 + col) * ly[dy];
+          const float bot = __ldg(r01 + col) * (1.f - ly[dy]) + __ldg(r11 + col) * ly[dy];
+          acc[oc] += __ldg(q + col) + top * (1.f - lx[dx]) + bot * lx[dx];
+        }
       }
     }
   }
-  for (int oc = 0; oc < OC; ++oc) out[((b * OC + oc) * OH + y) * OW + x] = acc[oc];
+  if (MODE == 1) {
+    uint8_t* o = static_cast<uint8_t*>(out_v) + ((b * OH + y) * OW + x) * OC;
+    for (int oc = 0; oc < OC; ++oc) o[oc] = static_cast<uint8_t>(__float2int_rn(fminf(fmaxf(acc[oc], 0.f), 1.f) * 255.f));
+    return;
+  }
+  float* out = static_cast<float*>(out_v);
+  if (live)
+    for (int oc = 0; oc < OC; ++oc) out[((b * OC + oc) * OH + y) * OW + x] = acc[oc];
+  if (MODE == 2) {
+    // train.py:437-443: luminance target, prob = sigmoid(logits), se = (logits - target)^2, weighted sums, Charbonnier
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+      const int64_t plane = static_cast<int64_t>(OH) * OW, pix = static_cast<int64_t>(y) * OW + x;
+      const float w = ev.weight ? __ldg(ev.weight + b * plane + pix) : 1.f;
+      for (int oc = 0; oc < OC; ++oc) {
+        float t;
+        if (ev.target_chans == OC) {
+          t = __ldg(ev.target + (b * OC + oc) * plane + pix);
+        } else {   // 3 -> 1
+          const float* tp = ev.target + b * 3 * plane + pix;
+          t = 0.2989f * __ldg(tp) + 0.5870f * __ldg(tp + plane) + 0.1140f * __ldg(tp + 2 * plane);
+        }
+        if (ev.prob) ev.prob[(b * OC + oc) * plane + pix] = 1.f / (1.f + expf(-acc[oc]));
+        const float d = acc[oc] - t, se = d * d;
+        part[0] += se;
+        part[1] += static_cast<double>(se * w);
+        part[2] += w;
+        part[3] += static_cast<double>(sqrtf(se + ev.eps * ev.eps) * w);
+      }
+    }
+    __shared__ double red[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+      if (lane == 0) red[k][warp] = part[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int wi = 0; wi < 8; ++wi) t += red[threadIdx.x][wi];
+      atomicAdd(ev.sums + threadIdx.x, t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 4) atomicAdd(ev.sums + 4, static_cast<double>(total) * OC);
+  }
 }
 
-int tail_stencil(const float* Qp, const float* Rb, float* out, int B, int H, int W, int OC, int NT, cudaStream_t s) {
+int tail_stencil(const float* Qp, const float* Rb, void* out, int out_fmt, const EvalEpilogue* ev, int B, int H, int W, int OC, int NT,
+                 cudaStream_t s) {
   if (OC < 1 || OC > 3 || NT < OC * 9) return fail(SUNET_E_SHAPE, "tail: out_chans=%d (1..3) NT=%d", OC, NT);
   const int64_t total = static_cast<int64_t>(B) * 16 * H * W;
-  SUNET_CUDA(launch_pdl(tail_stencil_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, s, Qp, Rb, out, H, W, OC, NT, total));
+  const dim3 grid(blocks_for(total, 256)), block(256);
+  EvalEpilogue e;
+  if (ev) {
+    if (out_fmt != IMG_F32_NCHW) return fail(SUNET_E_ARG, "tail: the validation epilogue needs fp32 output");
+    if (!ev->target || !ev->sums) return fail(SUNET_E_ARG, "tail: validation epilogue without target / sums");
+    if (ev->target_chans != OC && !(ev->target_chans == 3 && OC == 1))
+      return fail(SUNET_E_SHAPE, "tail: target has %d channels, output %d", ev->target_chans, OC);
+    e = *ev;
+    SUNET_CUDA(launch_pdl(tail_stencil_kernel<2>, grid, block, 0, s, Qp, Rb, out, e, H, W, OC, NT, total));
+  } else if (out_fmt == IMG_U8_NHWC) {
+    SUNET_CUDA(launch_pdl(tail_stencil_kernel<1>, grid, block, 0, s, Qp, Rb, out, e, H, W, OC, NT, total));
+  } else {
+    SUNET_CUDA(launch_pdl(tail_stencil_kernel<0>, grid, block, 0, s, Qp, Rb, out, e, H, W, OC, NT, total));
+  }
   SUNET_CHECK_LAUNCH();
   return 0;
 }

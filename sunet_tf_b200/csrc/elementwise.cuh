@@ -18,8 +18,11 @@ int merge_gather_ln_f16(const __half* in, __half* out, const float* gamma, const
                         cudaStream_t s);
 
 // conv_first (3x3, pad 1) folded with patch_embed.proj (4x4, stride 4) into one 6x6 / stride 4 / pad 1 conv, + LayerNorm.
-// img: fp32 NCHW (B, img_chans in {1,3}, Himg, Wimg); wfold: fp32 [108][E] (tap-major: k = c*36 + u*6 + v); out fp16 (B, Himg/4*Wimg/4, E).
-int patch_embed_fused(const float* img, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
+// img: fp32 NCHW (B, img_chans in {1,3}, Himg, Wimg), or - img_fmt IMG_U8_NHWC - the 8-bit interleaved image as PIL holds it
+// (B, Himg, Wimg, img_chans), scaled by 1/255 on load (TF.to_tensor, demo.py:71);
+// wfold: fp32 [108][E] (tap-major: k = c*36 + u*6 + v); out fp16 (B, Himg/4*Wimg/4, E).
+enum ImgFmt { IMG_F32_NCHW = 0, IMG_U8_NHWC = 1 };
+int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
                       const float* gamma, const float* beta, int E, __half* out, cudaStream_t s);
 
 // im2col for a stand-alone PatchEmbed (conv k = stride = P): A[m][c*P*P + ky*P + kx] fp16
@@ -32,8 +35,20 @@ int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, 
                      cudaStream_t s);
 
 // Folded tail: out[b][oc][y][x] = sum_{t=(dy,dx)} inb(y+dy-1, x+dx-1) * ( Qp[pix][oc*9+t] + bilinear4(Rb[..][oc*9+t])(pix) )
-// Qp: fp32 [B*H*W*16][NT] rows ordered (b,h,w,i,j); Rb: fp32 [B*H*W][NT]; out fp32 NCHW (B, OC, 4H, 4W).
-int tail_stencil(const float* Qp, const float* Rb, float* out, int B, int H, int W, int OC, int NT, cudaStream_t s);
+// Qp: fp32 [B*H*W*16][NT] rows ordered (b,h,w,i,j); Rb: fp32 [B*H*W][NT]; out fp32 NCHW (B, OC, 4H, 4W), or - out_fmt IMG_U8_NHWC -
+// the 8-bit interleaved image rint(clamp(out, 0, 1) * 255) of demo.py:76-79 (torch.clamp + img_as_ubyte), (B, 4H, 4W, OC).
+// With `ev` (validation forward, train.py:432-443; fp32 output only) the same pass also writes sigmoid(out) and accumulates
+// the squared-error / Charbonnier sums against the target (3-channel targets are reduced to luminance when OC == 1, :437-438).
+struct EvalEpilogue {
+  const float* target = nullptr;  // (B, target_chans, 4H, 4W) fp32
+  int target_chans = 0;           // OC, or 3 with OC == 1
+  const float* weight = nullptr;  // (B, 1, 4H, 4W) fp32 or null (= ones)
+  float* prob = nullptr;          // (B, OC, 4H, 4W) fp32 or null
+  double* sums = nullptr;         // [5]: sum se, sum se*w, sum w, sum sqrt(d^2+eps^2)*w, element count; accumulated (caller zeroes)
+  float eps = 1e-3f;
+};
+int tail_stencil(const float* Qp, const float* Rb, void* out, int out_fmt, const EvalEpilogue* ev, int B, int H, int W, int OC, int NT,
+                 cudaStream_t s);
 
 // ---- pre-pack helpers (run once per weight load)
 // dst[n][k] = half(src[n][k] * (n < scale_rows ? scale : 1))

@@ -82,6 +82,9 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   std::vector<ProfRec>* prof = nullptr;  // when set, every launch is bracketed by CUDA events on `stream`
+  // image formats at the two ends of the whole-model forward, and the optional validation epilogue of the last kernel
+  int in_fmt = IMG_F32_NCHW, out_fmt = IMG_F32_NCHW;
+  const EvalEpilogue* ev = nullptr;
   bool dry() const { return sc.dry; }
 };
 
@@ -398,7 +401,7 @@ struct TailPack {
     SUNET_TRY(fold_tail_taps(wo, up.Ab, gb.w, OC, E, NT, s));
     return 0;
   }
-  int forward(Ctx& c, const __half* x, float* out, int B) const {
+  int forward(Ctx& c, const __half* x, void* out, int B) const {
     ScratchMark mk(c.sc);
     const int64_t M = static_cast<int64_t>(B) * H * W;
     __half *Pb, *Bb;
@@ -417,7 +420,8 @@ struct TailPack {
     }
     SUNET_TRY(run_linear(c, up.b0, x, E, M, Bb, E, ACT_PRELU, up.slope_b));
     SUNET_TRY(run_linear(c, gb, Bb, E, M, Rb, NT, ACT_NONE, nullptr, nullptr, 0, 1));
-    RUN(c, K_TAIL, 0.0, 4.0 * M * NT * 17 + 4.0 * M * 16 * OC, tail_stencil(Qp, Rb, out, B, H, W, OC, NT, c.stream));
+    RUN(c, K_TAIL, 0.0, 4.0 * M * NT * 17 + (c.out_fmt == IMG_U8_NHWC ? 1.0 : 4.0) * M * 16 * OC,
+        tail_stencil(Qp, Rb, out, c.out_fmt, c.ev, B, H, W, OC, NT, c.stream));
     return 0;
   }
 };
@@ -508,7 +512,7 @@ static int pack_model(ModelHandle* h, const Params& P, const int64_t* ia, int ni
 }
 
 // one chunk of Bc images; x NCHW fp32 -> out NCHW fp32
-static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int in_chans, int Bc, float* out) {
+static int model_forward_chunk(const ModelPack& m, Ctx& c, const void* x, int in_chans, int Bc, void* out) {
   ScratchMark mk(c.sc);
   const int E = m.E, G = m.G;
   const int64_t S = static_cast<int64_t>(Bc) * G * G * E;  // elements of the stage-0 token stream
@@ -519,7 +523,8 @@ static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int i
   SUNET_TRY(c.sc.take_t(&Xa, S));
   SUNET_TRY(c.sc.take_t(&Xb, S));
   SUNET_TRY(c.sc.take_t(&T, S));
-  RUN(c, K_PATCH_EMBED, 2.0 * 108 * S, 4.0 * Bc * in_chans * m.img * m.img + 2.0 * S, patch_embed_fused(x, in_chans, Bc, m.img, m.img, m.wfold, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
+  RUN(c, K_PATCH_EMBED, 2.0 * 108 * S, (c.in_fmt == IMG_U8_NHWC ? 1.0 : 4.0) * Bc * in_chans * m.img * m.img + 2.0 * S,
+      patch_embed_fused(x, c.in_fmt, in_chans, Bc, m.img, m.img, m.wfold, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
   // encoder + bottleneck (:714-716).  x_downsample[i] = input of stage i stays untouched in skip[i].
   const __half* cur = skip[0];
   for (int i = 0; i < 4; ++i) {
@@ -551,16 +556,31 @@ static int model_forward_chunk(const ModelPack& m, Ctx& c, const float* x, int i
   return 0;
 }
 
-static int model_forward(const ModelPack& m, Ctx& c, const float* x, int in_chans, int batch, int max_chunk, float* out) {
+// x / out: c.in_fmt / c.out_fmt images (fp32 NCHW or 8-bit NHWC); c.ev (optional) describes the whole batch.
+static int model_forward(const ModelPack& m, Ctx& c, const void* x, int in_chans, int batch, int max_chunk, void* out) {
   if (in_chans != 1 && in_chans != 3) return fail(SUNET_E_SHAPE, "sunet: input has %d channels (1 or 3)", in_chans);
   if (batch <= 0) return fail(SUNET_E_SHAPE, "sunet: batch %d", batch);
   if (max_chunk <= 0) max_chunk = 64;
-  const int64_t in_img = static_cast<int64_t>(in_chans) * m.img * m.img, out_img = static_cast<int64_t>(m.out_chans) * m.img * m.img;
-  for (int b0 = 0; b0 < batch; b0 += max_chunk) {
+  const int64_t plane = static_cast<int64_t>(m.img) * m.img;
+  const int64_t in_img = in_chans * plane * (c.in_fmt == IMG_U8_NHWC ? 1 : 4);        // bytes per image
+  const int64_t out_img = m.out_chans * plane * (c.out_fmt == IMG_U8_NHWC ? 1 : 4);
+  const EvalEpilogue* whole = c.ev;
+  int rc = 0;
+  for (int b0 = 0; b0 < batch && !rc; b0 += max_chunk) {
     const int bc = batch - b0 < max_chunk ? batch - b0 : max_chunk;
-    SUNET_TRY(model_forward_chunk(m, c, x ? x + b0 * in_img : nullptr, in_chans, bc, out ? out + b0 * out_img : nullptr));
+    EvalEpilogue part;
+    if (whole) {
+      part = *whole;
+      part.target += b0 * whole->target_chans * plane;
+      if (part.weight) part.weight += b0 * plane;
+      if (part.prob) part.prob += b0 * m.out_chans * plane;
+      c.ev = &part;
+    }
+    rc = model_forward_chunk(m, c, x ? static_cast<const uint8_t*>(x) + b0 * in_img : nullptr, in_chans, bc,
+                             out ? static_cast<uint8_t*>(out) + b0 * out_img : nullptr);
   }
-  return 0;
+  c.ev = whole;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ per-module fp32 wrappers
@@ -802,6 +822,38 @@ int sunet_forward(sunet_handle_t h, const float* x, int in_chans, int batch, int
   c.sc.base = static_cast<uint8_t*>(workspace);
   c.sc.cap = workspace_bytes;
   return model_forward(mh->p, c, x, in_chans, batch, max_chunk, out);
+}
+
+int sunet_forward_u8(sunet_handle_t h, const uint8_t* x, int in_chans, int batch, int max_chunk, uint8_t* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  GET_HANDLE(ModelHandle, mh, h, "sunet");
+  if (!x || !out || !workspace) return fail(SUNET_E_ARG, "sunet_forward_u8: null pointer");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SUNET_E_ALIGN, "sunet_forward_u8: workspace must be 256-byte aligned");
+  Ctx c;
+  c.stream = static_cast<cudaStream_t>(stream);
+  c.sc.base = static_cast<uint8_t*>(workspace);
+  c.sc.cap = workspace_bytes;
+  c.in_fmt = c.out_fmt = IMG_U8_NHWC;
+  return model_forward(mh->p, c, x, in_chans, batch, max_chunk, out);
+}
+
+int sunet_forward_eval(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, const float* target, int target_chans,
+                       const float* weight, float eps, float* logits, float* prob, double* sums, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  GET_HANDLE(ModelHandle, mh, h, "sunet");
+  if (!x || !target || !logits || !sums || !workspace) return fail(SUNET_E_ARG, "sunet_forward_eval: null pointer");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SUNET_E_ALIGN, "sunet_forward_eval: workspace must be 256-byte aligned");
+  if (target_chans != mh->p.out_chans && !(target_chans == 3 && mh->p.out_chans == 1))
+    return fail(SUNET_E_SHAPE, "sunet_forward_eval: target has %d channels, the model outputs %d", target_chans, mh->p.out_chans);
+  Ctx c;
+  c.stream = static_cast<cudaStream_t>(stream);
+  c.sc.base = static_cast<uint8_t*>(workspace);
+  c.sc.cap = workspace_bytes;
+  EvalEpilogue ev;
+  ev.target = target; ev.target_chans = target_chans; ev.weight = weight; ev.prob = prob; ev.sums = sums; ev.eps = eps;
+  c.ev = &ev;
+  SUNET_CUDA(cudaMemsetAsync(sums, 0, 5 * sizeof(double), c.stream));
+  return model_forward(mh->p, c, x, in_chans, batch, max_chunk, logits);
 }
 
 int sunet_forward_profile(sunet_handle_t h, const float* x, int in_chans, int batch, int max_chunk, float* out, void* workspace,

@@ -28,3 +28,11 @@ class SUNet_model(nn.Module):
     def forward(self, x, out=None):
         # 1- or 3-channel input; the grey->RGB repeat is folded into the first kernel.  `out` (optional) receives the result.
         return self.swin_unet(x, out=out)
+
+    def forward_u8(self, x, out=None):
+        """uint8 (B, H, W, C) in -> uint8 (B, H, W, out_chans) out: the demo.py:70-79 edge fused into the forward."""
+        return self.swin_unet.forward_u8(x, out=out)
+
+    def forward_eval(self, x, target, weight=None, eps=1e-3):
+        """Validation forward (train.py:432-448): logits, sigmoid(logits) and the error sums in one pass."""
+        return self.swin_unet.forward_eval(x, target, weight=weight, eps=eps)

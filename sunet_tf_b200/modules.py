@@ -524,3 +524,51 @@ class SUNet(_Packed):
             _lib.check(_lib.load().sunet_forward(handle, _ptr(x), C, B, self.max_chunk, _ptr(out), _ptr(ws), ws.numel(),
                                                 _lib.stream_ptr(x.device)))
         return out
+
+    @torch.no_grad()
+    def forward_u8(self, x, out=None):
+        """demo.py:70-79 as one call: x (B, H, W, 1|3) uint8 as PIL holds it -> (B, H, W, out_chans) uint8 =
+        img_as_ubyte(clamp(model(to_tensor(x)), 0, 1)).  /255 and clamp*255 happen inside the first / last kernel."""
+        if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.uint8 or x.dim() != 4:
+            raise RuntimeError("SUNet.forward_u8: x must be a (B, H, W, C) uint8 CUDA tensor (this package has no CPU path)")
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        if H != self.img_size or W != self.img_size:
+            raise RuntimeError(f"SUNet: input {H}x{W} does not match img_size {self.img_size}; use sunet_tf_b200.tiles for other resolutions")
+        handle = self._handle()
+        ws = self._workspace(handle, B, x.device)
+        if out is None:
+            out = torch.empty(B, H, W, self.out_chans, device=x.device, dtype=torch.uint8)
+        elif out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous() or out.numel() != B * H * W * self.out_chans:
+            raise RuntimeError("SUNet.forward_u8: out must be a contiguous (B, H, W, out_chans) uint8 CUDA tensor")
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_forward_u8(handle, _ptr(x), C, B, self.max_chunk, _ptr(out), _ptr(ws), ws.numel(),
+                                                   _lib.stream_ptr(x.device)))
+        return out
+
+    @torch.no_grad()
+    def forward_eval(self, x, target, weight=None, eps=1e-3):
+        """The validation-loop forward of train.py:432-448 in one call.  Returns (logits, prob, sums) with prob =
+        sigmoid(logits) and sums a 5-element float64 CUDA tensor [sum se, sum se*w, sum w, sum charbonnier*w, count]
+        reduced inside the last kernel (no host sync here; see sunet_tf_b200.validation.metrics_from_sums)."""
+        x = _lib.require_cuda(x, "x")
+        target = _lib.require_cuda(target, "target")
+        B, C, H, W = x.shape
+        if H != self.img_size or W != self.img_size:
+            raise RuntimeError(f"SUNet: input {H}x{W} does not match img_size {self.img_size}")
+        if target.dim() != 4 or target.shape[0] != B or tuple(target.shape[2:]) != (H, W):
+            raise RuntimeError(f"SUNet.forward_eval: target {tuple(target.shape)} does not match the input batch {B}x{H}x{W}")
+        if weight is not None:
+            weight = _lib.require_cuda(weight, "weight")
+            if weight.numel() != B * H * W:
+                raise RuntimeError("SUNet.forward_eval: weight must be (B, 1, H, W)")
+        handle = self._handle()
+        ws = self._workspace(handle, B, x.device)
+        logits = torch.empty(B, self.out_chans, H, W, device=x.device, dtype=torch.float32)
+        prob = torch.empty_like(logits)
+        sums = torch.empty(5, device=x.device, dtype=torch.float64)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sunet_forward_eval(handle, _ptr(x), C, B, self.max_chunk, _ptr(target), target.shape[1],
+                                                     _ptr(weight) if weight is not None else None, float(eps), _ptr(logits), _ptr(prob),
+                                                     _ptr(sums), _ptr(ws), ws.numel(), _lib.stream_ptr(x.device)))
+        return logits, prob, sums

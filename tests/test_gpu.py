@@ -301,3 +301,114 @@ def test_error_paths(dev, model_init):
         model_init(torch.zeros(1, 2, 256, 256, device=dev))          # 2 channels
     with pytest.raises(RuntimeError):
         Mlp(96, 100).to(dev)(torch.zeros(4, 96, device=dev))         # hidden not a multiple of 16
+
+
+# ---------------------------------------------------------------- callers either side of the forward
+def _u8_model(dev):
+    from oracle.make_golden_edges import u8_state_dict
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    return load_sd(SUNet_model(DEFAULT_OPT), u8_state_dict(21), dev)
+
+
+def test_forward_u8_vs_reference_golden_and_float_path(dev):
+    """demo.py:70-79 in one call.  (a) bit-exact against the float entry point + the reference's quantisation rule (same kernels,
+    /255 and clamp*255 folded into the first / last one); (b) within one 8-bit level of the reference golden (the float outputs
+    differ by <= 2e-3 = 0.51 level) with <= 2 % of the pixels moved."""
+    from oracle.make_golden_edges import u8_images
+    g = load_golden("edge_demo_u8.npz")
+    model = _u8_model(dev)
+    imgs = u8_images(2, seed=int(g["seed_input"]))
+    out = model.forward_u8(imgs.to(dev))
+    assert out.dtype == torch.uint8 and tuple(out.shape) == (2, 256, 256, 1)
+    flt = model(O.to_tensor_u8(imgs).to(dev))
+    assert torch.equal(out.cpu(), O.to_ubyte(flt.cpu()))
+    d = (out.cpu().to(torch.int16) - torch.from_numpy(g["output"]).to(torch.int16)).abs()
+    print(f"[parity] forward_u8 vs reference: max level diff {int(d.max())}, moved {float((d != 0).float().mean()):.4f}")
+    assert int(d.max()) <= 1 and float((d != 0).float().mean()) < 0.02
+    # grey 8-bit input (B, H, W, 1) == the same image repeated to RGB (model/SUNet.py:27-28)
+    grey = imgs[:1, :, :, :1].contiguous()
+    assert torch.equal(model.forward_u8(grey.to(dev)), model.forward_u8(grey.repeat(1, 1, 1, 3).to(dev)))
+
+
+def test_u8_pipeline_batches_and_ragged_tail(dev):
+    """Pinned double-buffered 8-bit pipeline: 5 images in batches of 2 (ragged last batch) == per-image calls."""
+    from oracle.make_golden_edges import u8_images
+    from sunet_tf_b200.demo import U8Pipeline
+    model = _u8_model(dev)
+    imgs = u8_images(5, seed=31)
+    got = U8Pipeline(model, batch=2).run(imgs.numpy())
+    ref = torch.cat([model.forward_u8(imgs[i:i + 1].to(dev)).cpu() for i in range(5)])
+    assert torch.equal(got, ref)
+    assert U8Pipeline(model, batch=2).run(imgs[:0]).shape == (0, 256, 256, 1)
+
+
+def test_forward_eval_vs_reference_golden(dev):
+    """train.py:437-448: logits / sigmoid / squared-error sums from the fused epilogue vs the reference golden."""
+    from oracle.make_golden_edges import validation_case
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    from sunet_tf_b200.validation import metrics_from_sums, validate
+    g = load_golden("edge_validation.npz")
+    model = load_sd(SUNet_model(DEFAULT_OPT), Wt.synth_state_dict(Wt.sunet_spec(), seed=int(g["seed_weights"]), style="stress"), dev)
+    target, inp, weight = validation_case(2, seed=int(g["seed_input"]))
+    logits, prob, sums = model.forward_eval(inp.to(dev), target.to(dev), weight=weight.to(dev))
+    assert torch.equal(logits, model(inp.to(dev)))                       # same kernels; the epilogue only adds the reductions
+    report("eval logits vs reference", logits, torch.from_numpy(g["logits"].astype(np.float32)), MODEL_TOL, relative=False)
+    assert (prob - torch.sigmoid(logits)).abs().max().item() < 1e-6
+    m = metrics_from_sums(sums)
+    # the device sums against the oracle reductions on the device logits (tight) and against the reference figures (model tolerance)
+    _, mo = O.validation_batch(logits.cpu(), target, weight)
+    for k in ("mse", "mse_weighted", "charbonnier"):
+        print(f"[parity] eval {k}: {m[k]:.8f} oracle-on-logits {mo[k]:.8f} reference {float(g[k]):.8f}")
+        assert abs(m[k] - mo[k]) < 1e-6 * max(1.0, abs(mo[k]))
+        assert abs(m[k] - float(g[k])) < 1e-3
+    assert float(sums[4]) == logits.numel()
+    # unit weights + single-channel target + the epoch driver
+    lum = (0.2989 * target[:, 0:1] + 0.5870 * target[:, 1:2] + 0.1140 * target[:, 2:3]).contiguous()
+    res, probs = validate(model, [(lum[:1].to(dev), inp[:1].to(dev)), (lum[1:].to(dev), inp[1:].to(dev))])
+    _, m0 = O.validation_batch(logits[:1].cpu(), lum[:1], None)
+    _, m1 = O.validation_batch(logits[1:].cpu(), lum[1:], None)
+    assert abs(res["val_mse"] - 0.5 * (m0["mse"] + m1["mse"])) < 1e-6 and abs(res["val_loss"] - 0.5 * (m0["charbonnier"] + m1["charbonnier"])) < 1e-6
+    assert abs(res["val_mse_weighted"] - res["val_mse"]) < 1e-9 and len(probs) == 2
+    with pytest.raises(RuntimeError):
+        model.forward_eval(inp.to(dev), target[:, :2].contiguous().to(dev))    # 2-channel target for a 1-channel model
+
+
+def test_forward_eval_chunked_batch(dev):
+    """Batches above max_chunk run in chunks inside one call: the sums accumulate across chunks."""
+    from oracle.make_golden_edges import validation_case
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    model = load_sd(SUNet_model(DEFAULT_OPT), Wt.synth_state_dict(Wt.sunet_spec(), seed=23, style="stress"), dev)
+    target, inp, weight = validation_case(3, seed=40)
+    l1, p1, s1 = model.forward_eval(inp.to(dev), target.to(dev), weight=weight.to(dev))
+    model.swin_unet.max_chunk = 2
+    model.swin_unet._workspaces.clear()
+    l2, p2, s2 = model.forward_eval(inp.to(dev), target.to(dev), weight=weight.to(dev))
+    assert torch.equal(l1, l2) and torch.equal(p1, p2)
+    assert ((s1 - s2).abs() <= 1e-9 * s1.abs()).all()
+    out8 = model.forward_u8((inp * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous().to(dev))
+    model.swin_unet.max_chunk = 64
+    model.swin_unet._workspaces.clear()
+    assert torch.equal(out8, model.forward_u8((inp * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous().to(dev)))
+
+
+def test_checkpoint_load_repacks_device_weights(dev, tmp_path):
+    """demo.py:33-43: load_checkpoint after .cuda() - the pre-packed fp16 / folded copies follow the new parameters."""
+    from collections import OrderedDict
+
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200 import checkpoint as ck
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    g = load_golden("sunet_model_stress.npz")
+    sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=int(g["seed_weights"]), style="stress")
+    path = str(tmp_path / "model_bestPSNR.pth")
+    torch.save({"epoch": 3, "state_dict": OrderedDict(("module." + k, v) for k, v in sd.items()), "optimizer": {}}, path)
+    model = SUNet_model(DEFAULT_OPT).to(dev).eval()
+    noisy2, _ = Wt.awgn_input(2, seed=int(g["seed_input"]))
+    before = model(noisy2.to(dev))                      # packs the random-init weights
+    ck.load_checkpoint(model, path)
+    after = model(noisy2.to(dev))
+    assert not torch.equal(before, after)
+    report("checkpoint-loaded model vs reference golden", after, torch.from_numpy(g["output"]), MODEL_TOL, relative=False)

@@ -112,3 +112,55 @@ def test_two_rank_gloo_tile_shard_and_reduce(tmp_path):
                         "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_OK" in r.stdout
+
+
+# ---------------------------------------------------------------- checkpoint format
+def test_checkpoint_round_trip_and_module_prefix(tmp_path):
+    from collections import OrderedDict
+
+    from sunet_tf_b200 import checkpoint as ck
+    spec = Wt.sunet_spec()
+    sd = Wt.synth_state_dict(spec, seed=3, style="init")
+    # the training script's format (train.py:520-535): {'epoch', 'state_dict', 'optimizer'}
+    path = ck.save_checkpoint(str(tmp_path), {"epoch": 7, "state_dict": sd, "optimizer": {"state": {}, "param_groups": []}}, "bestPSNR")
+    assert os.path.basename(path) == "model_epoch_7_bestPSNR.pth"
+    m = SUNet_model(DEFAULT_OPT)
+    ckpt = ck.load_checkpoint(m, path)
+    assert ckpt["epoch"] == 7 and ck.load_start_epoch(path) == 7
+    assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+    # nn.DataParallel checkpoints: every key carries `module.` (model_utils.py:32-36)
+    dp = OrderedDict(("module." + k, v * 2 if v.dtype == torch.float32 else v) for k, v in sd.items())
+    m2 = SUNet_model(DEFAULT_OPT)
+    ck.load_checkpoint(m2, {"epoch": 1, "state_dict": dp})
+    assert torch.equal(m2.state_dict()["swin_unet.norm.weight"], sd["swin_unet.norm.weight"] * 2)
+    m3 = SUNet_model(DEFAULT_OPT)
+    ck.load_checkpoint_multigpu(m3, {"epoch": 1, "state_dict": dp})
+    assert torch.equal(m3.state_dict()["swin_unet.output.weight"], sd["swin_unet.output.weight"] * 2)
+    # strictness is kept: a missing key or a foreign dict fails loudly
+    broken = OrderedDict(sd)
+    broken.pop("swin_unet.norm.weight")
+    with pytest.raises(RuntimeError):
+        ck.load_checkpoint(SUNet_model(DEFAULT_OPT), {"state_dict": broken})
+    with pytest.raises(RuntimeError):
+        ck.load_checkpoint(SUNet_model(DEFAULT_OPT), {"weights": sd})
+
+
+def test_validation_accumulator_matches_reference_aggregation():
+    from sunet_tf_b200.validation import ValidationAccumulator, metrics_from_sums
+    # two batches; sums = [sum se, sum se*w, sum w, sum charb*w, count]
+    s1 = torch.tensor([4.0, 6.0, 3.0, 9.0, 8.0], dtype=torch.float64)
+    s2 = torch.tensor([2.0, 0.0, 0.0, 0.0, 4.0], dtype=torch.float64)      # all-zero weights: clamp(min=1e-8) (train.py:192)
+    assert metrics_from_sums(s1) == {"mse": 0.5, "mse_weighted": 2.0, "charbonnier": 3.0}
+    acc = ValidationAccumulator()
+    acc.update(s1)
+    acc.update(s2)
+    r = acc.result()
+    assert r["batches"] == 2 and r["val_mse"] == 0.5 and r["val_mse_weighted"] == 1.0 and r["val_loss"] == 1.5
+
+
+def test_u8_and_eval_entry_points_reject_cpu_tensors():
+    m = SUNet_model(DEFAULT_OPT)
+    with pytest.raises(RuntimeError):
+        m.forward_u8(torch.zeros(1, 256, 256, 3, dtype=torch.uint8))
+    with pytest.raises(RuntimeError):
+        m.forward_eval(torch.zeros(1, 3, 256, 256), torch.zeros(1, 3, 256, 256))

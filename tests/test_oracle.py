@@ -94,3 +94,33 @@ def test_oracle_against_live_reference():
         ref = model(x)
     out = O.sunet_model_forward(sd, x, O.arch_from_yaml(cfg))
     assert (out - ref).abs().max().item() < 2e-5
+
+
+# ---------------------------------------------------------------- callers either side of the forward
+def test_demo_u8_edge_matches_reference_golden():
+    from oracle.make_golden_edges import u8_images, u8_state_dict
+    g = load_golden("edge_demo_u8.npz")
+    imgs = u8_images(2, seed=int(g["seed_input"]))
+    out = O.demo_restore_u8(u8_state_dict(int(g["seed_weights"])), imgs[:1]).numpy()
+    d = np.abs(out.astype(np.int16) - g["output"][:1].astype(np.int16))
+    # 2e-5 between the restatement and the reference moves a level only on a rounding boundary
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3
+    # quantisation rule itself: half-to-even rint of x*255 after the clamp
+    x = torch.tensor([-0.3, 0.0, 0.5 / 255, 1.5 / 255, 0.49999 / 255, 0.999, 1.0, 1.7]).reshape(1, 1, 1, -1)
+    assert O.to_ubyte(x).flatten().tolist() == [0, 0, 0, 2, 0, 255, 255, 255]
+    u = torch.arange(256, dtype=torch.uint8).reshape(1, 16, 16, 1)
+    assert torch.equal(O.to_ubyte(O.to_tensor_u8(u)), u)          # to_tensor -> img_as_ubyte is the identity on 8-bit data
+
+
+def test_validation_reductions_match_reference_golden():
+    from oracle.make_golden_edges import validation_case
+    g = load_golden("edge_validation.npz")
+    target, inp, weight = validation_case(2, seed=int(g["seed_input"]))
+    logits = torch.from_numpy(g["logits"].astype(np.float32))     # stored as fp16: 1e-4 on values of O(0.2)
+    prob, m = O.validation_batch(logits, target, weight)
+    assert abs(m["mse"] - float(g["mse"])) < 2e-4
+    assert abs(m["mse_weighted"] - float(g["mse_weighted"])) < 2e-4
+    assert abs(m["charbonnier"] - float(g["charbonnier"])) < 2e-4
+    assert (prob - torch.from_numpy(g["prob"].astype(np.float32))).abs().max().item() < 1e-3
+    _, m1 = O.validation_batch(logits, target, None)
+    assert abs(m1["charbonnier"] - float(g["charbonnier_unit"])) < 2e-4 and abs(m1["mse_weighted"] - m1["mse"]) < 1e-7
