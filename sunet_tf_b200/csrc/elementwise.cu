@@ -2,6 +2,9 @@
 // folded tail stencil, and the one-off weight pre-pack / fold helpers.  All loads/stores are 8- or 16-byte vectors,
 // consecutive lanes touch consecutive addresses.
 #include "elementwise.cuh"
+
+#include <stdlib.h>
+
 #include "error.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -263,11 +266,232 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const void* __restrict
   }
 }
 
-int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
-                      const float* gamma, const float* beta, int E, __half* out, cudaStream_t s) {
+// Tensor-core form of the same folded conv (used when the token grid splits into 8 x 16 tiles): the 6x6x3 patch of a token is
+// one row of an implicit [tokens][108 -> 112] fp16 matrix that is never built - the A fragments of mma.sync.m16n8k16 are read
+// straight from the staged fp16 image tile (the k order (c, u, v) keeps every (k, k+1) pair adjacent in an image row, so a
+// fragment register is one 32-bit shared load), B fragments by ldmatrix from the [E][112] fp16 weights, fp32 accumulators,
+// bias + LayerNorm in registers, rows staged per warp so that the 16 tokens of a warp leave as one contiguous 16*E*2-byte run.
+// CTA = 8 x 16 tokens (34 x 66 x 3 pixels); warp = one token row = one m16 tile.  Persistent over the tiles, 2 CTAs per SM.
+__device__ __forceinline__ void pe_ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void pe_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int PE_KP = 112;   // 108 taps padded to 7 k-steps
+constexpr int PE_WP = 120;   // weight row pitch in halves (240 B: the 8 rows of an ldmatrix land in 8 different 16-byte columns)
+constexpr int PE_IP = 72;    // image row pitch in floats
+constexpr int PE_IMG = 3 * 34 * PE_IP;   // floats per staged image tile
+static_assert(PE_WP == PATCH_EMBED_WPK_PITCH, "pack_patch_embed_f16 layout");
+template <int EPL> constexpr int pe_mma_smem() { return EPL * 32 * PE_WP * 2 + 2 * PE_IMG * 4 + 8 * 16 * (EPL * 32 + 8) * 2 + 3 * EPL * 32 * 4; }
+
+__device__ __forceinline__ void pe_cp_async4(uint32_t dst, const void* src, int src_bytes) {   // src_bytes 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// The pixels of one 8 x 16-token tile (3 x 34 x 66, zero outside the image) into a staging buffer.  fp32 input goes through cp.async
+// (in flight while the previous tile is computed); 8-bit input is loaded, scaled by 1/255 (TF.to_tensor, demo.py:71) and stored.
+template <bool U8>
+__device__ __forceinline__ void pe_stage_tile(const void* __restrict__ img_v, int img_chans, int Himg, int Wimg, int b, int y_base, int x_base,
+                                              float* buf, int tid) {
+  constexpr int NPIX = 3 * 34 * 66;
+  if (!U8) {
+    const float* img = static_cast<const float*>(img_v);
+    const uint32_t dst0 = smem_u32(buf);
+    for (int i = tid; i < NPIX; i += 256) {
+      const int c = i / (34 * 66), rem = i - c * (34 * 66), r = rem / 66, col = rem - r * 66;
+      const int y = y_base + r, x = x_base + col;
+      const bool in = y >= 0 && y < Himg && x >= 0 && x < Wimg;
+      const int cs = img_chans == 1 ? 0 : c;   // grey input is repeated to 3 channels (model/SUNet.py:27-28)
+      const float* src = in ? img + ((static_cast<int64_t>(b) * img_chans + cs) * Himg + y) * Wimg + x : img;
+      pe_cp_async4(dst0 + ((c * 34 + r) * PE_IP + col) * 4, src, in ? 4 : 0);
+    }
+  } else {
+    const uint8_t* img = static_cast<const uint8_t*>(img_v);
+    constexpr int BATCH = 9;
+#pragma unroll 1
+    for (int i0 = 0; i0 < NPIX; i0 += 256 * BATCH) {
+      float v[BATCH];
+      int dst[BATCH];
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        const int i = i0 + k * 256 + tid;
+        const int c = i / (34 * 66), rem = i - c * (34 * 66), r = rem / 66, col = rem - r * 66;
+        const int y = y_base + r, x = x_base + col;
+        v[k] = 0.f;
+        dst[k] = i < NPIX ? (c * 34 + r) * PE_IP + col : -1;
+        if (i < NPIX && y >= 0 && y < Himg && x >= 0 && x < Wimg) {
+          const int cs = img_chans == 1 ? 0 : c;
+          v[k] = static_cast<float>(__ldg(img + ((static_cast<int64_t>(b) * Himg + y) * Wimg + x) * img_chans + cs));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k)
+        if (dst[k] >= 0) buf[dst[k]] = v[k] / 255.f;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int EPL, bool U8>
+__global__ void __launch_bounds__(256, 2) patch_embed_mma_kernel(const void* __restrict__ img_v, int img_chans, int Himg, int Wimg,
+                                                                 const __half* __restrict__ wpk, const float* __restrict__ bfold,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 __half* __restrict__ out, int tiles_total) {
+  constexpr int E = EPL * 32, NT = E / 8, OP = E + 8;
+  extern __shared__ __align__(16) uint8_t pe_smem[];
+  __half* s_w = reinterpret_cast<__half*>(pe_smem);                 // [E][PE_WP]
+  float* s_img = reinterpret_cast<float*>(s_w + E * PE_WP);         // [2][3][34][PE_IP] fp32, double-buffered
+  __half* s_out = reinterpret_cast<__half*>(s_img + 2 * PE_IMG);    // [8][16][OP]
+  float* s_par = reinterpret_cast<float*>(s_out + 8 * 16 * OP);     // bias | gamma | beta
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  // parameters do not depend on the preceding kernel: staged before the dependency wait
+  {   // wpk is already [E][PE_WP] fp16 (pack_patch_embed_f16): a straight 16-byte copy, all loads in flight at once
+    constexpr int NV = E * PE_WP / 8, IT = (NV + 255) / 256;
+    uint4 w[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k)
+      if (tid + k * 256 < NV) w[k] = __ldg(reinterpret_cast<const uint4*>(wpk) + tid + k * 256);
+#pragma unroll
+    for (int k = 0; k < IT; ++k)
+      if (tid + k * 256 < NV) reinterpret_cast<uint4*>(s_w)[tid + k * 256] = w[k];
+  }
+  for (int i = tid; i < E; i += 256) {
+    s_par[i] = __ldg(bfold + i);
+    s_par[E + i] = __ldg(gamma + i);
+    s_par[2 * E + i] = __ldg(beta + i);
+  }
+  // this lane's pair offsets into the image tile: pair j = k / 2 = (c * 6 + u) * 3 + v / 2
+  int aoff[7][2];
+#pragma unroll
+  for (int ks = 0; ks < 7; ++ks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int j = 8 * ks + tq + 4 * h;
+      if (j >= 54) j = 0;   // zero weights there; any staged value will do
+      const int cu = j / 3, vp = j - 3 * cu, c = cu / 6, u = cu - 6 * c;
+      aoff[ks][h] = (c * 34 + u) * PE_IP + 2 * vp;
+    }
+  pdl_wait();
+  pdl_launch_dependents();
+  const int GW = Wimg >> 2, GH = Himg >> 2;
+  const int tiles_x = GW >> 4, tiles_y = GH >> 3, tiles_img = tiles_x * tiles_y;
+  const uint32_t w_addr = smem_u32(s_w) + (((lane >> 4) * 8 + (lane & 7)) * PE_WP + 8 * ((lane >> 3) & 1)) * 2;
+  int buf = 0;
+  if (static_cast<int>(blockIdx.x) < tiles_total) {
+    const int t = blockIdx.x, b = t / tiles_img, trem = t - b * tiles_img;
+    pe_stage_tile<U8>(img_v, img_chans, Himg, Wimg, b, 32 * (trem / tiles_x) - 1, 64 * (trem % tiles_x) - 1, s_img, tid);
+  }
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, buf ^= 1) {
+    const int b = tile / tiles_img;
+    const int trem = tile - b * tiles_img;
+    const int ty0 = (trem / tiles_x) * 8, tx0 = (trem % tiles_x) * 16;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // this tile's pixels have landed; every warp is done reading the other buffer
+    const int next = tile + gridDim.x;
+    if (next < tiles_total) {
+      const int nb = next / tiles_img, nrem = next - nb * tiles_img;
+      pe_stage_tile<U8>(img_v, img_chans, Himg, Wimg, nb, 32 * (nrem / tiles_x) - 1, 64 * (nrem % tiles_x) - 1, s_img + (buf ^ 1) * PE_IMG, tid);
+    }
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    const float* a_base = s_img + buf * PE_IMG + (4 * warp) * PE_IP + 4 * g;   // token (row warp, col g); col g + 8 is 32 floats further
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {
+      const float2 f0 = *reinterpret_cast<const float2*>(a_base + aoff[ks][0]);
+      const float2 f1 = *reinterpret_cast<const float2*>(a_base + 32 + aoff[ks][0]);
+      const float2 f2 = *reinterpret_cast<const float2*>(a_base + aoff[ks][1]);
+      const float2 f3 = *reinterpret_cast<const float2*>(a_base + 32 + aoff[ks][1]);
+      uint32_t a[4];
+      {
+        const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f1.x, f1.y);
+        const __half2 h2 = __floats2half2_rn(f2.x, f2.y), h3 = __floats2half2_rn(f3.x, f3.y);
+        a[0] = *reinterpret_cast<const uint32_t*>(&h0); a[1] = *reinterpret_cast<const uint32_t*>(&h1);
+        a[2] = *reinterpret_cast<const uint32_t*>(&h2); a[3] = *reinterpret_cast<const uint32_t*>(&h3);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; nt += 2) {
+        uint32_t bf[4];   // (nt, k lo), (nt, k hi), (nt + 1, k lo), (nt + 1, k hi)
+        pe_ldsm_x4(bf, w_addr + (nt * 8 * PE_WP + ks * 16) * 2);
+        pe_mma(acc[nt], a, bf[0], bf[1]);
+        pe_mma(acc[nt + 1], a, bf[2], bf[3]);
+      }
+    }
+    // bias + LayerNorm: token g lives in acc[.][0..1], token g + 8 in acc[.][2..3], a row is spread over the 4 lanes of a quad
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float2 bb = *reinterpret_cast<const float2*>(s_par + 8 * nt + 2 * tq);
+      acc[nt][0] += bb.x; acc[nt][1] += bb.y; acc[nt][2] += bb.x; acc[nt][3] += bb.y;
+      sum0 += acc[nt][0] + acc[nt][1];
+      sum1 += acc[nt][2] + acc[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float mean0 = sum0 / E, mean1 = sum1 / E;
+    float sq0 = 0.f, sq1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float d0 = acc[nt][0] - mean0, d1 = acc[nt][1] - mean0, d2 = acc[nt][2] - mean1, d3 = acc[nt][3] - mean1;
+      sq0 += d0 * d0 + d1 * d1;
+      sq1 += d2 * d2 + d3 * d3;
+    }
+    sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+    sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+    const float rstd0 = rsqrtf(sq0 / E + 1e-5f), rstd1 = rsqrtf(sq1 / E + 1e-5f);
+    __half* so = s_out + warp * 16 * OP;
+    __syncwarp();   // the previous tile's copy-out of this warp's staging rows is complete
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float2 ga = *reinterpret_cast<const float2*>(s_par + E + 8 * nt + 2 * tq);
+      const float2 be = *reinterpret_cast<const float2*>(s_par + 2 * E + 8 * nt + 2 * tq);
+      *reinterpret_cast<__half2*>(so + g * OP + 8 * nt + 2 * tq) =
+          __floats2half2_rn((acc[nt][0] - mean0) * rstd0 * ga.x + be.x, (acc[nt][1] - mean0) * rstd0 * ga.y + be.y);
+      *reinterpret_cast<__half2*>(so + (g + 8) * OP + 8 * nt + 2 * tq) =
+          __floats2half2_rn((acc[nt][2] - mean1) * rstd1 * ga.x + be.x, (acc[nt][3] - mean1) * rstd1 * ga.y + be.y);
+    }
+    __syncwarp();
+    // the warp's 16 tokens are consecutive in the token stream: one contiguous run of 16 * E halves
+    __half* orow = out + ((static_cast<int64_t>(b) * GH + ty0 + warp) * GW + tx0) * E;
+    constexpr int CPR = E / 8;   // 16-byte chunks per token
+    for (int idx = lane; idx < 16 * CPR; idx += 32) {
+      const int row = idx / CPR, ch = idx - row * CPR;
+      *reinterpret_cast<uint4*>(orow + idx * 8) = *reinterpret_cast<const uint4*>(so + row * OP + ch * 8);
+    }
+  }
+}
+
+int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Himg, int Wimg, const float* wfold, const __half* wpk,
+                      const float* bfold, const float* gamma, const float* beta, int E, __half* out, cudaStream_t s) {
   if (img_chans != 1 && img_chans != 3) return fail(SUNET_E_SHAPE, "patch embed: input must have 1 or 3 channels, got %d", img_chans);
   if (Himg % 32 || Wimg % 32) return fail(SUNET_E_SHAPE, "patch embed: image %dx%d must be a multiple of 32", Himg, Wimg);
   if (E % 32 || E > 128) return fail(SUNET_E_SHAPE, "patch embed: embed_dim %d must be a multiple of 32 and <= 128", E);
+  if (wpk != nullptr && Wimg % 64 == 0 && getenv("SUNET_PE_FFMA") == nullptr) {   // tensor-core form: 8 x 16-token tiles
+    const int tiles = B * (Himg / 32) * (Wimg / 64);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const unsigned grid = static_cast<unsigned>(tiles < 2 * sms ? tiles : 2 * sms);
+#define PE_MMA_T(EPL, U8)                                                                                                    \
+  {                                                                                                                          \
+    SUNET_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<EPL, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, pe_mma_smem<EPL>())); \
+    SUNET_CUDA(launch_pdl(patch_embed_mma_kernel<EPL, U8>, dim3(grid), dim3(256), pe_mma_smem<EPL>(), s, img, img_chans, Himg, Wimg,  \
+                          wpk, bfold, gamma, beta, out, tiles));                                                          \
+  }
+#define PE_MMA(EPL) if (img_fmt == IMG_U8_NHWC) PE_MMA_T(EPL, true) else PE_MMA_T(EPL, false)
+    switch (E / 32) {
+      case 1: PE_MMA(1); break;
+      case 2: PE_MMA(2); break;
+      case 3: PE_MMA(3); break;
+      default: PE_MMA(4); break;
+    }
+#undef PE_MMA
+#undef PE_MMA_T
+    SUNET_CHECK_LAUNCH();
+    return 0;
+  }
   const unsigned grid = static_cast<unsigned>(B) * (Himg / 32) * (Wimg / 32);
   const int smem = (3 * 34 * 35 + 108 * E) * 4;
 #define PE_LAUNCH_T(EPL, U8)                                                                                    \
@@ -592,6 +816,17 @@ __global__ void fold_patch_embed_kernel(const float* __restrict__ w1, const floa
 int fold_patch_embed(const float* w1, const float* b1, const float* w2, const float* b2, int Cin, int E, float* wfold, float* bfold,
                      cudaStream_t s) {
   fold_patch_embed_kernel<<<blocks_for(static_cast<int64_t>(Cin) * 36 * E, 128), 128, 0, s>>>(w1, b1, w2, b2, Cin, E, wfold, bfold);
+  SUNET_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void pack_patch_embed_f16_kernel(const float* __restrict__ wfold, __half* __restrict__ wpk, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * PE_WP) return;
+  const int e = i / PE_WP, k = i - e * PE_WP;
+  wpk[i] = __float2half_rn(k < 108 ? wfold[k * E + e] : 0.f);
+}
+int pack_patch_embed_f16(const float* wfold, __half* wpk, int E, cudaStream_t s) {
+  pack_patch_embed_f16_kernel<<<blocks_for(static_cast<int64_t>(E) * PE_WP, 128), 128, 0, s>>>(wfold, wpk, E);
   SUNET_CHECK_LAUNCH();
   return 0;
 }

@@ -22,8 +22,12 @@ int merge_gather_ln_f16(const __half* in, __half* out, const float* gamma, const
 // (B, Himg, Wimg, img_chans), scaled by 1/255 on load (TF.to_tensor, demo.py:71);
 // wfold: fp32 [108][E] (tap-major: k = c*36 + u*6 + v); out fp16 (B, Himg/4*Wimg/4, E).
 enum ImgFmt { IMG_F32_NCHW = 0, IMG_U8_NHWC = 1 };
-int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Himg, int Wimg, const float* wfold, const float* bfold,
-                      const float* gamma, const float* beta, int E, __half* out, cudaStream_t s);
+// wpk (optional): the same weights as fp16 [E][PATCH_EMBED_WPK_PITCH] (pack_patch_embed_f16) for the tensor-core form of the kernel,
+// taken when the token grid splits into 8 x 16 tiles (Wimg % 64 == 0); otherwise the fp32 FFMA form runs.
+constexpr int PATCH_EMBED_WPK_PITCH = 120;
+int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Himg, int Wimg, const float* wfold, const __half* wpk,
+                      const float* bfold, const float* gamma, const float* beta, int E, __half* out, cudaStream_t s);
+int pack_patch_embed_f16(const float* wfold, __half* wpk, int E, cudaStream_t s);
 
 // im2col for a stand-alone PatchEmbed (conv k = stride = P): A[m][c*P*P + ky*P + kx] fp16
 int im2col_patch(const float* img, int B, int Cin, int Himg, int Wimg, int P, __half* out, cudaStream_t s);

@@ -515,7 +515,12 @@ static int pick_block_n(int N, int64_t m_tiles, int K) {
   // fall back to the widest tile <= 128 to spread the small-M stages over more SMs.
   const int64_t want = (6 * static_cast<int64_t>(num_sms())) / 10;
   for (int c : cand)
-    if (N % c == 0 && m_tiles * (N / c) >= want) return c;
+    if (N % c == 0 && m_tiles * (N / c) >= want) {
+      // a single partial wave of 256-wide tiles: 192-wide tiles that still fit one wave finish sooner (stage-3 proj / fc2,
+      // M = 4096, N = 768: 96 tiles -> 128 tiles, 31.0 -> 29.1 us; tools/gemm_stage_sweep.sh)
+      if (c == 256 && N % 192 == 0 && m_tiles * (N / 256) < num_sms() && m_tiles * (N / 192) <= num_sms()) return 192;
+      return c;
+    }
   (void)K;
   for (int c : cand)
     if (N % c == 0 && c <= 128) return c;
@@ -544,6 +549,10 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   const int stage_bytes = A_TILE_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2;
   int stages = (GEMM_MAX_DYN_SMEM - 1024 - EPI_WARPS * 4096) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (const char* cap = getenv("SUNET_GEMM_STAGES")) {   // pipeline-depth experiments (tools/gemm_stage_sweep.sh)
+    const int v = atoi(cap);
+    if (v >= 1 && v < stages) stages = v;
+  }
   if (stages < 1) stages = 1;
   SUNET_TRY(make_tmap_2d_f16(&op->tmA0, a.A0, a.K0, a.M, a.lda0, BLOCK_M));
   if (a.K1 > 0) SUNET_TRY(make_tmap_2d_f16(&op->tmA1, a.A1, a.K1, a.M, a.lda1, BLOCK_M));

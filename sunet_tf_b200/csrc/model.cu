@@ -436,6 +436,7 @@ struct ModelPack {
   int img = 0, patch = 0, in_chans = 0, out_chans = 0, E = 0, G = 0;
   int depths[4] = {0, 0, 0, 0}, heads[4] = {0, 0, 0, 0};
   float *wfold = nullptr, *bfold = nullptr, *pe_g = nullptr, *pe_b = nullptr;
+  __half* wpk = nullptr;   // wfold as fp16 [E][PATCH_EMBED_WPK_PITCH] for the tensor-core patch-embed kernel
   std::vector<BlockPack> enc[4], dec[4];
   MergePack merge[3];
   float *norm_g = nullptr, *norm_b = nullptr, *normup_g = nullptr, *normup_b = nullptr;
@@ -475,6 +476,8 @@ static int pack_model(ModelHandle* h, const Params& P, const int64_t* ia, int ni
   SUNET_TRY(ar.alloc_t(&m.wfold, static_cast<size_t>(108) * E));
   SUNET_TRY(ar.alloc_t(&m.bfold, E));
   SUNET_TRY(fold_patch_embed(w1, b1, w2, b2, 3, E, m.wfold, m.bfold, s));
+  SUNET_TRY(ar.alloc_t(&m.wpk, static_cast<size_t>(E) * PATCH_EMBED_WPK_PITCH));
+  SUNET_TRY(pack_patch_embed_f16(m.wfold, m.wpk, E, s));
   if (P.has("patch_embed.norm.weight")) {
     SUNET_TRY(copy_vec(ar, P, "patch_embed.norm.weight", E, &m.pe_g, s));
     SUNET_TRY(copy_vec(ar, P, "patch_embed.norm.bias", E, &m.pe_b, s));
@@ -524,7 +527,7 @@ static int model_forward_chunk(const ModelPack& m, Ctx& c, const void* x, int in
   SUNET_TRY(c.sc.take_t(&Xb, S));
   SUNET_TRY(c.sc.take_t(&T, S));
   RUN(c, K_PATCH_EMBED, 2.0 * 108 * S, (c.in_fmt == IMG_U8_NHWC ? 1.0 : 4.0) * Bc * in_chans * m.img * m.img + 2.0 * S,
-      patch_embed_fused(x, c.in_fmt, in_chans, Bc, m.img, m.img, m.wfold, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
+      patch_embed_fused(x, c.in_fmt, in_chans, Bc, m.img, m.img, m.wfold, m.wpk, m.bfold, m.pe_g, m.pe_b, E, skip[0], c.stream));  // :749, :708
   // encoder + bottleneck (:714-716).  x_downsample[i] = input of stage i stays untouched in skip[i].
   const __half* cur = skip[0];
   for (int i = 0; i < 4; ++i) {
