@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libsunet_b200.so")
-SOURCES = ["error.cu", "gemm_tcgen05.cu", "attn_core.cu", "attn_fused.cu", "mlp_fused.cu", "tail_fused.cu", "elementwise.cu", "tiles.cu", "model.cu"]
+SOURCES = ["error.cu", "gemm_tcgen05.cu", "attn_core.cu", "attn_fused.cu", "mlp_fused.cu", "proj_ln.cu", "tail_fused.cu", "elementwise.cu", "tiles.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               ] + os.environ.get("SUNET_NVCC_EXTRA", "").split()   # e.g. -DSUNET_KERNEL_TIMING=1 for the phase-cycle counters
 

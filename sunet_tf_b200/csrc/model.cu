@@ -17,6 +17,7 @@
 #include "error.h"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
+#include "proj_ln.cuh"
 #include "tail_fused.cuh"
 
 namespace sunet {
@@ -285,6 +286,15 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     }
     if (use_mf && mf.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one kernel
       RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim, mlp_proj_fused_launch(mf, O, x_in, x_out, M, c.stream));
+      return 0;
+    }
+    if (!use_mf && proj_ln_supported(dim) && getenv("SUNET_NO_PROJ_LN") == nullptr) {
+      // :136 proj, :261 shortcut, :262 norm2 in one kernel (whole rows per CTA); then the two MLP GEMMs
+      ProjLnPack pl;
+      pl.w = attn.proj.w; pl.bias = attn.proj.b; pl.gamma = g2; pl.beta = b2; pl.C = dim;
+      RUN(c, K_GEMM, 2.0 * M * dim * dim, 8.0 * M * dim + 2.0 * dim * dim, proj_ln_launch(pl, O, x_in, x_out, T, M, c.stream));
+      SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
+      SUNET_TRY(run_linear(c, mlp.fc2, Hd, 4 * dim, M, x_out, dim, ACT_NONE, nullptr, x_out, dim));  // :22, :262
       return 0;
     }
     if (attn.proj_res.w) {   // :136, :261 - the shortcut rides the TMA ring as a second K segment against an identity block
