@@ -294,7 +294,12 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       pl.w = attn.proj.w; pl.bias = attn.proj.b; pl.gamma = g2; pl.beta = b2; pl.C = dim;
       RUN(c, K_GEMM, 2.0 * M * dim * dim, 8.0 * M * dim + 2.0 * dim * dim, proj_ln_launch(pl, O, x_in, x_out, T, M, c.stream));
       SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
-      SUNET_TRY(run_linear(c, mlp.fc2, Hd, 4 * dim, M, x_out, dim, ACT_NONE, nullptr, x_out, dim));  // :22, :262
+      if (row_gemm_supported(dim, 4 * dim) && getenv("SUNET_NO_ROW_GEMM") == nullptr) {
+        RUN(c, K_GEMM, 8.0 * M * dim * dim, 12.0 * M * dim + 8.0 * dim * dim,
+            row_gemm_residual_launch(mlp.fc2.w, mlp.fc2.b, dim, 4 * dim, Hd, x_out, x_out, M, c.stream));   // :22, :262
+      } else {
+        SUNET_TRY(run_linear(c, mlp.fc2, Hd, 4 * dim, M, x_out, dim, ACT_NONE, nullptr, x_out, dim));  // :22, :262
+      }
       return 0;
     }
     if (attn.proj_res.w) {   // :136, :261 - the shortcut rides the TMA ring as a second K segment against an identity block

@@ -22,21 +22,24 @@ constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int STG_BYTES = 2048;   // per warp: 32 rows x 32 fp16
 
-template <int C>
+template <int C, int KTOT>
 struct Cfg {
   static constexpr int NH = C / 2;                 // columns per MMA instruction
   static constexpr int CQ = C / 4;                 // columns per epilogue column-quarter
-  static constexpr int KB = C / BK;                // k-blocks
+  static constexpr int KB = KTOT / BK;             // k-blocks
   static constexpr int W_BYTES = C * BK * 2;       // one weight k-block
   static constexpr int STAGE = A_BYTES + W_BYTES;
-  static constexpr int STAGES = (226 * 1024 - 1024 - EPI_WARPS * STG_BYTES - 2 * 4 * TILE_M * 4) / STAGE;
-  static constexpr int OFF_STG = STAGES * STAGE;
-  static constexpr int OFF_RED = OFF_STG + EPI_WARPS * STG_BYTES;   // float [2][4][128]
+  // The epilogue's staging tiles alias ring stage 0: the epilogue of a tile starts after its last MMA has read the ring, and the
+  // producer does not refill the ring for the next tile before the epilogue has handed the accumulator back (acc_empty).  With
+  // one tile per CTA (M <= 128 * SMs, every whole-model call) nothing is lost; more tiles per CTA serialise load and epilogue.
+  static constexpr int STAGES = (226 * 1024 - 1024 - 2 * 4 * TILE_M * 4) / STAGE;
+  static constexpr int OFF_STG = 0;
+  static constexpr int OFF_RED = STAGES * STAGE;   // float [2][4][128]
   static constexpr int SMEM = OFF_RED + 2 * 4 * TILE_M * 4 + 1024;
   static constexpr uint32_t TMEM_COLS = C <= 128 ? 128 : (C <= 256 ? 256 : 512);
-  static_assert(C % BK == 0 && CQ % 32 == 0 && NH % 16 == 0 && NH <= 256 && C <= 512, "unsupported width");
+  static_assert(KTOT % BK == 0 && CQ % 32 == 0 && NH % 16 == 0 && NH <= 256 && C <= 512, "unsupported width");
   static_assert((NH * 128) % 1024 == 0, "second weight half must start on a swizzle atom");
-  static_assert(STAGES >= 2, "ring too shallow");
+  static_assert(STAGES >= 2 && EPI_WARPS * STG_BYTES <= STAGE, "ring too shallow / staging must fit ring stage 0");
 };
 
 struct Params {
@@ -52,10 +55,10 @@ struct Params {
 
 __device__ __forceinline__ uint32_t stg_off(int row, int ch) { return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)); }
 
-template <int C>
+template <int C, int KTOT, bool LN>
 __global__ void __launch_bounds__(THREADS, 1)
     proj_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
-  using K = Cfg<C>;
+  using K = Cfg<C, KTOT>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[K::STAGES], empty_bar[K::STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_smem;
@@ -84,9 +87,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      uint32_t ph = 0, local = 0;
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
         const int m0 = static_cast<int>(tile * TILE_M);
+        mbar_wait(&acc_empty, (local & 1) ^ 1);   // the previous tile's epilogue no longer uses the staging tiles inside stage 0
         for (int kb = 0; kb < K::KB; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * K::STAGE;
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
           sts128(stg + stg_off(lane, ch), o);
         }
-        tmem_st32(taddr + cc, v);   // X1 (rounded) parked over the accumulator for the two statistics passes
+        if (LN) tmem_st32(taddr + cc, v);   // X1 (rounded) parked over the accumulator for the two statistics passes
         __syncwarp();
         __half* xbase = p.X1 + m_base * C + col0 + cc;
 #pragma unroll
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         __syncwarp();
       }
+      if (LN) {
       tmem_st_wait();
       // ---- row statistics across the four column-quarter warps of this lane quarter (two-pass: mean, then centred squares)
       red[quarter * TILE_M + row] = sum;
@@ -241,7 +246,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         __syncwarp();
       }
-      // all TMEM reads of this warp are complete: hand the accumulator back to the MMA warp
+      }   // LN
+      // all TMEM reads of this warp are complete: hand the accumulator (and the staging tiles inside ring stage 0, which the
+      // next tile's TMA loads overwrite through the async proxy) back
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
@@ -257,17 +265,17 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-template <int C>
+template <int C, int KTOT, bool LN>
 int launch_t(const ProjLnPack& pk, const __half* A, const __half* R, __half* X1, __half* T, int64_t M, cudaStream_t stream) {
-  using K = Cfg<C>;
+  using K = Cfg<C, KTOT>;
   static bool configured = false;
   if (!configured) {
-    SUNET_CUDA(cudaFuncSetAttribute(proj_ln_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    SUNET_CUDA(cudaFuncSetAttribute((proj_ln_kernel<C, KTOT, LN>), cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     configured = true;
   }
   alignas(64) CUtensorMap tmA, tmW;
-  SUNET_TRY(make_tmap_2d_f16(&tmA, A, C, M, C, TILE_M));
-  SUNET_TRY(make_tmap_2d_f16(&tmW, pk.w, C, C, C, K::NH));
+  SUNET_TRY(make_tmap_2d_f16(&tmA, A, KTOT, M, KTOT, TILE_M));
+  SUNET_TRY(make_tmap_2d_f16(&tmW, pk.w, KTOT, C, KTOT, K::NH));
   Params p;
   p.R = R; p.X1 = X1; p.T = T; p.bias = pk.bias; p.gamma = pk.gamma; p.beta = pk.beta; p.M = M;
   p.tiles = (M + TILE_M - 1) / TILE_M;
@@ -275,25 +283,35 @@ int launch_t(const ProjLnPack& pk, const __half* A, const __half* R, __half* X1,
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const unsigned grid = static_cast<unsigned>(p.tiles < sms ? p.tiles : sms);
-  SUNET_CUDA(launch_pdl(proj_ln_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmA, tmW, p));
+  SUNET_CUDA(launch_pdl(proj_ln_kernel<C, KTOT, LN>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmA, tmW, p));
   SUNET_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace
 
-bool proj_ln_supported(int C) { return C == 384 || C == 256; }
+bool proj_ln_supported(int C) { return C == 384; }
+bool row_gemm_supported(int C, int Kdim) { return C == 384 && Kdim == 1536; }
 
 int proj_ln_launch(const ProjLnPack& p, const __half* A, const __half* R, __half* X1, __half* T, int64_t M, cudaStream_t stream) {
   if (M <= 0) return 0;
   if (M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "proj_ln: M too large for 32-bit TMA coordinates");
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(X1) | reinterpret_cast<uintptr_t>(T)) & 15)
     return fail(SUNET_E_ALIGN, "proj_ln: operands must be 16-byte aligned");
-  switch (p.C) {
-    case 384: return launch_t<384>(p, A, R, X1, T, M, stream);
-    case 256: return launch_t<256>(p, A, R, X1, T, M, stream);
-    default: return fail(SUNET_E_SHAPE, "proj_ln: C=%d not instantiated", p.C);
-  }
+  if (p.C == 384 && p.gamma != nullptr && p.beta != nullptr && T != nullptr) return launch_t<384, 384, true>(p, A, R, X1, T, M, stream);
+  return fail(SUNET_E_SHAPE, "proj_ln: C=%d not instantiated", p.C);
+}
+
+int row_gemm_residual_launch(const __half* W, const float* bias, int C, int Kdim, const __half* A, const __half* R, __half* X,
+                             int64_t M, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "row_gemm: M too large for 32-bit TMA coordinates");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(X)) & 15)
+    return fail(SUNET_E_ALIGN, "row_gemm: operands must be 16-byte aligned");
+  ProjLnPack p;
+  p.w = W; p.bias = bias; p.C = C;
+  if (C == 384 && Kdim == 1536) return launch_t<384, 1536, false>(p, A, R, X, nullptr, M, stream);
+  return fail(SUNET_E_SHAPE, "row_gemm: C=%d K=%d not instantiated", C, Kdim);
 }
 
 }  // namespace sunet

@@ -19,6 +19,11 @@ struct ProjLnPack {
 };
 
 bool proj_ln_supported(int C);
+// Same pipeline without the LayerNorm half: X = A[M][Kdim] * W[C][Kdim]^T + bias + R with whole rows per CTA (mlp.fc2 + second
+// residual at C = 384: one wave of 128 full-row tiles instead of two partial waves of 128 x 192 tiles).
+bool row_gemm_supported(int C, int Kdim);
+int row_gemm_residual_launch(const __half* W, const float* bias, int C, int Kdim, const __half* A, const __half* R, __half* X,
+                             int64_t M, cudaStream_t stream);
 int proj_ln_launch(const ProjLnPack& p, const __half* A, const __half* R, __half* X1, __half* T, int64_t M, cudaStream_t stream);
 
 }  // namespace sunet

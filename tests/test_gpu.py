@@ -184,6 +184,26 @@ def test_fused_block_kernels_agree_with_the_unfused_path(dev, dim, grid, batch, 
     report(f"fused-vs-plain dim{dim} grid{grid} shift{shift}", y_fused, y_plain.cpu(), MODULE_TOL)
 
 
+@pytest.mark.parametrize("batch", [1, 80])
+def test_proj_ln_kernel_agrees_with_separate_kernels(dev, batch, monkeypatch):
+    """C = 384: proj + shortcut + norm2 as one full-row tcgen05 kernel (proj_ln.cu) against proj GEMM + LayerNorm kernel
+    (SUNET_NO_PROJ_LN) and the oracle.  batch 80 = 160 row tiles on 148 CTAs: the multi-tile path, where the epilogue staging
+    that aliases ring stage 0 is handed back before the next tile's loads; the block writes in place over its input."""
+    from sunet_tf_b200 import SwinTransformerBlock
+    dim, grid, shift = 384, 16, 4
+    sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, shift), seed=1234, style="stress")
+    x = module_input((batch, grid * grid, dim), seed=1235)
+    fused = load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+    y_fused = fused(x.to(dev))
+    monkeypatch.setenv("SUNET_NO_PROJ_LN", "1")
+    plain = load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+    y_plain = plain(x.to(dev))
+    nref = min(batch, 4)
+    ref = O.swin_block(sd, "", x[:nref], grid, grid, 8, shift, 8)
+    report(f"proj_ln-vs-oracle batch{batch}", y_fused[:nref], ref, MODULE_TOL)
+    report(f"proj_ln-vs-separate batch{batch}", y_fused, y_plain.cpu(), MODULE_TOL)
+
+
 def test_swin_block_default_scale_and_rect_grid(dev):
     """qk_scale=None -> head_dim**-0.5 (SUNet_detail.py:80); rectangular token grid"""
     from sunet_tf_b200 import SwinTransformerBlock
