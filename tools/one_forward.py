@@ -1,7 +1,7 @@
 """Two SUNet forwards of the bench workload (B = 64) and nothing else from this library: the target of the ncu launch-list capture.
 
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-      -k regex:'gemm_tn|attn_|mlp_|layernorm|patch_embed|upsample_combine|tail_stencil' --launch-skip N --launch-count N --csv \
+      -k regex:'gemm_tn|proj_ln|attn_|mlp_|layernorm|patch_embed|upsample_combine|tail_' --launch-skip N --launch-count N --csv \
       --log-file gpurun_out/launches.csv python tools/one_forward.py          (N = launches per forward, printed by this script)
 """
 import os
