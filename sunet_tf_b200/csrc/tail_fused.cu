@@ -31,7 +31,8 @@ constexpr int NT = 16;                  // folded tap maps per sub-pixel (9 taps
 constexpr int KBYTES = TILE_M * 128;    // one [128 rows][64 fp16] SW128 k-block
 constexpr int W1KB = E * 128;           // one [96 rows][64] k-block of a sub-pixel's weights
 constexpr int EPI_WARPS = 16;
-constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_WARPS * 32 + 32;   // TMA producer, fc1 issuer, 16 epilogue warps, fc2 issuer
+constexpr int FC2_WARP = 2 + EPI_WARPS;
 constexpr int R1 = 4;                   // weight ring stages
 constexpr int OFF_X = 0;                // 2 token-tile buffers x 2 k-blocks
 constexpr int OFF_HS = OFF_X + 2 * 2 * KBYTES;
@@ -57,6 +58,7 @@ struct Params {
   float* out;           // [M * 16][16] fp32 == [M][256]
   int64_t M;
   int64_t tiles;
+  int split;            // 1: fc2 MMAs are issued by their own thread (warp FC2_WARP), 0: interleaved with fc1 by warp 1
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -170,6 +172,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_commit(&hs_empty[hb]);
         if (j == SUB - 1) tc_commit(&y_full);
       };
+      if (p.split) {
+        // fc1 only: runs ahead as far as the two H buffers allow; fc2 has its own issuing thread, so neither waits behind the
+        // other's barrier round trips (an mbarrier wait costs ~200 clk even on a completed phase)
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+          const int xb = lt & 1;
+          mbar_wait(&x_full[xb], (lt >> 1) & 1);
+          tc_fence_after();
+          for (int j = 0; j < SUB; ++j) fc1(xb, g + j, j == SUB - 1);
+          g += SUB;
+        }
+      } else {
       mbar_wait(&gp_full, 0);
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
         const int xb = lt & 1;
@@ -181,6 +194,34 @@ __global__ void __launch_bounds__(THREADS, 1)
           if (j + 2 < SUB) fc1(xb, g + j + 2, j + 2 == SUB - 1);
           if (j == 0) { mbar_wait(&y_empty, (lt & 1) ^ 1); tc_fence_after(); }   // the previous tile's Q has been drained
           fc2(g + j, j);
+        }
+        g += SUB;
+      }
+      }
+    }
+  } else if (warp == FC2_WARP) {
+    // ------------------------------------------------------------------ fc2 issuer (split mode)
+    if (lane == 0 && p.split) {
+      const uint32_t idesc2 = umma_idesc_f16(TILE_M, NT);
+      uint32_t g = 0;
+      int lt = 0;
+      mbar_wait(&gp_full, 0);
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        for (int j = 0; j < SUB; ++j) {
+          if (j == 0) { mbar_wait(&y_empty, (lt & 1) ^ 1); tc_fence_after(); }   // the previous tile's Q has been drained
+          const uint32_t gg = g + j, hb = gg & 1;
+          mbar_wait(&g_done[hb], (gg >> 1) & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + TM_Y + j * NT;
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_HS + (hb * 2 + kb) * KBYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_GP + kb * NT * 128));
+            const int ksteps = kb == 1 ? 2 : 4;
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&hs_empty[hb]);
+          if (j == SUB - 1) tc_commit(&y_full);
         }
         g += SUB;
       }
@@ -321,6 +362,7 @@ int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p,
   prm.out = out;
   prm.M = M;
   prm.tiles = (M + TILE_M - 1) / TILE_M;
+  prm.split = getenv("SUNET_TAIL_NO_SPLIT") == nullptr;   // measured: 295 -> 224 us (tools/ab_split.sh)
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   SUNET_CUDA(launch_pdl(tail_up_fused_kernel, dim3(grid), dim3(THREADS), SMEM, stream, tmX, tmW1, tmGp, prm));
 #if SUNET_KERNEL_TIMING
