@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
       mbar_init(&h_full[i], 1);
-      mbar_init(&h_empty[i], EPI_WARPS);
-      mbar_init(&g_done[i], EPI_WARPS);
+      mbar_init(&h_empty[i], EPI_WARPS / 2);   // the epilogue warps work in two groups of 8, group b on the chunks of buffer b
+      mbar_init(&g_done[i], EPI_WARPS / 2);
       mbar_init(&hs_empty[i], 1);
     }
     mbar_init(&gp_full, 1);
@@ -242,25 +242,30 @@ __global__ void __launch_bounds__(THREADS, 1)
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tq0 = clock64();
 #endif
+    // Ping-pong: warps of column quarters 0-1 take the even sub-pixels (H / G buffer 0), quarters 2-3 the odd ones (buffer 1), each
+    // warp 48 of the 96 columns.  The per-chunk chain (accumulator ready -> TMEM load -> PReLU -> smem -> fence -> arrive) of one
+    // group runs under the other group's, instead of all 16 warps waiting through the same round trips together.
+    const uint32_t grp = static_cast<uint32_t>(quarter >> 1), half = static_cast<uint32_t>(quarter & 1);
     for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-      for (int j = 0; j < SUB; ++j, ++g) {
-        const uint32_t hb = g & 1, ph = (g >> 1) & 1;
+      for (int j = static_cast<int>(grp); j < SUB; j += 2) {
+        const uint32_t gg = g + static_cast<uint32_t>(j);
+        const uint32_t hb = grp, ph = (gg >> 1) & 1;   // g is a multiple of 16: gg & 1 == grp
         TF_T(7);
         mbar_wait_hint(&h_full[hb], ph, h_ok);
         tc_fence_after();
         TF_T(0);
-        uint32_t v[24];
+        uint32_t v[48];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) tmem_ld8(tmem_base + lane_off + TM_H + hb * 128 + quarter * 24 + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[i * 8]));
+        for (int i = 0; i < 6; ++i) tmem_ld8(tmem_base + lane_off + TM_H + hb * 128 + half * 48 + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[i * 8]));
         const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);
         tmem_ld_wait();
         TF_T(1);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&h_empty[hb]);   // the accumulator may be overwritten by the fc1 of sub-pixel g + 2
-        uint4 o[3];
+        if (lane == 0) mbar_arrive(&h_empty[hb]);   // the accumulator may be overwritten by the fc1 of sub-pixel gg + 2
+        uint4 o[6];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 6; ++i) {
           __half2* o2 = reinterpret_cast<__half2*>(&o[i]);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -271,10 +276,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         TF_T(2);
         mbar_wait_hint(&hs_empty[hb], ph ^ 1, hs_ok);
         TF_T(3);
-        h_ok = mbar_test(&h_full[hb ^ 1], ((g + 1) >> 1) & 1);
+        h_ok = mbar_test(&h_full[hb], ph ^ 1);   // this group's next sub-pixel (same buffer, next phase)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int gi = quarter * 3 + i;   // 16-byte chunk of the 96-wide row: k-block gi >> 3, chunk gi & 7
+        for (int i = 0; i < 6; ++i) {
+          const int gi = static_cast<int>(half) * 6 + i;   // 16-byte chunk of the 96-wide row: k-block gi >> 3, chunk gi & 7
           sts128(smem_u32(smem + OFF_HS + (hb * 2 + (gi >> 3)) * KBYTES) + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4), o[i]);
         }
         fence_proxy_async_smem();
@@ -283,6 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (lane == 0) mbar_arrive(&g_done[hb]);
         TF_T(4);
       }
+      g += SUB;
       // ---- output: Q tile columns [64 quarter, +64) of this row = sub-pixels 4 quarter .. 4 quarter + 3, 16 taps each
       mbar_wait(&y_full, lt & 1);
       tc_fence_after();
