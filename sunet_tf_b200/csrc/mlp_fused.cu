@@ -36,6 +36,14 @@ constexpr int KBYTES = TILE_M * 128;    // one [128 rows][64 fp16] SW128 k-block
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
+// mlp_proj_fused with two MMA-issuing threads: warp 1 issues fc1, a 19th warp proj + fc2, so neither sits behind the other's
+// barrier round trips (-DSUNET_MLP_SPLIT=0 restores the single issuer).  Measured (tools/ab_mlp_split.sh): 3.30 -> 3.21 ms over the
+// 32 launches of a forward; an idle 19th warp alone costs +2.6%, the split itself gains 6%.
+#ifndef SUNET_MLP_SPLIT
+#define SUNET_MLP_SPLIT 1
+#endif
+constexpr int PTHREADS = SUNET_MLP_SPLIT ? THREADS + 32 : THREADS;
+constexpr int FC2_WARP = 2 + EPI_WARPS;
 
 template <int C>
 struct Cfg {
@@ -407,7 +415,7 @@ struct ProjParams {
 };
 
 template <int C>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(PTHREADS, 1)
     mlp_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWp,
                           const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const ProjParams p) {
   using K = Cfg<C>;
@@ -448,10 +456,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
   {
     float* hb = reinterpret_cast<float*>(smem + K::OFF_HC);
-    for (int i = threadIdx.x; i < K::HID; i += THREADS) hb[i] = __ldg(p.hbias + i);
+    for (int i = threadIdx.x; i < K::HID; i += PTHREADS) hb[i] = __ldg(p.hbias + i);
     float* b2s = reinterpret_cast<float*>(smem + K::OFF_B2);
     float* bps = reinterpret_cast<float*>(smem + OFF_BP);
-    for (int i = threadIdx.x; i < C; i += THREADS) { b2s[i] = __ldg(p.b2 + i); bps[i] = __ldg(p.bp + i); }
+    for (int i = threadIdx.x; i < C; i += PTHREADS) { b2s[i] = __ldg(p.b2 + i); bps[i] = __ldg(p.bp + i); }
   }
   tc_fence_before();
   __syncthreads();
@@ -509,6 +517,116 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
     }
+#if SUNET_MLP_SPLIT
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ fc1 issuer (the r1 ring is consumed only here)
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_f16(TILE_M, NC);
+      uint32_t i1 = 0, g = 0;
+      int lt = 0;
+      uint32_t r1_ok = mbar_test(&r1_full[0], 0);
+      auto r1_acquire = [&]() -> int {
+        const int s = i1 % K::R1;
+        mbar_wait_hint(&r1_full[s], (i1 / K::R1) & 1, r1_ok);
+        ++i1;
+        r1_ok = mbar_test(&r1_full[i1 % K::R1], (i1 / K::R1) & 1);
+        tc_fence_after();
+        return s;
+      };
+      auto fc1 = [&](int xb, uint32_t gg, int j, bool last) {   // H[gg & 1] = x1 * W1h_j^T   (gg: global chunk index)
+        const uint32_t hb = gg & 1, use = gg >> 1;
+        if (use > 0) mbar_wait(&h_empty[hb], (use - 1) & 1);   // the epilogue has loaded the previous contents of this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + K::TM_H + hb * 128;
+        for (int kb = 0; kb < K::KB1; ++kb) {
+          const int s = r1_acquire();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
+          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r1_empty[s]);
+        }
+        tc_commit(&h_full[hb]);
+        if (last) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
+        (void)j;
+      };
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
+        const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
+        mbar_wait(&x1_ready[xb], xuse & 1);
+        tc_fence_after();
+        for (int j = 0; j < K::NCH; ++j) fc1(xb, g + j, j, j == K::NCH - 1);   // runs ahead as far as the two H accumulators allow
+        g += K::NCH;
+      }
+    }
+  } else if (warp == FC2_WARP) {
+    // ------------------------------------------------------------------ proj + fc2 issuer (the r2 ring is consumed only here, in the
+    // producer's order: [Wp] then per chunk the two W2 k-blocks, the next tile's Wp before the last chunk when EARLY)
+    if (lane == 0) {
+      const uint32_t idesc2 = umma_idesc_f16(TILE_M, C);
+      uint32_t i2 = 0, g = 0;
+      int lt = 0;
+      uint32_t r2_ok = mbar_test(&r2_full[0], 0);
+      auto r2_acquire = [&]() -> int {
+        const int s = i2 % K::R2;
+        mbar_wait_hint(&r2_full[s], (i2 / K::R2) & 1, r2_ok);
+        ++i2;
+        r2_ok = mbar_test(&r2_full[i2 % K::R2], (i2 / K::R2) & 1);
+        tc_fence_after();
+        return s;
+      };
+      auto fc2 = [&](int yb, uint32_t gg, int j) {   // Y[yb] (+)= G_j * W2_j^T
+        const uint32_t hb = gg & 1;
+        mbar_wait(&gelu_done[hb], (gg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+        for (int kb = 0; kb < 2; ++kb) {
+          const int s = r2_acquire();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_HS + (hb * 2 + kb) * KBYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
+                        (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r2_empty[s]);
+        }
+        tc_commit(&hs_empty[hb]);
+        if (j == K::NCH - 1) tc_commit(&y_full[yb]);
+      };
+      auto mma0 = [&](int lt2) {   // P = attn_out * Wp^T into the (idle) fc2 accumulator of local tile lt2
+        const int xb = K::NXBUF == 2 ? (lt2 & 1) : 0;
+        const uint32_t xuse = K::NXBUF == 2 ? (lt2 >> 1) : lt2;
+        const int yb = K::NYBUF == 2 ? (lt2 & 1) : 0;
+        const uint32_t yuse = K::NYBUF == 2 ? (lt2 >> 1) : lt2;
+        mbar_wait(&x_full[xb], xuse & 1);
+        mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+        for (int kb = 0; kb < K::KB1; ++kb) {
+          const int s = r2_acquire();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
+          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&r2_empty[s]);
+        }
+        tc_commit(&p_full[yb]);
+      };
+      constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;
+      if (EARLY && static_cast<int64_t>(blockIdx.x) < p.tiles) mma0(0);
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
+        if (!EARLY) mma0(lt);
+        for (int j = 0; j < K::NCH; ++j) {
+          if (EARLY && j == K::NCH - 1 && tile + gridDim.x < p.tiles) mma0(lt + 1);
+          fc2(yb, g + j, j);
+        }
+        g += K::NCH;
+      }
+    }
+#else
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
@@ -612,7 +730,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         g += K::NCH;
       }
     }
-  } else {
+#endif
+  } else if (warp < 2 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps
     const int e = warp - 2;
     const int q = warp & 3;
@@ -971,7 +1090,7 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   prm.timing = mlp_timing_buf(stream);
-  SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(THREADS), SMEM, stream, tmX, p.tmWp, p.tmW1h, p.tmW2, prm));
+  SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(PTHREADS), SMEM, stream, tmX, p.tmWp, p.tmW1h, p.tmW2, prm));
   mlp_timing_report("mlp_proj_fused (wait_p, epi0, wait_h, gelu, wait_hs, store, wait_y, out)", C, grid, prm.timing, stream);
   return 0;
 }
