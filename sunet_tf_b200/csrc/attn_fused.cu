@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
         tma_load_2d(smem + K::OFF_W + (kb * K::NMMA + m) * K::NPM * 128, &tmW, &w_full, kb * 64, g * K::NGC + m * K::NPM);
   };
   auto issue_mma = [&](uint32_t it) {   // thread 0: D[128 x NGC] = X * Wg^T for work item `it`
-    mbar_wait(&w_full, it & 1);
+    if (K::NG > 1 || it == 0) mbar_wait(&w_full, it & 1);   // a single head group keeps its weights for the whole kernel
     tc_fence_after();
     const uint32_t idesc = umma_idesc_f16(128, K::NPM);
 #pragma unroll
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       tc_fence_after();
       AF_T(0);
       // the MMAs of this item have read the weight buffer (and, for the last group, the token tile): refill them
-      if (!K::RING && tid == 0 && has_next) load_w(last_g ? 0 : g + 1);
+      if (!K::RING && K::NG > 1 && tid == 0 && has_next) load_w(last_g ? 0 : g + 1);   // (NG == 1: loaded once, never replaced)
       if (last_g && has_next_tile) {
         geo_next = tile_geo(next_tile);
         gather(geo_next);
