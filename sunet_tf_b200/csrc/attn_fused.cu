@@ -552,8 +552,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     tc_commit(&mma_done);
     while (rk_loaded < rk_total && rk_loaded < c0 + K::KB + K::RSTAGES - 1) ring_load(0u);   // prefetch the next item's first k-blocks
   };
+#ifndef SUNET_AF_SPLIT
+#define SUNET_AF_SPLIT 1   // measured at C = 384 (tools/ab_af_split.sh): 55.9 -> 49.6 us per launch
+#endif
+  // RING mode with two threads (SUNET_AF_SPLIT): the ring's TMA producer is lane 0 of a second idle warp, the MMA issuer only waits
+  // for full slots, issues and commits - the k-block loop of a single producer + issuer thread (~1k clk per k-block of barrier round
+  // trips) did not fit under the core and showed up as a 10% wait for the accumulator at the top of every item.
+  auto ring_produce = [&](uint32_t upto) {   // producer thread: TMA of k-blocks [rk_loaded, min(upto, rk_total))
+    while (rk_loaded < rk_total && rk_loaded < upto) ring_load(0u);
+  };
+  auto ring_mma_only = [&](uint32_t it) {
+    const uint32_t idesc = umma_idesc_f16(128, K::NPM);
+    const uint32_t c0 = it * K::KB;
+    uint32_t full_ok = mbar_test(&rk_full[c0 % K::RSTAGES], (c0 / K::RSTAGES) & 1);
+#pragma unroll 1
+    for (int kb = 0; kb < K::KB; ++kb) {
+      const uint32_t c = c0 + kb, slot = c % K::RSTAGES;
+      mbar_wait_hint(&rk_full[slot], (c / K::RSTAGES) & 1, full_ok);
+      const uint32_t cn = c + 1;
+      full_ok = kb + 1 < K::KB ? mbar_test(&rk_full[cn % K::RSTAGES], (cn / K::RSTAGES) & 1) : 0u;
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
+      const uint64_t bdesc = umma_desc_sw128(sW + slot * K::WKB_BYTES);
+      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
+      for (int k = 0; k < ksteps; ++k)
+        umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&rk_empty[slot]);
+    }
+    tc_commit(&mma_done);
+  };
   // the thread that issues TMA + MMA: lane 0 of warp 0, or in RING mode of a warp without a query tile in the core
   constexpr int ISSUER_WARP = K::RING ? K::WPU * K::GH : 0;
+  constexpr bool SPLIT = K::RING && SUNET_AF_SPLIT;
+  const bool is_producer = SPLIT && tid == (ISSUER_WARP + 1) * 32;
   static_assert(!K::RING || (K::NU * K::WPU < 16 && ISSUER_WARP < 8), "RING mode needs an idle warp for the issuer");
   const bool is_issuer = tid == ISSUER_WARP * 32;
 
@@ -580,9 +611,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     normalize();
     tc_fence_before();
     __syncthreads();
+    if (is_producer) ring_produce(K::KB + K::RSTAGES - 1);
     if (is_issuer) {
       tc_fence_after();
-      if (K::RING) ring_mma(0); else issue_mma(0);
+      if (SPLIT) ring_mma_only(0); else if (K::RING) ring_mma(0); else issue_mma(0);
     }
     __syncwarp();
   }
@@ -627,8 +659,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       __syncthreads();   // (B) q/k/v operand tiles complete, accumulator drained
       AF_T(3);
       AF_T(8);
+      if (is_producer && has_next) ring_produce((item + 2) * K::KB + K::RSTAGES - 1);
       if (is_issuer && has_next) {                     // runs on the tensor pipe while the core below runs on the CUDA cores
-        if (K::RING) ring_mma(item + 1); else issue_mma(item + 1);
+        if (SPLIT) ring_mma_only(item + 1); else if (K::RING) ring_mma(item + 1); else issue_mma(item + 1);
       }
       __syncwarp();
       AF_T(9);
