@@ -201,14 +201,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();                 // the prologue above overlapped the previous kernel's tail; its results are visible from here on
   pdl_launch_dependents();
-
+  // Programmatic dependent launch: only the threads that touch the predecessor's output wait for it.  The TMA producer first
+  // issues the WEIGHT halves of its first ring stages (parameters, constant across the forward), then waits, then the activation
+  // halves - the weight bytes (2/3 of a stage at 256-wide tiles) arrive under the previous kernel's tail.
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter: the ring runs across tiles
       int s = 0;
       uint32_t ph = 0;
+      uint32_t pre = 0;   // k-blocks of the first tile whose expect_tx + weight load were issued before the dependency wait
+      if (static_cast<int64_t>(blockIdx.x) < total_tiles && !(p.dbg & 4)) {
+        const int n0 = static_cast<int>(blockIdx.x % p.n_tiles) * block_n;
+        pre = static_cast<uint32_t>(min(stages, num_kb));
+        for (uint32_t kb = 0; kb < pre; ++kb) {
+          uint8_t* sb = smem + kb * stage_bytes + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[kb], stage_bytes);
+          const int kw = static_cast<int>(kb) < kb0 ? static_cast<int>(kb) * BLOCK_K : p.K0 + (static_cast<int>(kb) - kb0) * BLOCK_K;
+          tma_load_2d(sb, &tmW, &full_bar[kb], kw, n0);
+        }
+      }
+      pdl_wait();
       uint32_t ready = mbar_test(&empty_bar[0], 1);
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = static_cast<int>(tile % p.n_tiles) * block_n;
@@ -221,14 +234,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* sa = smem + s_cur * stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
           if (p.dbg & 4) { mbar_arrive(&full_bar[s_cur]); continue; }
-          mbar_arrive_expect_tx(&full_bar[s_cur], stage_bytes);
+          const bool early = it < pre;   // expect_tx and the weight half are already in flight
+          if (!early) mbar_arrive_expect_tx(&full_bar[s_cur], stage_bytes);
           if (kb < kb0) {
             tma_load_2d(sa, &tmA0, &full_bar[s_cur], kb * BLOCK_K, m0);
-            tma_load_2d(sb, &tmW, &full_bar[s_cur], kb * BLOCK_K, n0);
+            if (!early) tma_load_2d(sb, &tmW, &full_bar[s_cur], kb * BLOCK_K, n0);
           } else {
             const int j = kb - kb0;
             tma_load_2d(sa, &tmA1, &full_bar[s_cur], j * BLOCK_K, m0);
-            tma_load_2d(sb, &tmW, &full_bar[s_cur], p.K0 + j * BLOCK_K, n0);
+            if (!early) tma_load_2d(sb, &tmW, &full_bar[s_cur], p.K0 + j * BLOCK_K, n0);
           }
         }
       }
@@ -273,6 +287,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ---------------- epilogue: thread <-> one row of the tile, warp <-> (lane quadrant, column half)
+    pdl_wait();   // residual reads / output writes below must follow the predecessor
     const int q = warp & 3;
     const int quarter = (warp - 2) >> 2;                    // 0..3: which slice of the tile columns
     const int units = block_n >> 4;                          // 16-column units, split as evenly as possible

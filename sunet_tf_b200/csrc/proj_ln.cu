@@ -81,13 +81,23 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();
   pdl_launch_dependents();
-
+  // only the threads that touch the predecessor's output wait for it (the TMA producer before its first activation load, the
+  // epilogue warps before the shortcut reads); the weight k-blocks of the first ring stages are in flight before that wait
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0, local = 0;
+      constexpr int PRE = K::STAGES < K::KB ? K::STAGES : K::KB;
+      if (static_cast<int64_t>(blockIdx.x) < p.tiles) {
+        for (int kb = 0; kb < PRE; ++kb) {
+          uint8_t* sb = smem + kb * K::STAGE + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[kb], K::STAGE);
+          tma_load_2d(sb, &tmW, &full_bar[kb], kb * BK, 0);
+          tma_load_2d(sb + K::NH * 128, &tmW, &full_bar[kb], kb * BK, K::NH);
+        }
+      }
+      pdl_wait();
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
         const int m0 = static_cast<int>(tile * TILE_M);
         mbar_wait(&acc_empty, (local & 1) ^ 1);   // the previous tile's epilogue no longer uses the staging tiles inside stage 0
@@ -95,10 +105,13 @@ __global__ void __launch_bounds__(THREADS, 1)
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * K::STAGE;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], K::STAGE);
+          const bool early = local == 0 && kb < PRE;   // expect_tx and the weight k-block were issued before the dependency wait
+          if (!early) mbar_arrive_expect_tx(&full_bar[s], K::STAGE);
           tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
-          tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, 0);
-          tma_load_2d(sb + K::NH * 128, &tmW, &full_bar[s], kb * BK, K::NH);
+          if (!early) {
+            tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, 0);
+            tma_load_2d(sb + K::NH * 128, &tmW, &full_bar[s], kb * BK, K::NH);
+          }
           if (++s == K::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -131,6 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else {
+    pdl_wait();
     const int e = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int quarter = e >> 2;             // column quarter
