@@ -383,8 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();   // everything above read only parameters (constant across the forward); the token stream is touched below
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // (the dependency wait itself sits below, after the first weight loads have been issued)
 
   const int nWc = p.W >> 3, nWr = p.H >> 3, nW = nWr * nWc;
   const long long nwin = static_cast<long long>(p.B) * nW;
@@ -604,8 +603,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   uint32_t item = 0;
   AF_T_DECL;
   Geo geo = tile_geo(it_begin / K::NG);
+  // Everything up to here read only parameters (constant across the forward); so do the first weight loads: they are issued
+  // before the programmatic-dependency wait and arrive under the previous kernel's tail.  The token stream is touched below.
   if (it_begin < it_end) {
     if (!K::RING && tid == 0) load_w(g_first);
+    if (is_producer) ring_produce(K::RSTAGES);   // the free slots only: nothing here may block (no MMA has been issued yet)
+  }
+  pdl_wait();
+  if (it_begin < it_end) {
     gather(geo);
     cp_async_wait_all();
     normalize();
