@@ -31,8 +31,13 @@ constexpr int NT = 16;                  // folded tap maps per sub-pixel (9 taps
 constexpr int KBYTES = TILE_M * 128;    // one [128 rows][64 fp16] SW128 k-block
 constexpr int W1KB = E * 128;           // one [96 rows][64] k-block of a sub-pixel's weights
 constexpr int EPI_WARPS = 16;
-constexpr int THREADS = 64 + EPI_WARPS * 32 + 32;   // TMA producer, fc1 issuer, 16 epilogue warps, fc2 issuer
+#ifndef SUNET_TAIL_FC1_SPLIT
+#define SUNET_TAIL_FC1_SPLIT 1   // measured (tools/ab_tail_fc1.sh): 207 -> 182 us
+#endif
+// TMA producer, fc1 issuer, 16 epilogue warps, fc2 issuer (+ with SUNET_TAIL_FC1_SPLIT a second fc1 issuer: even / odd sub-pixels)
+constexpr int THREADS = 64 + EPI_WARPS * 32 + 32 + (SUNET_TAIL_FC1_SPLIT ? 32 : 0);
 constexpr int FC2_WARP = 2 + EPI_WARPS;
+constexpr int FC1B_WARP = FC2_WARP + 1;
 constexpr int R1 = 4;                   // weight ring stages
 constexpr int OFF_X = 0;                // 2 token-tile buffers x 2 k-blocks
 constexpr int OFF_HS = OFF_X + 2 * 2 * KBYTES;
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     tma_prefetch_desc(&tmGp);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 1);
-      mbar_init(&x_empty[i], 1);
+      mbar_init(&x_empty[i], (SUNET_TAIL_FC1_SPLIT && p.split) ? 2 : 1);
       mbar_init(&h_full[i], 1);
       mbar_init(&h_empty[i], EPI_WARPS / 2);   // the epilogue warps work in two groups of 8, group b on the chunks of buffer b
       mbar_init(&g_done[i], EPI_WARPS / 2);
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           const int s = i1 % R1;
           mbar_wait_hint(&r1_full[s], (i1 / R1) & 1, r1_ok);
           ++i1;
-          r1_ok = mbar_test(&r1_full[i1 % R1], (i1 / R1) & 1);
+          r1_ok = (SUNET_TAIL_FC1_SPLIT && kb == 1) ? 0u : mbar_test(&r1_full[i1 % R1], (i1 / R1) & 1);   // (split: the next k-block is the other thread's)
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_X + (xb * 2 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_R1 + s * W1KB));
@@ -179,7 +184,11 @@ __global__ void __launch_bounds__(THREADS, 1)
           const int xb = lt & 1;
           mbar_wait(&x_full[xb], (lt >> 1) & 1);
           tc_fence_after();
+#if SUNET_TAIL_FC1_SPLIT
+          for (int j = 0; j < SUB; j += 2) { i1 = 2 * (g + j); fc1(xb, g + j, j == SUB - 2); }   // even sub-pixels; warp FC1B_WARP takes the odd ones
+#else
           for (int j = 0; j < SUB; ++j) fc1(xb, g + j, j == SUB - 1);
+#endif
           g += SUB;
         }
       } else {
@@ -199,6 +208,41 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       }
     }
+#if SUNET_TAIL_FC1_SPLIT
+  } else if (warp == FC1B_WARP) {
+    // ------------------------------------------------------------------ second fc1 issuer: the odd sub-pixels (H buffer 1)
+    if (lane == 0 && p.split) {
+      const uint32_t idesc1 = umma_idesc_f16(TILE_M, E);
+      uint32_t g = 0;
+      int lt = 0;
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int xb = lt & 1;
+        mbar_wait(&x_full[xb], (lt >> 1) & 1);
+        tc_fence_after();
+        for (int j = 1; j < SUB; j += 2) {
+          const uint32_t gg = g + j, hb = 1, use = gg >> 1;
+          if (use > 0) mbar_wait(&h_empty[hb], (use - 1) & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + TM_H + hb * 128;
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t i1 = 2 * gg + kb;
+            const int s = i1 % R1;
+            mbar_wait(&r1_full[s], (i1 / R1) & 1);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_X + (xb * 2 + kb) * KBYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_R1 + s * W1KB));
+            const int ksteps = kb == 1 ? 2 : 4;
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r1_empty[s]);
+          }
+          tc_commit(&h_full[hb]);
+          if (j == SUB - 1) tc_commit(&x_empty[xb]);
+        }
+        g += SUB;
+      }
+    }
+#endif
   } else if (warp == FC2_WARP) {
     // ------------------------------------------------------------------ fc2 issuer (split mode)
     if (lane == 0 && p.split) {
@@ -226,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         g += SUB;
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps
     const int e = warp - 2;
     const int q = warp & 3;            // TMEM lane quadrant this warp may touch
