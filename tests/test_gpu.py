@@ -433,3 +433,14 @@ def test_checkpoint_load_repacks_device_weights(dev, tmp_path):
     after = model(noisy2.to(dev))
     assert not torch.equal(before, after)
     report("checkpoint-loaded model vs reference golden", after, torch.from_numpy(g["output"]), MODEL_TOL, relative=False)
+
+
+def test_forward_is_bit_reproducible(dev, model_init):
+    """The fused kernels hand tiles between TMA, two or three MMA-issuing threads and the epilogue warps through mbarriers: a
+    protocol race would show up as run-to-run differences.  40 forwards of a 24-image batch must be bit-identical (300 forwards of
+    the B = 64 bench batch were, profiles / DESIGN.md)."""
+    x, _ = Wt.awgn_input(24, seed=77)
+    x = x.to(dev)
+    ref = model_init(x).clone()
+    for _ in range(40):
+        assert torch.equal(model_init(x), ref)
