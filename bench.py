@@ -33,6 +33,16 @@ WORKLOAD = ("BASELINE configs[1]: SUNet fwd 256x256 RGB batch 64 per GPU, traini
             "heads 8, win 8, qk_scale 8), random init, AWGN sigma=50 8-bit quantised input")
 
 
+def base_config(batch, world, h2d_bytes):
+    """The `config` object of the JSON line - identical for the b200 arm and the reference arm (same workload)."""
+    return {"workload": WORKLOAD,
+            "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"batch-sharded dp{world}, no collective",
+            "l2": f"inputs rotate over {N_INPUT_BUFFERS} distinct batches ({N_INPUT_BUFFERS * h2d_bytes / 1e6:.0f} MB) and each forward "
+                  "streams a ~2 GB workspace, both > 126 MB L2",
+            "precision": "fp16 operands/activations, fp32 accumulate/LN/softmax; parity max-abs ~3e-4 vs reference (bar 2e-3, tests/test_gpu.py)",
+            "launch": "programmatic dependent launch on every forward kernel (SUNET_NO_PDL=1 disables)"}
+
+
 def read_traffic(kind):
     """Measured DRAM bytes per launch of a kernel family (ncu dram__bytes_read.sum + dram__bytes_write.sum over one forward of this
     workload, committed under profiles/ by tools/ncu_traffic.py); None when no capture is present."""
@@ -110,27 +120,83 @@ def make_inputs(torch, device, seed, n_buffers, batch):
     return bufs
 
 
-def cpu_port_images_per_s(torch, state_dict, images, passes, warmup=1):
-    """Times the CPU oracle port (oracle/sunet_oracle.py) of the reference forward with all host threads."""
+def cpu_forward_fn(torch, state_dict):
+    """The reference's CPU forward of the path: the UNMODIFIED reference model (baseline/_ref, installed by
+    baseline/install_ref.py and shipped by gpurun; kind "reference") when it is present, else the oracle port (kind "port").
+    Returns (callable(x) -> out, kind, description)."""
+    from oracle.reference_loader import load_reference, reference_root
+    root = reference_root()
+    if root is not None:
+        SUNet_model, _, cfg = load_reference()
+        model = SUNet_model(cfg).eval()
+        model.load_state_dict(state_dict, strict=True)
+        return (lambda x: model(x)), "reference", f"unmodified reference model/SUNet.py from {os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}"
     from oracle import sunet_oracle as O
+    return (lambda x: O.sunet_model_forward(state_dict, x)), "port", "CPU oracle port (oracle/sunet_oracle.py); reference tree not present"
+
+
+def cpu_images_per_s(torch, state_dict, images, passes, warmup=1):
+    """Times the reference's CPU forward (see cpu_forward_fn) with all host threads."""
     from oracle import weights as Wt
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    fwd, kind, desc = cpu_forward_fn(torch, state_dict)
     x, _ = Wt.awgn_input(images, seed=1)
     times = []
     with torch.no_grad():
         for i in range(warmup + passes):
             t0 = time.perf_counter()
-            O.sunet_model_forward(state_dict, x)
+            fwd(x)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return images / statistics.median(times), cores, times
+    return images / statistics.median(times), cores, kind, desc
+
+
+def run_anyres(torch, dist, shard, device, rank, world, size=2048, reps=3):
+    """BASELINE config 5 (demo_any_resolution.py:35-52, :116-139): one (1,3,2048,2048) AWGN image = 225 overlapping 256x256 tiles
+    (stride 128), tile t on rank t*N//225, each rank folds its tiles into a zeroed canvas, ONE reduce sums the canvases on rank 0,
+    which normalises / crops / clamps.  out_chans = 3 as the reference script assumes.  Device-timed, max over ranks."""
+    from sunet_tf_b200 import SUNet, tiles
+    torch.manual_seed(0)
+    net = SUNet(img_size=256, patch_size=4, in_chans=3, out_chans=3, embed_dim=96, depths=[8] * 4, num_heads=[8] * 4, window_size=8,
+                mlp_ratio=4.0, qkv_bias=True, qk_scale=8).to(device).eval()
+    g = torch.Generator(device=device)
+    g.manual_seed(4)
+    clean = torch.rand(1, 3, size, size, generator=g, device=device)
+    noisy = torch.round(torch.clamp(clean + torch.randn(1, 3, size, size, generator=g, device=device) * (50 / 255.0), 0, 1) * 255) / 255
+    X, n = tiles.canvas_geometry(size, size)
+    lo, hi = shard.tile_range(n * n, rank, world)
+    for _ in range(2):
+        tiles.denoise_any_resolution(net, noisy, tile_batch=64, rank=rank, world_size=world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    e0.record()
+    for _ in range(reps):
+        ev = {}
+        tiles.denoise_any_resolution(net, noisy, tile_batch=64, rank=rank, world_size=world, events=ev)
+        evs.append(ev)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1) / reps, device)
+    red_ms = shard.max_over_ranks(sum(ev["reduce_begin"].elapsed_time(ev["reduce_end"]) for ev in evs) / reps if world > 1 else 0.0, device)
+    del net
+    if rank != 0:
+        return None
+    return {"workload": f"BASELINE configs[4]: demo_any_resolution {size}x{size}, {n * n} tiles of 256 stride 128, tiles sharded over {world} GPU(s)",
+            "ms": ms, "tiles_per_s": n * n / ms * 1e3, "mpixel_per_s": size * size / ms * 1e-3, "tiles_per_rank_max": -(-n * n // world),
+            "forwards_per_rank": -(-(-(-n * n // world)) // 64), "reduce_bytes": 3 * X * X * 4 if world > 1 else 0, "reduce_ms": red_ms,
+            "collective": "one NCCL reduce (sum) of the fp32 canvases to rank 0" if world > 1 else "none (single rank)", "reps": reps}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (the oracle port; the PyTorch reference tree
-    does not travel to the GPU box) on the host cores.  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path on the host cores - the unmodified reference model
+    from baseline/_ref when present (kind "reference"), else the oracle port.  Rank 0 only."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
@@ -138,27 +204,26 @@ def run_reference(args):
     from oracle import weights as Wt
     sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="init")
     images = 2
-    from oracle import sunet_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    fwd, kind, desc = cpu_forward_fn(torch, sd)
     x, _ = Wt.awgn_input(images, seed=1)
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 2))):
-            O.sunet_model_forward(sd, x)
+            fwd(x)
         steps = max(1, min(args.steps, 40))
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.sunet_model_forward(sd, x)
+            fwd(x)
         dt = time.perf_counter() - t0
     value = images * steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "step": f"bounded sample: {images} images of that workload per step through the CPU oracle port of the reference "
-                           f"forward (torch {torch.__version__} CPU fp32, {cores} threads)"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {images} images, {cores} threads"},
+        "config": base_config(args.batch, args.gpus, args.batch * 3 * 256 * 256 * 4),
+        "step": f"bounded sample: {images} images of that workload per step through {desc} (torch {torch.__version__} CPU fp32, {cores} threads)",
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} steps x {images} images, {cores} threads; {desc}"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,6 +239,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 4-image parity check against the CPU oracle")
+    ap.add_argument("--no-anyres", action="store_true", help="skip the config-5 (2048x2048 tiles) sub-record")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel breakdown to this file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -303,13 +370,31 @@ def main():
             with open(args.profile_json, "w") as fh:
                 json.dump({"batch": B, "kernels": kernels, "launch_list": recs}, fh, indent=1)
 
+    # ---------------- parity of this very run (rank 0): 4 images of the timed batch against the CPU oracle, outside the timed region
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import sunet_oracle as O
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        xs = inputs[0][:4]
+        got = model(xs.contiguous()).cpu()
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            ref = O.sunet_model_forward(sd_cpu, xs.cpu())
+        parity = {"max_abs": float((got - ref).abs().max()), "images": 4, "bar": 2e-3,
+                  "against": "CPU oracle (oracle/sunet_oracle.py, pinned to the reference <= 2e-5) on the first 4 images of the timed batch"}
+
+    # ---------------- config 5 sub-record: 2048 x 2048 any-resolution input, 225 tiles sharded over the ranks, one canvas reduce
+    anyres = None
+    if not args.no_anyres:
+        anyres = run_anyres(torch, dist, shard, device, rank, world)
+
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        v, cores, times = cpu_port_images_per_s(torch, sd, images=2, passes=5, warmup=1)
-        cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"5 timed passes x 2 images (median), same arch/input recipe, torch {torch.__version__} CPU fp32, {cores} threads"}
+        v, cores, kind, desc = cpu_images_per_s(torch, sd, images=2, passes=5, warmup=1)
+        cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
+                        "sample": f"5 timed passes x 2 images (median), same arch/input recipe, torch {torch.__version__} CPU fp32, {cores} threads; {desc}"}
 
     if rank == 0:
         launches = model.swin_unet.launches_per_forward(B)
@@ -317,12 +402,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-sharded dp{world}, no collective",
-                       "l2": f"inputs rotate over {N_INPUT_BUFFERS} distinct batches ({N_INPUT_BUFFERS * h2d / 1e6:.0f} MB) and each forward "
-                             "streams a ~2 GB workspace, both > 126 MB L2",
-                       "precision": "fp16 operands/activations, fp32 accumulate/LN/softmax; parity max-abs ~3e-4 vs reference (bar 2e-3, tests/test_gpu.py)",
-                       "launch": "programmatic dependent launch on every forward kernel (SUNET_NO_PDL=1 disables)"},
+            "config": base_config(B, world, h2d),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K, "wall_ms_per_step": wall_ms / K,
@@ -336,6 +416,11 @@ def main():
                                  "achieved_tflops_per_gpu": value / world * REF_FLOPS_PER_IMAGE / 1e12,
                                  "frac_of_sustained_peak": value / world * REF_FLOPS_PER_IMAGE / 1e12 / peaks["tflops_sustained"]},
             "cpu_baseline": cpu_baseline,
+            "parity_max_abs": parity["max_abs"] if parity else None,
+            "parity": parity,
+            "anyres_2048": anyres,
+            "timing_note": "kernels/roofline come from a profiling forward that brackets every launch with CUDA events, which serialises what "
+                           "programmatic dependent launch overlaps: the per-launch sum exceeds ms_per_step by ~10%; shares are of the serialised forward",
         }
         print(json.dumps(line), flush=True)
     if world > 1:

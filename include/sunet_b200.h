@@ -54,6 +54,16 @@ int sunet_destroy(sunet_handle_t h);
 
 /* SwinTransformerBlock.forward (:227-264): x (B, H*W, C) -> out (B, H*W, C). */
 int sunet_swin_block_fwd(sunet_handle_t h, const float* x, int batch, float* out, void* stream);
+/* The same block on the library's own activation format - fp16 token rows (B*H*W, C), image order - without the fp32 casts and
+ * the stream-ordered allocation of the entry point above: the form the whole-model forward runs, exposed for measurement
+ * (BASELINE config 4) and for callers that keep an fp16 stream.  part 0: the whole block (:227-264), out may alias x;
+ * part 1: only its window-attention part up to the per-head attention output (norm1, cyclic shift, window partition, qkv,
+ * QK^T + relative-position bias + shifted-window mask, softmax, AV, window reverse, un-shift; :233-257 and :107-135, i.e.
+ * WindowAttention.forward without its proj Linear, which the fused design runs inside the MLP kernel), out must not alias x.
+ * The workspace (sunet_swin_block_f16_workspace_bytes) is caller-owned; nothing is allocated on the call. */
+size_t sunet_swin_block_f16_workspace_bytes(sunet_handle_t h, int batch);
+int sunet_swin_block_f16(sunet_handle_t h, const void* x, int batch, int part, void* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
 /* WindowAttention.forward (:107-138): x (num_windows_total, 64, C); mask (mask_nw, 64, 64) fp32 or NULL. */
 int sunet_window_attention_fwd(sunet_handle_t h, const float* x, int64_t num_windows, const float* mask, int mask_nw,
                                float* out, void* stream);
@@ -116,6 +126,14 @@ int sunet_gemm_f16(const void* A, const void* W, const float* bias, void* C, int
  * SwinTransformerBlock.forward :262) - the fused tcgen05 kernel in isolation (C in {96, 192}); packs, runs, frees. */
 int sunet_ln_mlp_residual_f16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, const float* w1,
                               const float* b1, const float* w2, const float* b2, void* out, void* stream);
+
+/* The two remaining pieces of SUNet.forward_up_features on fp16 rows, in isolation (parity tests at module granularity):
+ * out[rows,C] = LayerNorm(x) - the model's `norm` (:677, :718) and `norm_up` (:678, :732);
+ * out[rows,C] = Linear(2C -> C)(cat([x, skip], -1)) - `concat_back_dim[i]` (:652-654, :728-729) as one tcgen05 GEMM with two
+ * K segments (w fp32 [C][2C], b fp32 [C] or NULL; packs, runs, synchronises, frees). */
+int sunet_layernorm_f16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, void* out, void* stream);
+int sunet_concat_linear_f16(const void* x, const void* skip, int64_t rows, int C, const float* w, const float* b, void* out,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference model (mehrdad78/SUNet_TF) for golden generation.
 
-TEST INFRASTRUCTURE ONLY.  Works only where the reference tree exists ($SUNET_REF or
-/root/reference, i.e. the build container, never the GPU box).  The reference imports two packages
+TEST INFRASTRUCTURE ONLY.  Works where the reference tree exists: $SUNET_REF, /root/reference (the build
+container) or baseline/_ref (the verbatim, git-ignored install made by baseline/install_ref.py, which gpurun ships
+to the GPU box).  The reference imports two packages
 that are absent from this image at module import time (model/SUNet_detail.py:5-6):
   * timm.models.layers.{DropPath, to_2tuple, trunc_normal_}
   * thop.profile (used only under __main__, SUNet_detail.py:786)
@@ -16,7 +17,10 @@ import types
 import torch
 import yaml
 
-REF_CANDIDATES = [os.environ.get("SUNET_REF", ""), "/root/reference"]
+# $SUNET_REF, the build container's read-only tree, or the verbatim install made by baseline/install_ref.py (git-ignored,
+# shipped to the GPU box): the same three unmodified files in every case
+REF_CANDIDATES = [os.environ.get("SUNET_REF", ""), "/root/reference",
+                  os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
 
 
 def reference_root():

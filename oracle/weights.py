@@ -180,8 +180,26 @@ def make_tensor(key, shape, kind, extra, seed, style):
     raise ValueError(kind)
 
 
+OUTLIER_GAIN = 50.0        # a few LayerNorm gains per block, as trained Swin models grow on their massive-activation channels
+OUTLIER_CHANNEL = 7
+OUTLIER_BIAS = 300.0       # one residual-stream channel carried at O(10^2): fp16 ulp there is 0.25
+
+
 def synth_state_dict(spec, seed=0, style="init"):
-    return {k: make_tensor(k, shape, kind, extra, seed, style) for k, shape, kind, extra in spec}
+    """style "init": the reference's initialisation; "stress": every parameter class perturbed so that bias / mask / affine
+    errors are observable; "outlier": "stress" plus the magnitude pattern of trained checkpoints that random init never
+    shows: three channels of every block's norm1 / norm2 gain x50, and stream channel 7 offset by 300 at the
+    patch embedding, so that the fp16 token stream and the fp16 MMA operands see large-magnitude values."""
+    base = "stress" if style == "outlier" else style
+    sd = {k: make_tensor(k, shape, kind, extra, seed, base) for k, shape, kind, extra in spec}
+    if style == "outlier":
+        for k in sd:
+            if k.endswith(("norm1.weight", "norm2.weight")):
+                idx = torch.randint(0, sd[k].numel(), (3,), generator=_gen(k + "#outlier", seed))
+                sd[k][idx] *= OUTLIER_GAIN
+            elif k.endswith("patch_embed.norm.bias"):
+                sd[k][OUTLIER_CHANNEL] = OUTLIER_BIAS
+    return sd
 
 
 def awgn_input(batch, seed=1, size=256, sigma=50.0, chans=3, quantize=True):

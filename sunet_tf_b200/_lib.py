@@ -30,6 +30,9 @@ _SIGNATURES = {
                                      ctypes.POINTER(ctypes.c_void_p)]),
     "sunet_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "sunet_swin_block_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "sunet_swin_block_f16_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
+    "sunet_swin_block_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_size_t, ctypes.c_void_p]),
     "sunet_window_attention_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int,
                                                   ctypes.c_void_p, ctypes.c_void_p]),
     "sunet_mlp_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
@@ -57,6 +60,10 @@ _SIGNATURES = {
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "sunet_selftest_umma": (ctypes.c_int, [ctypes.c_void_p]),
     "sunet_ln_mlp_residual_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 8),
+    "sunet_layernorm_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    "sunet_concat_linear_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p]),
     "sunet_gemm_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }

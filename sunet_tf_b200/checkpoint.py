@@ -24,17 +24,20 @@ def strip_module_prefix(state_dict):
     return out
 
 
-def _read(weights, map_location):
-    ckpt = torch.load(weights, map_location=map_location, weights_only=False) if isinstance(weights, (str, os.PathLike)) else weights
+def _read(weights, map_location, trusted=False):
+    """``weights_only=True`` by default: the reference's {'epoch', 'state_dict', 'optimizer'} checkpoints hold only tensors and
+    plain containers, so nothing needs the full (code-executing) unpickler.  ``trusted=True`` opts in to it for checkpoints
+    from a source you control that pickled other objects."""
+    ckpt = torch.load(weights, map_location=map_location, weights_only=not trusted) if isinstance(weights, (str, os.PathLike)) else weights
     if not isinstance(ckpt, dict) or "state_dict" not in ckpt:
         raise RuntimeError("checkpoint has no 'state_dict' entry (expected {'epoch', 'state_dict', 'optimizer'}, train.py:520-535)")
     return ckpt
 
 
-def load_checkpoint(model, weights, map_location="cpu"):
+def load_checkpoint(model, weights, map_location="cpu", trusted=False):
     """model_utils.py:27-37 / demo.py:33-43: strict load, retrying with the ``module.`` prefix stripped.  ``weights`` is a path
     or an already loaded checkpoint dict.  Returns the checkpoint dict (the reference returns None)."""
-    ckpt = _read(weights, map_location)
+    ckpt = _read(weights, map_location, trusted)
     state = ckpt["state_dict"]
     try:
         model.load_state_dict(state)
@@ -43,16 +46,16 @@ def load_checkpoint(model, weights, map_location="cpu"):
     return ckpt
 
 
-def load_checkpoint_multigpu(model, weights, map_location="cpu"):
+def load_checkpoint_multigpu(model, weights, map_location="cpu", trusted=False):
     """model_utils.py:40-47: the prefix is always stripped."""
-    ckpt = _read(weights, map_location)
+    ckpt = _read(weights, map_location, trusted)
     model.load_state_dict(strip_module_prefix(ckpt["state_dict"]))
     return ckpt
 
 
-def load_start_epoch(weights, map_location="cpu"):
+def load_start_epoch(weights, map_location="cpu", trusted=False):
     """model_utils.py:50-53."""
-    return _read(weights, map_location)["epoch"]
+    return _read(weights, map_location, trusted)["epoch"]
 
 
 def save_checkpoint(model_dir, state, session):

@@ -14,6 +14,7 @@
 // run the register-resident flash-style core (mma.sync.m16n8k16, fp16 in, fp32 accumulate) on the current one.
 // The linear layers around it (>= 90% of the block FLOPs) run on tcgen05 (gemm_tcgen05.cu, mlp_fused.cu).
 #include "attn_core.cuh"
+#include "device.h"
 #include "error.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -377,15 +378,12 @@ template <int HD, int HPC, int NWARPS>
 int launch_core(const AttnCoreArgs& a, int64_t windows, cudaStream_t stream) {
   using K = CoreCfg<HD, HPC, NWARPS>;
   if (a.heads > 8) return fail(SUNET_E_SHAPE, "attn: at most 8 heads are staged (got %d)", a.heads);
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(attn_core_kernel<HD, HPC, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    configured = true;
+    once.done();
   }
+  const int sms = device_sms();
   const int64_t units = windows * (a.heads / HPC);
   if (units > 0x7fffffff) return fail(SUNET_E_SHAPE, "attn: too many (window, head-group) units");
   const unsigned grid = static_cast<unsigned>(units < sms ? units : sms);

@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "device.h"
 #include "error.h"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -761,15 +762,12 @@ __global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __
 template <int C, int GH>
 int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H, int W, int shift, cudaStream_t stream) {
   using K = FCfg<C, GH>;
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(attn_fused_kernel<C, GH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    configured = true;
+    once.done();
   }
+  const int sms = device_sms();
   FParams prm;
   prm.x = x; prm.out = out;
   prm.hconst = p.hconst;

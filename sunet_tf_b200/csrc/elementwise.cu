@@ -5,6 +5,7 @@
 
 #include <stdlib.h>
 
+#include "device.h"
 #include "error.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -468,11 +469,10 @@ int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Hi
   if (img_chans != 1 && img_chans != 3) return fail(SUNET_E_SHAPE, "patch embed: input must have 1 or 3 channels, got %d", img_chans);
   if (Himg % 32 || Wimg % 32) return fail(SUNET_E_SHAPE, "patch embed: image %dx%d must be a multiple of 32", Himg, Wimg);
   if (E % 32 || E > 128) return fail(SUNET_E_SHAPE, "patch embed: embed_dim %d must be a multiple of 32 and <= 128", E);
-  if (wpk != nullptr && Wimg % 64 == 0 && getenv("SUNET_PE_FFMA") == nullptr) {   // tensor-core form: 8 x 16-token tiles
+  static const bool pe_ffma = getenv("SUNET_PE_FFMA") != nullptr;   // read once per process, never on the hot call
+  if (wpk != nullptr && Wimg % 64 == 0 && !pe_ffma) {   // tensor-core form: 8 x 16-token tiles
     const int tiles = B * (Himg / 32) * (Wimg / 64);
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const int sms = device_sms();
     const unsigned grid = static_cast<unsigned>(tiles < 2 * sms ? tiles : 2 * sms);
 #define PE_MMA_T(EPL, U8)                                                                                                    \
   {                                                                                                                          \

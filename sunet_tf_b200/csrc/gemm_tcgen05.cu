@@ -8,6 +8,7 @@
 // co-running CTAs share A rows in L2).  While the epilogue drains accumulator stage s, the MMA warp fills stage s^1
 // and the producer prefetches the operands of the tiles after that.
 #include "act.cuh"
+#include "device.h"
 #include "error.h"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -513,15 +514,7 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms() { return device_sms(); }
 
 static int pick_block_n(int N, int64_t m_tiles, int K) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
@@ -564,10 +557,8 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   const int stage_bytes = A_TILE_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2;
   int stages = (GEMM_MAX_DYN_SMEM - 1024 - EPI_WARPS * 4096) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (const char* cap = getenv("SUNET_GEMM_STAGES")) {   // pipeline-depth experiments (tools/gemm_stage_sweep.sh)
-    const int v = atoi(cap);
-    if (v >= 1 && v < stages) stages = v;
-  }
+  static const int stage_cap = [] { const char* cap = getenv("SUNET_GEMM_STAGES"); return cap ? atoi(cap) : 0; }();   // pipeline-depth experiments (tools/gemm_stage_sweep.sh); read once
+  if (stage_cap >= 1 && stage_cap < stages) stages = stage_cap;
   if (stages < 1) stages = 1;
   SUNET_TRY(make_tmap_2d_f16(&op->tmA0, a.A0, a.K0, a.M, a.lda0, BLOCK_M));
   if (a.K1 > 0) SUNET_TRY(make_tmap_2d_f16(&op->tmA1, a.A1, a.K1, a.M, a.lda1, BLOCK_M));
@@ -601,11 +592,11 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
-  static bool configured = false;  // per process; one device per process (one rank per GPU)
-  if (!configured) {
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(gemm_tn_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_MAX_DYN_SMEM));
     SUNET_CUDA(cudaFuncSetAttribute(gemm_tn_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_MAX_DYN_SMEM));
-    configured = true;
+    once.done();
   }
   if (op.pair) SUNET_CUDA(launch_pdl(gemm_tn_f16_pair_kernel, dim3(op.grid), dim3(GEMM_THREADS), op.smem, stream, op.tmA0, op.tmA1, op.tmW, op.epi));
   else SUNET_CUDA(launch_pdl(gemm_tn_f16_kernel, dim3(op.grid), dim3(GEMM_THREADS), op.smem, stream, op.tmA0, op.tmA1, op.tmW, op.epi));

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "act.cuh"
+#include "device.h"
 #include "error.h"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -1042,10 +1043,10 @@ static void mlp_timing_report(const char* what, int C, unsigned grid, const long
 template <int C>
 int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cudaStream_t stream) {
   using K = Cfg<C>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    configured = true;
+    once.done();
   }
   alignas(64) CUtensorMap tmX;
   SUNET_TRY(make_tmap_2d_f16(&tmX, x, C, M, C, TILE_M));
@@ -1055,9 +1056,7 @@ int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cud
   prm.out = out;
   prm.M = M;
   prm.tiles = (M + TILE_M - 1) / TILE_M;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const int sms = device_sms();
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   prm.timing = mlp_timing_buf(stream);
   SUNET_CUDA(launch_pdl(mlp_fused_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmX, p.tmW1, p.tmW2, prm));
@@ -1070,10 +1069,10 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   using K = Cfg<C>;
   constexpr int SMEM = K::SMEM + C * 4;
   static_assert(SMEM <= 227 * 1024, "shared memory budget (proj variant)");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(mlp_proj_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
+    once.done();
   }
   alignas(64) CUtensorMap tmX;
   SUNET_TRY(make_tmap_2d_f16(&tmX, attn_out, C, M, C, TILE_M));
@@ -1085,9 +1084,7 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   prm.out = out;
   prm.M = M;
   prm.tiles = (M + TILE_M - 1) / TILE_M;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const int sms = device_sms();
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   prm.timing = mlp_timing_buf(stream);
   SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(PTHREADS), SMEM, stream, tmX, p.tmWp, p.tmW1h, p.tmW2, prm));

@@ -213,6 +213,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
   bool use_mf = false;
   AttnFusedPack af;     // norm1 + shift/partition + qkv + attention core + reverse/un-shift as one kernel
   bool use_af = false;
+  bool use_proj_ln = false, use_row_gemm = false;   // C = 384 whole-row kernels (proj + shortcut + norm2; fc2 + residual)
   int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, int heads_, int shift_, double qk_scale,
            cudaStream_t s) {
     dim = dim_; H = H_; W = W_; heads = heads_; shift = shift_;
@@ -262,17 +263,15 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     } else {
       SUNET_TRY(mlp.pack(ar, P, pre + "mlp.", dim, 4 * dim, dim, s));
     }
+    // kernel selection is fixed here, once per pre-pack: the forward never consults the environment
+    use_proj_ln = !use_mf && proj_ln_supported(dim) && getenv("SUNET_NO_PROJ_LN") == nullptr;
+    use_row_gemm = row_gemm_supported(dim, 4 * dim) && getenv("SUNET_NO_ROW_GEMM") == nullptr;
     return 0;
   }
-  // x_in [B*H*W][dim] -> x_out (may alias x_in); image-order rows throughout
-  int forward(Ctx& c, const __half* x_in, __half* x_out, int B) const {
-    ScratchMark mk(c.sc);
+  // The window-attention part of the block up to the per-head attention output O (norm1, shift, partition, qkv, QK^T + bias +
+  // mask, softmax, AV, reverse, un-shift; SUNet_detail.py:233-257 without the proj Linear of :136): x_in -> O [B*H*W][dim]
+  int attention_part(Ctx& c, const __half* x_in, __half* O, __half* T, __half* QKV, int B) const {
     const int64_t M = static_cast<int64_t>(B) * H * W;
-    __half *T, *QKV, *O, *Hd;
-    SUNET_TRY(c.sc.take_t(&T, (use_af && use_mf) ? 0 : M * dim));
-    SUNET_TRY(c.sc.take_t(&QKV, use_af ? 0 : M * 3 * dim));
-    SUNET_TRY(c.sc.take_t(&O, M * dim));
-    SUNET_TRY(c.sc.take_t(&Hd, use_mf ? 0 : M * 4 * dim));
     if (use_af) {
       RUN(c, K_ATTN_FUSED, 6.0 * M * dim * dim + 256.0 * M * dim, 4.0 * M * dim,
           attn_fused_launch(af, x_in, O, B, H, W, shift, c.stream));                             // :233-257 minus proj
@@ -284,17 +283,29 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;
       RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_launch(a, c.stream));             // :118-135, :236-257
     }
+    return 0;
+  }
+  // x_in [B*H*W][dim] -> x_out (may alias x_in); image-order rows throughout
+  int forward(Ctx& c, const __half* x_in, __half* x_out, int B) const {
+    ScratchMark mk(c.sc);
+    const int64_t M = static_cast<int64_t>(B) * H * W;
+    __half *T, *QKV, *O, *Hd;
+    SUNET_TRY(c.sc.take_t(&T, (use_af && use_mf) ? 0 : M * dim));
+    SUNET_TRY(c.sc.take_t(&QKV, use_af ? 0 : M * 3 * dim));
+    SUNET_TRY(c.sc.take_t(&O, M * dim));
+    SUNET_TRY(c.sc.take_t(&Hd, use_mf ? 0 : M * 4 * dim));
+    SUNET_TRY(attention_part(c, x_in, O, T, QKV, B));
     if (use_mf && mf.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one kernel
       RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim, mlp_proj_fused_launch(mf, O, x_in, x_out, M, c.stream));
       return 0;
     }
-    if (!use_mf && proj_ln_supported(dim) && getenv("SUNET_NO_PROJ_LN") == nullptr) {
+    if (use_proj_ln) {
       // :136 proj, :261 shortcut, :262 norm2 in one kernel (whole rows per CTA); then the two MLP GEMMs
       ProjLnPack pl;
       pl.w = attn.proj.w; pl.bias = attn.proj.b; pl.gamma = g2; pl.beta = b2; pl.C = dim;
       RUN(c, K_GEMM, 2.0 * M * dim * dim, 8.0 * M * dim + 2.0 * dim * dim, proj_ln_launch(pl, O, x_in, x_out, T, M, c.stream));
       SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
-      if (row_gemm_supported(dim, 4 * dim) && getenv("SUNET_NO_ROW_GEMM") == nullptr) {
+      if (use_row_gemm) {
         RUN(c, K_GEMM, 8.0 * M * dim * dim, 12.0 * M * dim + 8.0 * dim * dim,
             row_gemm_residual_launch(mlp.fc2.w, mlp.fc2.b, dim, 4 * dim, Hd, x_out, x_out, M, c.stream));   // :22, :262
       } else {
@@ -400,6 +411,7 @@ struct UpPack {
 struct TailPack {
   UpPack up;
   int E = 0, OC = 0, NT = 0, H = 0, W = 0;
+  bool fused = false;   // tail_up_fused instead of two GEMMs (decided at pre-pack)
   Linear gp, gb;
   int pack(Arena& ar, const Params& P, const std::string& up_pre, const std::string& out_key, int E_, int OC_, int H_, int W_,
            cudaStream_t s) {
@@ -414,6 +426,7 @@ struct TailPack {
     SUNET_TRY(ar.alloc_t(&gb.w, static_cast<size_t>(NT) * E));
     SUNET_TRY(fold_tail_taps(wo, up.Ap, gp.w, OC, E, NT, s));
     SUNET_TRY(fold_tail_taps(wo, up.Ab, gb.w, OC, E, NT, s));
+    fused = tail_up_fused_supported(E, NT) && getenv("SUNET_NO_FUSED_TAIL") == nullptr;
     return 0;
   }
   int forward(Ctx& c, const __half* x, void* out, int B) const {
@@ -421,7 +434,6 @@ struct TailPack {
     const int64_t M = static_cast<int64_t>(B) * H * W;
     __half *Pb, *Bb;
     float *Qp, *Rb;
-    const bool fused = tail_up_fused_supported(E, NT) && getenv("SUNET_NO_FUSED_TAIL") == nullptr;
     SUNET_TRY(c.sc.take_t(&Pb, fused ? 0 : M * 16 * E));
     SUNET_TRY(c.sc.take_t(&Qp, M * 16 * NT));
     SUNET_TRY(c.sc.take_t(&Bb, M * E));
@@ -718,6 +730,38 @@ int sunet_swin_block_fwd(sunet_handle_t h, const float* x, int batch, float* out
   });
 }
 
+size_t sunet_swin_block_f16_workspace_bytes(sunet_handle_t h, int batch) {
+  Handle* base = reinterpret_cast<Handle*>(h);
+  if (!base || base->kind != "swin_block") { fail(SUNET_E_ARG, "handle is not a swin_block"); return 0; }
+  const BlockPack& p = static_cast<BlockHandle*>(base)->p;
+  Ctx dry;
+  dry.sc.dry = true;
+  if (p.forward(dry, nullptr, nullptr, batch)) return 0;
+  return dry.sc.peak + 256;
+}
+
+int sunet_swin_block_f16(sunet_handle_t h, const void* x, int batch, int part, void* out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  GET_HANDLE(BlockHandle, bh, h, "swin_block");
+  const BlockPack& p = bh->p;
+  if (!x || !out || !workspace) return fail(SUNET_E_ARG, "sunet_swin_block_f16: null pointer");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SUNET_E_ALIGN, "sunet_swin_block_f16: workspace must be 256-byte aligned");
+  if (batch <= 0) return fail(SUNET_E_SHAPE, "sunet_swin_block_f16: batch %d", batch);
+  if (part != 0 && part != 1) return fail(SUNET_E_ARG, "sunet_swin_block_f16: part %d (0 whole block, 1 attention part)", part);
+  Ctx c;
+  c.stream = static_cast<cudaStream_t>(stream);
+  c.sc.base = static_cast<uint8_t*>(workspace);
+  c.sc.cap = workspace_bytes;
+  const __half* xi = static_cast<const __half*>(x);
+  __half* xo = static_cast<__half*>(out);
+  if (part == 0) return p.forward(c, xi, xo, batch);
+  const int64_t M = static_cast<int64_t>(batch) * p.H * p.W;
+  __half *T, *QKV;
+  SUNET_TRY(c.sc.take_t(&T, p.use_af ? 0 : M * p.dim));
+  SUNET_TRY(c.sc.take_t(&QKV, p.use_af ? 0 : M * 3 * p.dim));
+  return p.attention_part(c, xi, xo, T, QKV, batch);
+}
+
 int sunet_window_attention_fwd(sunet_handle_t h, const float* x, int64_t num_windows, const float* mask, int mask_nw, float* out,
                                void* stream) {
   GET_HANDLE(AttnHandle, ah, h, "window_attention");
@@ -941,6 +985,34 @@ int sunet_gemm_f16(const void* A, const void* W, const float* bias, void* C, int
   a.C = C; a.ldc = N;
   if (act == ACT_PRELU) return fail(SUNET_E_ARG, "sunet_gemm_f16: PReLU not exposed here");
   return gemm_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int sunet_layernorm_f16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, void* out, void* stream) {
+  if (!x || !out || !gamma || !beta) return fail(SUNET_E_ARG, "sunet_layernorm_f16: null pointer");
+  if (rows <= 0 || C <= 0 || C % 8) return fail(SUNET_E_SHAPE, "sunet_layernorm_f16: rows %lld, C %d (C must be a multiple of 8)", (long long)rows, C);
+  return layernorm_f16(static_cast<const __half*>(x), C, static_cast<__half*>(out), C, gamma, beta, rows, C, static_cast<cudaStream_t>(stream));
+}
+
+int sunet_concat_linear_f16(const void* x, const void* skip, int64_t rows, int C, const float* w, const float* b, void* out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!x || !skip || !w || !out) return fail(SUNET_E_ARG, "sunet_concat_linear_f16: null pointer");
+  if (rows <= 0 || C <= 0 || C % 16) return fail(SUNET_E_SHAPE, "sunet_concat_linear_f16: rows %lld, C %d (C must be a multiple of 16)", (long long)rows, C);
+  Arena ar;
+  Linear L;
+  L.N = C; L.K = 2 * C;
+  SUNET_TRY(ar.alloc_t(&L.w, static_cast<size_t>(C) * 2 * C));
+  SUNET_TRY(pack_weight_f16(w, L.w, C, 2 * C, 0, 1.f, s));
+  if (b) {
+    SUNET_TRY(ar.alloc_t(&L.b, C));
+    SUNET_CUDA(cudaMemcpyAsync(L.b, b, C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  Ctx c;
+  c.stream = s;
+  // cat([x, skip], -1) -> Linear(2C -> C) as two accumulating K segments: the concatenated tensor never exists (:728-729)
+  int rc = run_linear(c, L, static_cast<const __half*>(x), C, rows, out, C, ACT_NONE, nullptr, nullptr, 0, 0, static_cast<const __half*>(skip), C, C);
+  cudaError_t e = cudaStreamSynchronize(s);   // the pack buffers are freed when `ar` goes out of scope
+  if (!rc && e != cudaSuccess) rc = fail((int)e, "sunet_concat_linear_f16: %s", cudaGetErrorString(e));
+  return rc;
 }
 
 int sunet_ln_mlp_residual_f16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, const float* w1,

@@ -6,6 +6,7 @@
 // row segments (thread-per-row accesses are LSU-bound).
 #include "proj_ln.cuh"
 
+#include "device.h"
 #include "error.h"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -282,10 +283,10 @@ __global__ void __launch_bounds__(THREADS, 1)
 template <int C, int KTOT, bool LN>
 int launch_t(const ProjLnPack& pk, const __half* A, const __half* R, __half* X1, __half* T, int64_t M, cudaStream_t stream) {
   using K = Cfg<C, KTOT>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute((proj_ln_kernel<C, KTOT, LN>), cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    configured = true;
+    once.done();
   }
   alignas(64) CUtensorMap tmA, tmW;
   SUNET_TRY(make_tmap_2d_f16(&tmA, A, KTOT, M, KTOT, TILE_M));
@@ -293,9 +294,7 @@ int launch_t(const ProjLnPack& pk, const __half* A, const __half* R, __half* X1,
   Params p;
   p.R = R; p.X1 = X1; p.T = T; p.bias = pk.bias; p.gamma = pk.gamma; p.beta = pk.beta; p.M = M;
   p.tiles = (M + TILE_M - 1) / TILE_M;
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const int sms = device_sms();
   const unsigned grid = static_cast<unsigned>(p.tiles < sms ? p.tiles : sms);
   SUNET_CUDA(launch_pdl(proj_ln_kernel<C, KTOT, LN>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmA, tmW, p));
   SUNET_CHECK_LAUNCH();

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "device.h"
 #include "error.h"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -385,15 +386,12 @@ bool tail_up_fused_supported(int E_, int NT_) { return E_ == E && NT_ == NT; }
 int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p, const float* slope, float* out, int64_t M, cudaStream_t stream) {
   if (M <= 0 || M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "fused tail: bad row count %lld", (long long)M);
   if ((reinterpret_cast<uintptr_t>(T) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "fused tail: T/out must be 16-byte aligned");
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(tail_up_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    configured = true;
+    once.done();
   }
+  const int sms = device_sms();
   alignas(64) CUtensorMap tmX, tmW1, tmGp;
   SUNET_TRY(make_tmap_2d_f16(&tmX, T, E, M, E, TILE_M));
   SUNET_TRY(make_tmap_2d_f16(&tmW1, w_p0, E, SUB * E, E, E));
@@ -412,7 +410,8 @@ int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p,
   prm.out = out;
   prm.M = M;
   prm.tiles = (M + TILE_M - 1) / TILE_M;
-  prm.split = getenv("SUNET_TAIL_NO_SPLIT") == nullptr;   // measured: 295 -> 224 us (tools/ab_split.sh)
+  static const bool no_split = getenv("SUNET_TAIL_NO_SPLIT") != nullptr;   // read once per process
+  prm.split = !no_split;   // measured: 295 -> 224 us (tools/ab_split.sh)
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   SUNET_CUDA(launch_pdl(tail_up_fused_kernel, dim3(grid), dim3(THREADS), SMEM, stream, tmX, tmW1, tmGp, prm));
 #if SUNET_KERNEL_TIMING

@@ -41,14 +41,43 @@ def window_reverse(windows, window_size, H, W):
 
 
 class _Packed(nn.Module):
-    """Owns the pre-packed device handle of a module and keeps it in sync with the fp32 parameters."""
+    """Owns the pre-packed device handle of a module and keeps it in sync with the fp32 parameters.
+
+    The handle is a raw pointer into libsunet_b200 (device weights behind it): it must never be shared between two Python objects.
+    Everything that clones a module's ``__dict__`` - ``copy.copy`` / ``copy.deepcopy``, pickling (``torch.save(model)``),
+    ``nn.DataParallel`` replicas (train.py:89 wraps the model in one) - therefore gets an EMPTY handle slot and packs its own on
+    its first forward."""
 
     _kind = None
+    _TRANSIENT = ("_sunet_handle", "_sunet_key", "_sunet_named", "_workspaces")
 
     def __init__(self):
         super().__init__()
-        self.__dict__["_sunet_handle"] = None
-        self.__dict__["_sunet_key"] = None
+        self._reset_transient()
+
+    def _reset_transient(self):
+        d = self.__dict__
+        d["_sunet_handle"] = None
+        d["_sunet_key"] = None
+        d["_sunet_named"] = None
+        if "_workspaces" in d:
+            d["_workspaces"] = {}
+
+    def __getstate__(self):          # pickle, copy.copy, copy.deepcopy (via __reduce_ex__)
+        state = self.__dict__.copy()
+        for k in self._TRANSIENT:
+            if k in state:
+                state[k] = {} if k == "_workspaces" else None
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_transient()
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._reset_transient()
+        return replica
 
     def _pack_args(self):  # -> (iargs, fargs)
         raise NotImplementedError
@@ -62,8 +91,22 @@ class _Packed(nn.Module):
                 sd[k] = b
         return list(sd.items())
 
+    def _apply(self, fn, *args, **kwargs):   # .to() / .cuda() / .half(): the cached tensor list is stale afterwards
+        self.__dict__["_sunet_named"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_sunet_named"] = None
+        return super().load_state_dict(*args, **kwargs)
+
     def _handle(self):
-        named = self._named_tensors()
+        # the (name, tensor) list is cached: walking 867 parameters through named_parameters() costs more than a batch-1 forward.
+        # In-place updates bump ``_version`` and re-assigned ``.data`` changes ``data_ptr``: both are seen by the key below;
+        # replacing a Parameter OBJECT needs ``invalidate_pack()`` (load_state_dict / .to() do it themselves).
+        named = self._sunet_named
+        if named is None:
+            named = self._named_tensors()
+            self.__dict__["_sunet_named"] = named
         if not named or not named[0][1].is_cuda:
             raise RuntimeError(f"{type(self).__name__}: parameters must live on a CUDA device (call .cuda()); there is no CPU path")
         key = tuple((t.data_ptr(), t._version) for _, t in named)
@@ -74,10 +117,17 @@ class _Packed(nn.Module):
             self.__dict__["_sunet_key"] = key
         return ctypes.c_void_p(self._sunet_handle)
 
+    def invalidate_pack(self):
+        """Forget the cached parameter list and the device pack (call after replacing a Parameter object by hand)."""
+        self._release()
+        self.__dict__["_sunet_named"] = None
+        self.__dict__["_sunet_key"] = None
+
     def _release(self):
-        if self.__dict__.get("_sunet_handle"):
-            _lib.destroy(self._sunet_handle)
+        h = self.__dict__.get("_sunet_handle")
+        if h:
             self.__dict__["_sunet_handle"] = None
+            _lib.destroy(h)
 
     def __del__(self):
         try:
@@ -520,6 +570,10 @@ class SUNet(_Packed):
         ws = self._workspace(handle, B, x.device)
         if out is None:
             out = torch.empty(B, self.out_chans, H, W, device=x.device, dtype=torch.float32)
+        elif (not isinstance(out, torch.Tensor) or out.dtype != torch.float32 or out.device != x.device or not out.is_contiguous()
+              or out.numel() != B * self.out_chans * H * W):
+            raise RuntimeError(f"SUNet.forward: out must be a contiguous float32 tensor of {B * self.out_chans * H * W} elements "
+                               f"(B, out_chans, H, W) on {x.device}")
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().sunet_forward(handle, _ptr(x), C, B, self.max_chunk, _ptr(out), _ptr(ws), ws.numel(),
                                                 _lib.stream_ptr(x.device)))

@@ -60,9 +60,11 @@ def finish(acc, h, w, kernel=256, stride=128):
 
 
 @torch.no_grad()
-def denoise_any_resolution(model, img, kernel=256, stride=128, tile_batch=64, rank=0, world_size=1):
+def denoise_any_resolution(model, img, kernel=256, stride=128, tile_batch=64, rank=0, world_size=1, events=None):
     """img (1, C, h, w) fp32 CUDA in [0,1] -> restored (1, C_out, h, w), clamped to [0,1] (valid on rank 0).
-    Tiles are sharded contiguously over ranks; each rank needs the full input image."""
+    Tiles are sharded contiguously over ranks; each rank needs the full input image.
+    ``events`` (optional dict) receives CUDA events recorded on the current stream around the one collective of the path:
+    'reduce_begin' / 'reduce_end' (+ 'reduce_bytes'), so a caller can report the time spent in the canvas reduce."""
     img = _lib.require_cuda(img, "img")
     _, _, h, w = img.shape
     X, n = canvas_geometry(h, w, kernel, stride)
@@ -76,7 +78,14 @@ def denoise_any_resolution(model, img, kernel=256, stride=128, tile_batch=64, ra
         c_out = getattr(getattr(model, "swin_unet", model), "out_chans", 1)
         acc = torch.zeros(c_out, X, X, device=img.device, dtype=torch.float32)
     if world_size > 1:
+        if events is not None:
+            events["reduce_begin"] = torch.cuda.Event(enable_timing=True)
+            events["reduce_end"] = torch.cuda.Event(enable_timing=True)
+            events["reduce_bytes"] = acc.numel() * 4
+            events["reduce_begin"].record()
         dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+        if events is not None:
+            events["reduce_end"].record()
         if rank != 0:
             return None
     return finish(acc, h, w, kernel, stride)

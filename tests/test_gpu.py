@@ -444,3 +444,154 @@ def test_forward_is_bit_reproducible(dev, model_init):
     ref = model_init(x).clone()
     for _ in range(40):
         assert torch.equal(model_init(x), ref)
+
+
+# ---------------------------------------------------------------- round 2: the configs as written
+def test_batch64_distinct_images_vs_live_oracle(dev, model_init):
+    """BASELINE config 2 as written: 64 DISTINCT AWGN sigma=50 images (seed 1) in one batch against the CPU oracle run live
+    on the same inputs (the oracle is pinned to the reference to <= 2e-5, tests/test_oracle.py).  Bars: max-abs <= 2e-3 over
+    the whole batch and |dPSNR| <= 0.02 dB for EVERY image."""
+    noisy, clean = Wt.awgn_input(64, seed=1)
+    out = model_init(noisy.to(dev)).cpu()
+    sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="init")
+    torch.set_num_threads(max(1, (torch.get_num_threads() or 1)))
+    with torch.no_grad():
+        ref = torch.cat([O.sunet_model_forward(sd, noisy[i:i + 8]) for i in range(0, 64, 8)], 0)
+    report("sunet_model B=64 distinct images", out, ref, MODEL_TOL, relative=False)
+    tgt = Wt.luminance(clean)
+    worst = 0.0
+    for i in range(64):
+        d = abs(O.torch_psnr(out[i:i + 1], tgt[i:i + 1]).item() - O.torch_psnr(ref[i:i + 1], tgt[i:i + 1]).item())
+        worst = max(worst, d)
+    print(f"[parity] sunet_model B=64 distinct images: worst per-image |dPSNR| {worst:.5f} dB")
+    assert worst <= PSNR_TOL
+    # and the two images the committed reference golden holds are the first two of this batch
+    g = load_golden("sunet_model_init.npz")
+    report("sunet_model B=64 slots 0-1 vs reference golden", out[:2], torch.from_numpy(g["output"]), MODEL_TOL, relative=False)
+
+
+def test_whole_model_vs_reference_golden_outlier(dev):
+    """Trained-checkpoint magnitudes (oracle/weights.py style "outlier": LayerNorm gains x50 on three channels of every block,
+    one residual-stream channel carried at +300 where the fp16 ulp is 0.25): the fp16 token stream and fp16 MMA operands must
+    still meet the whole-model bar against the UNMODIFIED reference's output (tests/golden/sunet_model_outlier.npz)."""
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    g = load_golden("sunet_model_outlier.npz")
+    assert float(g["stream_max"]) > 250.0
+    m = SUNet_model(DEFAULT_OPT)
+    m.load_state_dict(Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="outlier"), strict=True)
+    m = m.to(dev).eval()
+    noisy, clean = Wt.awgn_input(2, seed=1)
+    out = m(noisy.to(dev))
+    ref = torch.from_numpy(g["output"])
+    assert torch.isfinite(out).all()
+    report("sunet_model outlier (stream max |x| %.0f)" % float(g["stream_max"]), out, ref, MODEL_TOL, relative=False)
+    d = psnr_delta(out, ref, clean)
+    print(f"[parity] sunet_model outlier: |dPSNR| {d:.4f} dB")
+    assert d <= PSNR_TOL
+
+
+def _f16_call(dev, fn, *args):
+    from sunet_tf_b200 import _lib
+    _lib.check(getattr(_lib.load(), fn)(*args, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("inx,dim", [(1, 384), (2, 192), (3, 96)])
+def test_concat_back_dim_vs_reference_golden(dev, inx, dim):
+    """concat_back_dim[inx] (SUNet_detail.py:652-654, :728-729): cat([x, skip], -1) -> Linear(2C -> C), here one tcgen05 GEMM
+    with two K segments, against the reference model's own member module (tests/golden/modules_r2.npz)."""
+    g = load_golden("modules_r2.npz")
+    ref = torch.from_numpy(g[f"concat_back_dim_{inx}"])
+    L = ref.shape[1]
+    sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="stress")
+    w = sd[f"swin_unet.concat_back_dim.{inx}.weight"].to(dev).contiguous()
+    b = sd[f"swin_unet.concat_back_dim.{inx}.bias"].to(dev).contiguous()
+    x = module_input((1, L, dim), seed=600 + inx).to(dev).half().contiguous()
+    skip = module_input((1, L, dim), seed=610 + inx).to(dev).half().contiguous()
+    out = torch.empty(L, dim, device=dev, dtype=torch.float16)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _f16_call(dev, "sunet_concat_linear_f16", p(x), p(skip), L, dim, p(w), p(b), p(out))
+    report(f"concat_back_dim[{inx}] C={dim}", out.float().cpu()[None], ref, MODULE_TOL)
+
+
+@pytest.mark.parametrize("name,key,C,rows,seed,scale,offset", [("norm", "swin_unet.norm", 768, 70, 620, 3.0, 0.5),
+                                                              ("norm_up", "swin_unet.norm_up", 96, 777, 621, 3.0, -0.25)])
+def test_final_layernorms_vs_reference_golden(dev, name, key, C, rows, seed, scale, offset):
+    """norm (SUNet_detail.py:677, :718) and norm_up (:678, :732) against the reference model's member modules."""
+    g = load_golden("modules_r2.npz")
+    ref = torch.from_numpy(g[name])
+    sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="stress")
+    gam, bet = sd[key + ".weight"].to(dev).contiguous(), sd[key + ".bias"].to(dev).contiguous()
+    x = (module_input((1, rows, C), seed=seed, scale=scale) + offset).to(dev).half().contiguous()
+    out = torch.empty(rows, C, device=dev, dtype=torch.float16)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _f16_call(dev, "sunet_layernorm_f16", p(x), rows, C, p(gam), p(bet), p(out))
+    report(f"{name} C={C}", out.float().cpu()[None], ref, MODULE_TOL)
+
+
+def test_swin_block_f16_entry_matches_fp32_entry(dev):
+    """sunet_swin_block_f16 (the fp16-stream form the whole model runs, used by the config-4 microbenchmark) against the fp32
+    module entry point on the same block: part 0 must agree with SwinTransformerBlock.forward up to the input/output casts."""
+    from sunet_tf_b200 import SwinTransformerBlock, _lib
+    for dim, G, shift in ((96, 16, 4), (384, 16, 0), (768, 16, 4)):
+        blk = load_sd(SwinTransformerBlock(dim, (G, G), 8, window_size=8, shift_size=shift, qk_scale=8),
+                      Wt.synth_state_dict(Wt.block_spec("", dim, G, G, shift), seed=dim + shift, style="stress"), dev)
+        x = module_input((2, G * G, dim), seed=42 + dim).to(dev)
+        ref = blk(x)
+        xh = x.half().contiguous()
+        lib = _lib.load()
+        h = blk._handle()
+        nbytes = lib.sunet_swin_block_f16_workspace_bytes(h, 2)
+        assert nbytes > 0
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty_like(xh)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(lib.sunet_swin_block_f16(h, p(xh), 2, 0, p(out), p(ws), nbytes, _lib.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(2, G * G, dim).float(), ref), f"dim {dim}: fp16 entry differs from the fp32 entry"
+        # the attention part alone runs and stays finite (its value is covered through the block goldens)
+        _lib.check(lib.sunet_swin_block_f16(h, p(xh), 2, 1, p(out), p(ws), nbytes, _lib.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all()
+
+
+def test_any_resolution_2048_vs_oracle_tile_subset_and_fold(dev):
+    """BASELINE config 5 at its full size (2048 x 2048, 225 tiles): the device tile pipeline against the oracle on a subset of
+    tiles (corner, edge, interior, last - the oracle needs ~0.2 s per tile) and against the oracle's restatement of the
+    reference fold / normalise / crop / clamp (demo_any_resolution.py:125-139) over ALL 225 tile outputs."""
+    from sunet_tf_b200 import SUNet, tiles
+    size = 2048
+    sd = Wt.synth_state_dict(Wt.sunet_spec(pre="", out_chans=3), seed=3, style="init")
+    net = SUNet(img_size=256, patch_size=4, in_chans=3, out_chans=3, embed_dim=96, depths=[8] * 4, num_heads=[8] * 4, window_size=8,
+                mlp_ratio=4.0, qkv_bias=True, qk_scale=8)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    gen = torch.Generator().manual_seed(4)
+    clean = torch.rand(1, 3, size, size, generator=gen)
+    noisy = torch.round(torch.clamp(clean + torch.randn(1, 3, size, size, generator=gen) * (50 / 255.0), 0, 1) * 255) / 255
+    X, n = tiles.canvas_geometry(size, size)
+    assert (X, n * n) == (2048, 225)
+    img = noisy.to(dev)
+    dt = tiles.extract_tiles(img, 0, n * n)
+    ot, _, oX = O.overlapped_square(noisy)
+    assert oX == X and torch.equal(dt.cpu(), ot)                      # 225 tiles, bit-exact extraction
+    outs = torch.cat([net(dt[i:i + 64]) for i in range(0, n * n, 64)], 0)
+    subset = [0, 7, 14, 112, 224]
+    arch = dict(O.DEFAULT_ARCH)
+    with torch.no_grad():
+        ref = O.sunet_forward(sd, ot[subset], arch, pre="")
+    report("any-resolution 2048: tiles %s vs oracle" % subset, outs[subset], ref, MODEL_TOL, relative=False)
+    full = tiles.denoise_any_resolution(net, img, tile_batch=64)
+    folded = O.fold_tiles(outs.cpu(), X, size, size, 256, 128)
+    report("any-resolution 2048: device fold vs oracle fold of the same 225 tile outputs", full, folded, 1e-6, relative=False)
+    # tile ranges of 8 ranks cover the 225 tiles exactly once; folding them rank by rank gives the same canvas
+    from sunet_tf_b200.shard import tile_range
+    acc, seen = None, 0
+    for r in range(8):
+        lo, hi = tile_range(n * n, r, 8)
+        assert lo == seen and 28 <= hi - lo <= 29
+        seen = hi
+        acc = tiles.fold_tiles(outs[lo:hi].contiguous(), lo, size, size, acc)
+    assert seen == n * n
+    assert torch.allclose(tiles.finish(acc, size, size), full, atol=1e-6)

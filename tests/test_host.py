@@ -164,3 +164,37 @@ def test_u8_and_eval_entry_points_reject_cpu_tensors():
         m.forward_u8(torch.zeros(1, 256, 256, 3, dtype=torch.uint8))
     with pytest.raises(RuntimeError):
         m.forward_eval(torch.zeros(1, 3, 256, 256), torch.zeros(1, 3, 256, 256))
+
+
+# ---------------------------------------------------------------- the device pack handle is never shared between objects
+def test_pack_handle_is_not_copied_by_deepcopy_pickle_or_dataparallel(monkeypatch):
+    """copy.deepcopy / pickle / nn.DataParallel replicas clone a module's __dict__; each clone must start with an empty handle
+    slot, and dropping a clone must not destroy the source's handle (use-after-free / double free otherwise)."""
+    import copy
+    import pickle
+
+    from sunet_tf_b200 import _lib, modules
+    destroyed = []
+    monkeypatch.setattr(_lib, "destroy", lambda h: destroyed.append(h))
+    blk = modules.SwinTransformerBlock(96, (8, 8), 8, window_size=8, shift_size=0, qk_scale=8)
+    blk.__dict__["_sunet_handle"] = 0xDEAD0   # as if packed
+    blk.__dict__["_sunet_key"] = ("k",)
+    for clone in (copy.deepcopy(blk), copy.copy(blk), pickle.loads(pickle.dumps(blk)), blk._replicate_for_data_parallel()):
+        assert clone.__dict__["_sunet_handle"] is None and clone.__dict__["_sunet_key"] is None
+        assert clone.attn.__dict__["_sunet_handle"] is None
+        clone._release()
+        del clone
+    assert destroyed == [], destroyed
+    assert blk.__dict__["_sunet_handle"] == 0xDEAD0
+    m = SUNet_model(DEFAULT_OPT)
+    m.swin_unet.__dict__["_sunet_handle"] = 0xBEEF0
+    m.swin_unet.__dict__["_workspaces"][("cuda:0", 1)] = object()
+    m2 = copy.deepcopy(m)
+    assert m2.swin_unet.__dict__["_sunet_handle"] is None and m2.swin_unet.__dict__["_workspaces"] == {}
+    assert set(m2.state_dict()) == set(m.state_dict())
+    del m2
+    assert destroyed == []
+    m.swin_unet._release()
+    assert destroyed == [0xBEEF0] and m.swin_unet.__dict__["_sunet_handle"] is None
+    blk._release()
+    assert destroyed == [0xBEEF0, 0xDEAD0]
