@@ -81,6 +81,9 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
+    override = os.environ.get("SUNET_LIB_PATH")   # A/B experiments (tools/ab_variants.py): another build of the SAME library
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing:
         try:
             path = _build.build()

@@ -54,8 +54,14 @@ struct Cfg {
   static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;  // k-steps in the last fc1 k-block
   static constexpr int NXBUF = C <= 96 ? 2 : 1;            // token-tile buffers
   static constexpr int NYBUF = C <= 128 ? 2 : 1;           // fc2 accumulators in TMEM
-  static constexpr int R1 = 3;                             // fc1 weight ring: [128 rows][64] k-blocks
-  static constexpr int R2 = C <= 96 ? 3 : 2;               // fc2 weight ring: [C rows][64] k-blocks
+#ifndef SUNET_MLP_R1_96
+#define SUNET_MLP_R1_96 3
+#endif
+#ifndef SUNET_MLP_R2_96
+#define SUNET_MLP_R2_96 3
+#endif
+  static constexpr int R1 = C <= 96 ? SUNET_MLP_R1_96 : 3;  // fc1 weight ring: [128 rows][64] k-blocks
+  static constexpr int R2 = C <= 96 ? SUNET_MLP_R2_96 : 2;  // fc2 weight ring: [C rows][64] k-blocks
   static constexpr int R2BYTES = C * 128;
   static constexpr int QC = C / 4;                         // output columns per epilogue column-quarter
   static constexpr int QCH = C / 32;                       // 16-byte chunks (8 fp16) per quarter
