@@ -762,345 +762,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
   }
 }
 
-// ================================================================================================ ping-pong form (C = 96)
-// Same dataflow, but the two windows of a tile belong to two independent groups of 8 warps that never meet at a block-wide barrier:
-// each group runs gather -> LayerNorm -> QKV MMA -> drain -> core -> scatter for ITS window (named barrier 1 + group, 256 threads),
-// and the groups run half a period apart, so the exponentials / FMAs of one group's core issue under the TMEM-load, cp.async and
-// global-store latencies of the other group's drain, gather and scatter (the single-group kernel runs those phases back to back on
-// all 16 warps: 38% issue utilisation, 18% tensor pipe).  What makes the split possible:
-//   * tcgen05.mma with M = 64 writes row r of its tile to TMEM lane 32 (r / 16) + (r % 16): half of every lane quadrant.  Group 0
-//     accumulates into lanes +0..15, group 1 into lanes +16..31 of the SAME 288 columns, each from its own 64 rows of the token tile
-//     (the qkv weights are loaded once and shared).  An M = 64 instruction costs the tensor pipe as much as an M = 128 one, but the
-//     pipe is 80% idle here;
-//   * tcgen05.ld.16x256b reads 16 lanes x 8 columns per warp in the mma.sync accumulator layout (thread t: rows t/4 and t/4 + 8,
-//     columns 2 (t%4), +1), so warp w of a group (lane quadrant w & 3, column half w >> 2) drains window rows 16 (w & 3) .. + 15
-//     with 32-bit conflict-free operand stores;
-//   * everything else (gather / LayerNorm / core / scatter) already mapped warps 8g .. 8g+7 to window g.
-#ifndef SUNET_AF_PP
-#define SUNET_AF_PP 1
-#endif
-
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// One 16-row x 8-column block B (compile-time, columns 8B .. 8B+7 of the 288 accumulator columns) of the fragment registers
-// v[0..3] = (row g, cols 2tq, +1), (row g + 8, same cols): + bias -> fp16 pair -> operand tile of (q|k|v, head).
-// The head / chunk / byte position of columns 8B + 2tq depends on tq only through the three residues of 8B mod 12: off3[B % 3].
-template <int B>
-__device__ __forceinline__ void pp_store_block(const uint32_t* v, const float* bf2, uint32_t dst_row, const uint32_t (&off3)[3]) {
-  constexpr int n0 = 8 * B, m = n0 / 96, head0 = (n0 % 96) / 12;
-  constexpr int UNIT = 64 * 32, NU = 16;
-  const float2 b2 = *reinterpret_cast<const float2*>(bf2 + n0);
-  const uint32_t dst = dst_row + (m * NU + head0) * UNIT + off3[B % 3];
-  sts32(dst, pack_half2(__uint_as_float(v[0]) + b2.x, __uint_as_float(v[1]) + b2.y));
-  sts32(dst + 8 * 32, pack_half2(__uint_as_float(v[2]) + b2.x, __uint_as_float(v[3]) + b2.y));
-}
-template <int B0, int NB>
-__device__ __forceinline__ void pp_store_blocks(const uint32_t* v, const float* bf2, uint32_t dst_row, const uint32_t (&off3)[3]) {
-  if constexpr (NB > 0) {
-    pp_store_block<B0>(v, bf2, dst_row, off3);
-    pp_store_blocks<B0 + 1, NB - 1>(v + 4, bf2, dst_row, off3);
-  }
-}
-// drain of column half H (blocks 18 H .. 18 H + 17) for the 16 rows of this warp: 4 loads of 4 blocks + 1 load of 2 blocks,
-// the next load in flight while the previous one is converted and stored
-template <int H>
-__device__ __forceinline__ void pp_drain_half(uint32_t t_addr, const float* bf2, uint32_t dst_row, const uint32_t (&off3)[3]) {
-  constexpr int B0 = 18 * H;
-  uint32_t va[16], vb[16];
-  tmem_ld_16x256b_x4(t_addr + 8 * (B0 + 0), va);
-  tmem_ld_wait();
-  tmem_ld_16x256b_x4(t_addr + 8 * (B0 + 4), vb);
-  pp_store_blocks<B0 + 0, 4>(va, bf2, dst_row, off3);
-  tmem_ld_wait();
-  tmem_ld_16x256b_x4(t_addr + 8 * (B0 + 8), va);
-  pp_store_blocks<B0 + 4, 4>(vb, bf2, dst_row, off3);
-  tmem_ld_wait();
-  tmem_ld_16x256b_x4(t_addr + 8 * (B0 + 12), vb);
-  pp_store_blocks<B0 + 8, 4>(va, bf2, dst_row, off3);
-  tmem_ld_wait();
-  tmem_ld_16x256b_x2(t_addr + 8 * (B0 + 16), *reinterpret_cast<uint32_t(*)[8]>(&va[0]));
-  pp_store_blocks<B0 + 12, 4>(vb, bf2, dst_row, off3);
-  tmem_ld_wait();
-  pp_store_blocks<B0 + 16, 2>(va, bf2, dst_row, off3);
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1) attn_fused_pp96_kernel(const __grid_constant__ CUtensorMap tmW, const FParams p) {
-  using K = FCfg<96, 8>;
-  constexpr int C = 96, GH = 8, RB = K::RB, HD = K::HD, MT = K::MT;
-  constexpr int GT = 256;   // threads per group
-  static_assert(K::NG == 1 && !K::RING && K::NMMA == 3 && K::NPM == 96 && MT == 4 && K::NU == 16 && RB == 32, "ping-pong form is written for C = 96");
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t w_full, mma_done[2];
-  __shared__ uint32_t tmem_base_smem;
-
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t sX = smem_u32(smem + K::OFF_X), sW = smem_u32(smem + K::OFF_W), sQKV = smem_u32(smem + K::OFF_QKV);
-  float* sTbl = reinterpret_cast<float*>(smem + K::OFF_TBL);
-  const float* sBf = reinterpret_cast<const float*>(smem + K::OFF_HC);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = warp >> 3;           // group == window of the tile
-  const int gw = warp & 7;             // warp within the group
-  const int sub = warp & 3;            // TMEM lane quadrant this warp may read
-  const int chalf = gw >> 2;           // column half drained by this warp
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmW);
-    mbar_init(&w_full, 1);
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(&tmem_base_smem, 512);
-    tmem_relinquish();
-  }
-  for (int i = tid; i < K::HEADS * 225; i += NTHREADS) {
-    const int e = i / K::HEADS, h = i - e * K::HEADS;
-    sTbl[h * TBL + e] = __ldg(p.table + i) * LOG2E;
-  }
-  for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
-  {
-    // pad columns of every operand tile: 0 for q / k, V column HD = 1.0 (softmax denominator through the MMA)
-    constexpr int PADW = (K::HD_PAD - HD) / 2;
-    for (int i = tid; i < 3 * K::NU * 64 * PADW; i += NTHREADS) {
-      const int w = i % PADW, r = (i / PADW) & 63, unit = i / (PADW * 64);
-      const int d = HD + 2 * w;
-      const uint32_t addr = sQKV + unit * K::UNIT_BYTES + op_off<RB>(r, d >> 3) + (d & 7) * 2;
-      const uint32_t val = (unit / K::NU == 2 && w == 0) ? 0x00003C00u : 0u;
-      sts32(addr, val);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-  pdl_launch_dependents();
-
-  const int nWc = p.W >> 3, nWr = p.H >> 3, nW = nWr * nWc;
-  const long long nwin = static_cast<long long>(p.B) * nW;
-  const long long tiles = (nwin + 1) >> 1;
-  const long long t_begin = tiles * blockIdx.x / gridDim.x;
-  const long long t_end = tiles * (blockIdx.x + 1) / gridDim.x;
-
-  // thread <-> token mapping inside the group (same as the single-group kernel: 4 threads per token, rows 4 apart per quarter-warp)
-  const int tk_lin = tid >> 2;
-  const int tk = (tk_lin & ~7) | ((tk_lin >> 1) & 3) | ((tk_lin & 1) << 2);
-  const int part = tid & 3;
-  const int tt = tk & 63;
-  struct Geo { int row; bool mrow, mcol; };
-  auto tile_geo = [&](long long tile) {
-    Geo gg;
-    const unsigned win = static_cast<unsigned>(tile) * 2u + grp;
-    const unsigned b = win / static_cast<unsigned>(nW);
-    const unsigned wimg = win - b * nW;
-    const unsigned wr = wimg / static_cast<unsigned>(nWc), wc = wimg - wr * nWc;
-    int r = static_cast<int>(wr) * 8 + p.shift + (tt >> 3), c = static_cast<int>(wc) * 8 + p.shift + (tt & 7);
-    if (r >= p.H) r -= p.H;
-    if (c >= p.W) c -= p.W;
-    gg.row = win < static_cast<unsigned>(nwin) ? (static_cast<int>(b) * p.H + r) * p.W + c : -1;
-    gg.mrow = p.shift > 0 && static_cast<int>(wr) == nWr - 1;
-    gg.mcol = p.shift > 0 && static_cast<int>(wc) == nWc - 1;
-    return gg;
-  };
-  auto x_chunk = [&](int j) -> uint32_t {
-    const int cg = part + 4 * j;
-    return sX + (cg >> 3) * 16384 + tk * 128 + ((static_cast<uint32_t>(cg & 7) ^ static_cast<uint32_t>(tk & 7)) << 4);
-  };
-  auto gather = [&](const Geo& gg) {
-    const __half* src = p.x + static_cast<long long>(gg.row) * C + part * 8;
-#pragma unroll
-    for (int j = 0; j < K::CPR / 4; ++j) {
-      if (gg.row >= 0) cp_async16(x_chunk(j), src + j * 32);
-      else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(x_chunk(j)), "r"(0u) : "memory");
-    }
-    cp_async_commit();
-  };
-  auto normalize = [&]() {
-    constexpr int NJ = K::CPR / 4;
-    uint4 v[NJ];
-    float k0 = 0.f;
-    {
-      const uint4 f0 = lds128(x_chunk(0));
-      k0 = __half2float(__ushort_as_half(static_cast<unsigned short>(f0.x & 0xffffu)));
-      k0 = __shfl_sync(0xffffffffu, k0, lane & ~3);
-    }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const uint4 u = lds128(x_chunk(j));
-      v[j] = u;
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(h2[t]);
-        const float d0 = f.x - k0, d1 = f.y - k0;
-        s1 += d0 + d1;
-        s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-      }
-    }
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-    const float ms = s1 * (1.0f / C);
-    const float var = fmaxf(s2 * (1.0f / C) - ms * ms, 0.f);
-    const float a = rsqrtf(var + 1e-5f);
-    const float b = -(k0 + ms) * a;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v[j]);
-      uint4 o;
-      __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(h2[t]);
-        o2[t] = __floats2half2_rn(fmaf(f.x, a, b), fmaf(f.y, a, b));
-      }
-      sts128(x_chunk(j), o);
-    }
-    fence_proxy_async_smem();
-  };
-  // group issuer (lane 0 of the group's first warp): D_g[64 x 288] = X_g[64 x 96] * W^T into lanes +16 g of every quadrant
-  const bool is_issuer = (tid & (GT - 1)) == 0;
-  auto issue_mma = [&](uint32_t it) {
-    if (it == 0) mbar_wait(&w_full, 0);
-    tc_fence_after();
-    const uint32_t idesc = umma_idesc_f16(64, K::NPM);
-    const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(16 * grp) << 16);
-#pragma unroll
-    for (int kb = 0; kb < K::KB; ++kb) {
-      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
-      const uint64_t adesc = umma_desc_sw128(sX + kb * 16384 + grp * 8192);
-#pragma unroll
-      for (int k = 0; k < ksteps; ++k)
-#pragma unroll
-        for (int m = 0; m < K::NMMA; ++m) {
-          const uint64_t bdesc = umma_desc_sw128(sW + (kb * K::NMMA + m) * K::NPM * 128);
-          umma_f16_ss(d_tmem + m * K::NPM, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-        }
-    }
-    tc_commit(&mma_done[grp]);
-  };
-
-  // core mapping (as in the single-group kernel): warp gw of group g runs head gw of window g, all four 16-row query tiles
-  const int unit = grp * GH + gw;
-  const int lg = lane >> 2, ltq = lane & 3;
-  float tb[2][2 * MT + 7];
-#pragma unroll
-  for (int e = 0; e < 2; ++e)
-#pragma unroll
-    for (int k = 0; k < 2 * MT + 7; ++k) tb[e][k] = sTbl[gw * TBL + k * 15 + (lg - 2 * ltq - e + 7)];
-  // drain constants: rows 16 sub + lg (+8) of the window, column pair 2 ltq of every 8-column block
-  const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * sub + 16 * grp) << 16);
-  const int drow = 16 * sub + lg;
-  const uint32_t dsx = static_cast<uint32_t>((drow >> 2) & 1) << 4;
-  const uint32_t dst_row = sQKV + (grp * GH) * K::UNIT_BYTES + drow * RB;
-  uint32_t off3[3];
-  off3[0] = ((0u << 4) ^ dsx) + 4 * ltq;                                                               // d = 2 tq        (chunk 0)
-  off3[1] = ltq < 2 ? ((1u << 4) ^ dsx) + 4 * ltq : K::UNIT_BYTES + ((0u << 4) ^ dsx) + 4 * (ltq - 2);  // d = 8 + 2 tq | next head, d = 2 (tq - 2)
-  off3[2] = ltq < 2 ? ((0u << 4) ^ dsx) + 8 + 4 * ltq : ((1u << 4) ^ dsx) + 4 * (ltq - 2);              // d = 4 + 2 tq
-  const float* bf2 = sBf + 2 * ltq;
-
-  Geo geo = tile_geo(t_begin);
-  if (t_begin < t_end && tid == 0) {   // the qkv weights: loaded once, shared by both groups (parameters: before the dependency wait)
-    mbar_arrive_expect_tx(&w_full, K::W_BYTES);
-#pragma unroll
-    for (int kb = 0; kb < K::KB; ++kb)
-#pragma unroll
-      for (int m = 0; m < K::NMMA; ++m)
-        tma_load_2d(smem + K::OFF_W + (kb * K::NMMA + m) * K::NPM * 128, &tmW, &w_full, kb * 64, m * K::NPM);
-  }
-  pdl_wait();
-  // group 1 starts half a period late: it waits here until group 0 has drained its first accumulator (barrier 3: 256 arrive + 256 sync)
-  if (grp == 1 && t_begin < t_end) named_bar_sync(3, NTHREADS);
-  if (t_begin < t_end) {
-    gather(geo);
-    cp_async_wait_all();
-    normalize();
-    tc_fence_before();
-    named_bar_sync(1 + grp, GT);
-    if (is_issuer) {
-      tc_fence_after();
-      issue_mma(0);
-    }
-    __syncwarp();
-  }
-  uint32_t md_ok = 0, item = 0;
-  Geo geo_next = geo;
-#pragma unroll 1
-  for (long long tile = t_begin; tile < t_end; ++tile, ++item) {
-    const bool has_next = tile + 1 < t_end;
-    mbar_wait_hint(&mma_done[grp], item & 1, md_ok);
-    tc_fence_after();
-    if (has_next) {   // the MMAs of this item have read the token rows of this group: fetch the next window into them
-      geo_next = tile_geo(tile + 1);
-      gather(geo_next);
-    }
-    if (chalf == 0) pp_drain_half<0>(t_addr, bf2, dst_row, off3); else pp_drain_half<1>(t_addr, bf2, dst_row, off3);
-    if (has_next) {
-      cp_async_wait_all();
-      normalize();
-    }
-    tc_fence_before();
-    named_bar_sync(1 + grp, GT);   // (B) operand tiles of this window complete, accumulator drained, next window normalised
-    if (grp == 0 && item == 0) named_bar_arrive(3, NTHREADS);   // releases group 1 (see above)
-    if (is_issuer && has_next) {
-      tc_fence_after();
-      issue_mma(item + 1);
-    }
-    __syncwarp();
-    if (geo.row >= 0) {
-      const uint32_t q_h = sQKV + (0 * K::NU + unit) * K::UNIT_BYTES;
-      const uint32_t k_h = sQKV + (1 * K::NU + unit) * K::UNIT_BYTES;
-      const uint32_t v_h = sQKV + (2 * K::NU + unit) * K::UNIT_BYTES;
-      if (geo.mrow || geo.mcol) attn_tiles<HD, MT, true>(q_h, k_h, v_h, 0, lane, tb, geo.mrow, geo.mcol);
-      else attn_tiles<HD, MT, false>(q_h, k_h, v_h, 0, lane, tb, false, false);
-    }
-    const uint32_t md_next = has_next ? mbar_test(&mma_done[grp], (item + 1) & 1) : 0u;
-    named_bar_sync(1 + grp, GT);   // (C) O rows of every head parked in the q tiles
-    if (geo.row >= 0) {
-      __half* dst = p.out + static_cast<long long>(geo.row) * C;
-#pragma unroll
-      for (int j = 0; j < (K::VPT + 3) / 4; ++j) {
-        const int vv = part + 4 * j;
-        const int hl = vv / K::VPH, d0 = (vv - hl * K::VPH) * K::VEC;
-        const uint32_t src = sQKV + (grp * GH + hl) * K::UNIT_BYTES + op_off<RB>(tt, d0 >> 3) + (d0 & 7) * 2;
-        uint2 o;
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(src) : "memory");
-        *reinterpret_cast<uint2*>(dst + vv * 4) = o;
-      }
-    }
-    md_ok = md_next;
-    named_bar_sync(1 + grp, GT);   // (D) q tiles free for the next drain
-    geo = geo_next;
-  }
-  if (grp == 0 && t_begin >= t_end) { /* no work: group 1 never waits either */ }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ---- pre-pack: permuted rows, W * gamma (q rows additionally * qscale), row sums of the rounded weights, folded bias
 __global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __restrict__ bqkv, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ wp, float* __restrict__ hconst, int C, int HD,
@@ -1150,18 +811,6 @@ int launch_t(const AttnFusedPack& p, const __half* x, __half* out, int B, int H,
   const long long tiles = (nwin + 1) / 2;
   const long long items = tiles * K::NG;
   const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
-  if constexpr (C == 96 && SUNET_AF_PP) {
-    static const bool no_pp = getenv("SUNET_NO_AF_PP") != nullptr;   // read once per process
-    if (!no_pp && !timing) {
-      static DeviceOnce once_pp;
-      if (once_pp.need()) {
-        SUNET_CUDA(cudaFuncSetAttribute(attn_fused_pp96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-        once_pp.done();
-      }
-      SUNET_CUDA(launch_pdl(attn_fused_pp96_kernel, dim3(grid), dim3(NTHREADS), K::SMEM, stream, p.tmW, prm));
-      return 0;
-    }
-  }
   SUNET_CUDA(launch_pdl(attn_fused_kernel<C, GH>, dim3(grid), dim3(NTHREADS), K::SMEM, stream, p.tmW, prm));
   if (timing) {   // bring-up aid: per-phase cycles averaged over CTAs, for warp 0 (MMA issuer) and the mean of the other warps
     SUNET_CUDA(cudaStreamSynchronize(stream));

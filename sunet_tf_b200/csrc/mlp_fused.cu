@@ -54,11 +54,13 @@ struct Cfg {
   static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;  // k-steps in the last fc1 k-block
   static constexpr int NXBUF = C <= 96 ? 2 : 1;            // token-tile buffers
   static constexpr int NYBUF = C <= 128 ? 2 : 1;           // fc2 accumulators in TMEM
+  // C = 96 ring depths: 2 fc1 slots + 4 fc2 / proj slots (80 KB) instead of 3 + 3 (84 KB): the fc2 ring is the one whose refill
+  // latency sits on the GELU -> fc2 -> next proj chain (measured, tools/ab_variants.py: 122.7 -> 119.5 us per launch)
 #ifndef SUNET_MLP_R1_96
-#define SUNET_MLP_R1_96 3
+#define SUNET_MLP_R1_96 2
 #endif
 #ifndef SUNET_MLP_R2_96
-#define SUNET_MLP_R2_96 3
+#define SUNET_MLP_R2_96 4
 #endif
   static constexpr int R1 = C <= 96 ? SUNET_MLP_R1_96 : 3;  // fc1 weight ring: [128 rows][64] k-blocks
   static constexpr int R2 = C <= 96 ? SUNET_MLP_R2_96 : 2;  // fc2 weight ring: [C rows][64] k-blocks
