@@ -38,12 +38,9 @@ constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 // mlp_proj_fused with two MMA-issuing threads: warp 1 issues fc1, a 19th warp proj + fc2, so neither sits behind the other's
-// barrier round trips (-DSUNET_MLP_SPLIT=0 restores the single issuer).  Measured (tools/ab_mlp_split.sh): 3.30 -> 3.21 ms over the
+// barrier round trips.  Measured against a single issuing thread (round 1, tools/ab_mlp_split.sh): 3.30 -> 3.21 ms over the
 // 32 launches of a forward; an idle 19th warp alone costs +2.6%, the split itself gains 6%.
-#ifndef SUNET_MLP_SPLIT
-#define SUNET_MLP_SPLIT 1
-#endif
-constexpr int PTHREADS = SUNET_MLP_SPLIT ? THREADS + 32 : THREADS;
+constexpr int PTHREADS = THREADS + 32;
 constexpr int FC2_WARP = 2 + EPI_WARPS;
 
 template <int C>
@@ -89,19 +86,34 @@ struct Params {
   int64_t M;
   int64_t tiles;
   long long* timing;   // optional [grid][16 epilogue warps][8] phase cycle counters (SUNET_MLP_TIMING bring-up aid)
+  long long* trace;    // optional event trace of CTA 0 (timing builds): [0] = count, then (event, clock) pairs
 };
 
 // Phase cycle counters of the epilogue warps: compiled in only with -DSUNET_KERNEL_TIMING=1 (they cost ~20 registers)
 #ifndef SUNET_KERNEL_TIMING
 #define SUNET_KERNEL_TIMING 0
 #endif
+#define TR_SLICE 400   // event-trace slots per traced thread (timing builds)
 #if SUNET_KERNEL_TIMING
-#define MLP_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; } } while (0)
-#define MLP_T_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+// event trace of CTA 0, lane 0 of the first and last epilogue warp and the issuing threads: (warp << 8 | event, clock) pairs
+// (no atomics, no loads: every traced thread appends to its own slice - warp w owns events [400 w, 400 w + 400) - with plain stores,
+// so that logging costs the issuing threads a few cycles, not a global round trip)
+__device__ __forceinline__ void tr_log(long long* tr, unsigned& n, int ev, long long t) {
+  if (n < TR_SLICE) {
+    const unsigned i = (threadIdx.x >> 5) * TR_SLICE + n;
+    tr[1 + 2 * i] = ev; tr[2 + 2 * i] = t;
+    ++n;
+  }
+}
+#define TR(ev) do { if (p.trace && blockIdx.x == 0) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | (ev), clock64()); } while (0)
+#define MLP_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; \
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 2 || (threadIdx.x >> 5) == 17)) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | (i), _t); } } while (0)
+#define MLP_T_DECL long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define MLP_T_START long long tq0 = p.timing ? clock64() : 0
 #define MLP_T_RESTART do { if (p.timing) tq0 = clock64(); } while (0)
 #else
 #define MLP_T(i) do { } while (0)
+#define TR(ev) do { } while (0)
 #define MLP_T_DECL do { } while (0)
 #define MLP_T_START do { } while (0)
 #define MLP_T_RESTART do { } while (0)
@@ -122,6 +134,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   // the compiler (LDS / STS instead of generic LD / ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#if SUNET_KERNEL_TIMING
+  unsigned trn = 0;   // events logged by this thread (event trace of CTA 0)
+#endif
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -390,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #if SUNET_KERNEL_TIMING
     if (p.timing && lane == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
+      for (int i = 0; i < 16; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 16 + i] = tacc[i];
     }
 #endif
   }
@@ -421,6 +436,7 @@ struct ProjParams {
   int64_t M;
   int64_t tiles;
   long long* timing;   // see Params::timing
+  long long* trace;    // see Params::trace
 };
 
 template <int C>
@@ -437,6 +453,9 @@ __global__ void __launch_bounds__(PTHREADS, 1)
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#if SUNET_KERNEL_TIMING
+  unsigned trn = 0;   // events logged by this thread (event trace of CTA 0)
+#endif
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -480,53 +499,76 @@ __global__ void __launch_bounds__(PTHREADS, 1)
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t i1 = 0, i2 = 0;
-      int lt = 0;
-      auto load_x = [&](int64_t tile, int ltile) {
-        const int xb = K::NXBUF == 2 ? (ltile & 1) : 0;
-        const uint32_t use = K::NXBUF == 2 ? (ltile >> 1) : ltile;
-        mbar_wait(&x_empty[xb], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&x_full[xb], K::KB1 * KBYTES);
-        for (int kb = 0; kb < K::KB1; ++kb)
-          tma_load_2d(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES, &tmX, &x_full[xb], kb * 64, static_cast<int>(tile * TILE_M));
-      };
-      auto load_r2 = [&](const CUtensorMap* tm, int col) {   // one [C rows][64] k-block of Wp or W2
-        const int s = i2 % K::R2;
-        mbar_wait(&r2_empty[s], ((i2 / K::R2) & 1) ^ 1);
-        mbar_arrive_expect_tx(&r2_full[s], K::R2BYTES);
-        tma_load_2d(smem + K::OFF_R2 + s * K::R2BYTES, tm, &r2_full[s], col, 0);
-        ++i2;
-      };
-      if (K::NXBUF == 2 && static_cast<int64_t>(blockIdx.x) < p.tiles) load_x(blockIdx.x, 0);
-      auto load_w1 = [&](int j) {
-        for (int kb = 0; kb < K::KB1; ++kb, ++i1) {
-          const int s = i1 % K::R1;
-          mbar_wait(&r1_empty[s], ((i1 / K::R1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&r1_full[s], KBYTES);
-          tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
-        }
-      };
+      // Three independent streams - token tiles, the fc1 weight ring, the proj / fc2 weight ring - each in the order its consumer
+      // reads it, served by ONE thread that never blocks on any of them: it polls the next slot of every stream and issues whatever
+      // is free.  (The in-order producer it replaces sat in the wait for a free fc2-ring slot - freed at the pace of the GELU
+      // passes - with the next tile's fc1 weights and proj weights queued behind it: 1.5k clk per tile at the first fc1 accumulator
+      // and 1.4k clk at the proj accumulator of every tile, tools/phase_timing.sh.)
       constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;
-      if (EARLY && static_cast<int64_t>(blockIdx.x) < p.tiles)
-        for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
-      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-        // same order as the MMA issuer consumes: [Wp] fc1(0) fc1(1) { fc1(j+2), fc2(j) } ... ; EARLY: the next tile's Wp before the last fc2
-        if (K::NXBUF != 2) load_x(tile, lt);
-        if (!EARLY)
-          for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
-        if (K::NXBUF == 2 && tile + gridDim.x < p.tiles) load_x(tile + gridDim.x, lt + 1);   // prefetch one tile ahead
-        load_w1(0);
-        if (K::NCH > 1) load_w1(1);
-        for (int j = 0; j < K::NCH; ++j) {
-          if (j + 2 < K::NCH) load_w1(j + 2);
-          if (EARLY && j == K::NCH - 1 && tile + gridDim.x < p.tiles)
-            for (int kb = 0; kb < K::KB1; ++kb) load_r2(&tmWp, kb * 64);
-          load_r2(&tmW2, j * NC);
-          load_r2(&tmW2, j * NC + 64);
+      const int64_t first = blockIdx.x, stride = gridDim.x;
+      const int64_t my_tiles = first < p.tiles ? (p.tiles - first + stride - 1) / stride : 0;
+      // X stream: local tile xl
+      int64_t xl = 0;
+      // r1 stream: i1 counts k-blocks over (tile, chunk, kb)
+      uint32_t i1 = 0;
+      const uint64_t n1 = static_cast<uint64_t>(my_tiles) * K::NCH * K::KB1;
+      // r2 stream: i2 counts k-blocks; (r2_lt, r2_k) = position inside the per-tile sequence; r2_pro = proj k-blocks of the first tile (EARLY)
+      uint32_t i2 = 0;
+      int64_t r2_lt = 0;
+      int r2_k = 0, r2_pro = (EARLY && my_tiles > 0) ? K::KB1 : 0;
+      // per tile, in the consumer's order: [Wp: KB1 k-blocks] then the two W2 k-blocks of every hidden chunk.  EARLY: the Wp of a
+      // tile's sequence is the NEXT tile's (absent for the last tile), the first tile's own Wp is the prologue r2_pro.
+      auto r2_has_wp = [&](int64_t ltile) -> bool { return EARLY ? (ltile + 1 < my_tiles) : true; };
+      auto r2_len = [&](int64_t ltile) -> int { return (r2_has_wp(ltile) ? K::KB1 : 0) + 2 * K::NCH; };
+      auto r2_item = [&](int64_t ltile, int k, const CUtensorMap*& tm, int& col) {
+        if (r2_has_wp(ltile)) {
+          if (k < K::KB1) { tm = &tmWp; col = k * 64; return; }
+          k -= K::KB1;
         }
+        tm = &tmW2; col = (k >> 1) * NC + (k & 1) * 64;
+      };
+      while (xl < my_tiles || i1 < n1 || r2_lt < my_tiles) {
+        bool progress = false;
+        if (xl < my_tiles) {
+          const int xb = K::NXBUF == 2 ? static_cast<int>(xl & 1) : 0;
+          const uint32_t use = static_cast<uint32_t>(K::NXBUF == 2 ? (xl >> 1) : xl);
+          if (mbar_test(&x_empty[xb], (use & 1) ^ 1)) {
+            mbar_arrive_expect_tx(&x_full[xb], K::KB1 * KBYTES);
+            for (int kb = 0; kb < K::KB1; ++kb)
+              tma_load_2d(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES, &tmX, &x_full[xb], kb * 64, static_cast<int>((first + xl * stride) * TILE_M));
+            ++xl;
+            progress = true;
+          }
+        }
+        if (i1 < n1) {
+          const int s = i1 % K::R1;
+          if (mbar_test(&r1_empty[s], ((i1 / K::R1) & 1) ^ 1)) {
+            const int kb = static_cast<int>(i1 % K::KB1), j = static_cast<int>((i1 / K::KB1) % K::NCH);
+            mbar_arrive_expect_tx(&r1_full[s], KBYTES);
+            tma_load_2d(smem + K::OFF_R1 + s * KBYTES, &tmW1, &r1_full[s], kb * 64, j * NC);
+            ++i1;
+            progress = true;
+          }
+        }
+        if (r2_lt < my_tiles) {
+          const int s = i2 % K::R2;
+          if (mbar_test(&r2_empty[s], ((i2 / K::R2) & 1) ^ 1)) {
+            const CUtensorMap* tm = &tmWp;
+            int col = 0;
+            if (r2_pro > 0) { col = (K::KB1 - r2_pro) * 64; --r2_pro; }
+            else {
+              r2_item(r2_lt, r2_k, tm, col);
+              if (++r2_k == r2_len(r2_lt)) { r2_k = 0; ++r2_lt; }
+            }
+            mbar_arrive_expect_tx(&r2_full[s], K::R2BYTES);
+            tma_load_2d(smem + K::OFF_R2 + s * K::R2BYTES, tm, &r2_full[s], col, 0);
+            ++i2;
+            progress = true;
+          }
+        }
+        if (!progress) __nanosleep(64);
       }
     }
-#if SUNET_MLP_SPLIT
   } else if (warp == 1) {
     // ------------------------------------------------------------------ fc1 issuer (the r1 ring is consumed only here)
     if (lane == 0) {
@@ -534,21 +576,45 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       uint32_t i1 = 0, g = 0;
       int lt = 0;
       uint32_t r1_ok = mbar_test(&r1_full[0], 0);
+#if SUNET_KERNEL_TIMING
+      long long it_acc[4] = {0, 0, 0, 0};
+      const long long it_start = p.timing ? clock64() : 0;
+#define ISS_T0 const long long _i0 = p.timing ? clock64() : 0
+#define ISS_T1(k) do { if (p.timing) { const long long _i1 = clock64(); it_acc[k] += _i1 - _i0; if (p.trace && blockIdx.x == 0) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | 0x40 | (k), _i1); } } while (0)
+#else
+#define ISS_T0 do { } while (0)
+#define ISS_T1(k) do { } while (0)
+#endif
       auto r1_acquire = [&]() -> int {
         const int s = i1 % K::R1;
-        mbar_wait_hint(&r1_full[s], (i1 / K::R1) & 1, r1_ok);
+        { ISS_T0; mbar_wait_hint(&r1_full[s], (i1 / K::R1) & 1, r1_ok); ISS_T1(2); }
         ++i1;
         r1_ok = mbar_test(&r1_full[i1 % K::R1], (i1 / K::R1) & 1);
         tc_fence_after();
         return s;
       };
-      auto fc1 = [&](int xb, uint32_t gg, int j, bool last) {   // H[gg & 1] = x1 * W1h_j^T   (gg: global chunk index)
+      // One barrier round trip costs this thread 350-550 clk even on a completed phase (event trace, tools/decode_mlp_trace.py), and
+      // the chain x1_ready -> h_empty -> KB1 ring slots -> issue sat on the tile-boundary critical path (2.2k clk from x1_ready to
+      // the first fc1 issue against the 2.1k clk the epilogue spends in `out`).  Everything the first chunk of a tile needs EXCEPT
+      // x1 - its accumulator and its ring slots - is therefore acquired while the epilogue is still building x1.
+      // (Only the FIRST chunk of a tile is acquired whole: for the others a ring slot is handed back as soon as its k-block has been
+      // issued, so that the refill of slot kb runs under the MMAs of kb + 1 - acquiring all of them first cost C = 192 9%.)
+      constexpr bool PRE = K::KB1 <= K::R1;   // all k-blocks of a chunk fit in the ring at once
+      auto fc1_acquire = [&](uint32_t gg, bool whole, int (&slots)[K::KB1]) {
         const uint32_t hb = gg & 1, use = gg >> 1;
-        if (use > 0) mbar_wait(&h_empty[hb], (use - 1) & 1);   // the epilogue has loaded the previous contents of this accumulator
+        if (use > 0) { ISS_T0; mbar_wait(&h_empty[hb], (use - 1) & 1); ISS_T1(1); }   // the epilogue has loaded the previous contents of this accumulator
+        if (PRE && whole) {
+#pragma unroll
+          for (int kb = 0; kb < K::KB1; ++kb) slots[kb] = r1_acquire();
+        }
+      };
+      auto fc1_issue = [&](int xb, uint32_t gg, int j, bool last, bool whole, int (&slots)[K::KB1]) {   // H[gg & 1] = x1 * W1h_j^T   (gg: global chunk index)
+        const uint32_t hb = gg & 1;
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_H + hb * 128;
+#pragma unroll
         for (int kb = 0; kb < K::KB1; ++kb) {
-          const int s = r1_acquire();
+          const int s = (PRE && whole) ? slots[kb] : r1_acquire();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
           const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
@@ -557,17 +623,32 @@ __global__ void __launch_bounds__(PTHREADS, 1)
           tc_commit(&r1_empty[s]);
         }
         tc_commit(&h_full[hb]);
+        TR(0x50 + j);
         if (last) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
+#if SUNET_KERNEL_TIMING && defined(SUNET_MLP_DIAG_HFULL)
+        if (j == 0 && p.trace && blockIdx.x == 0) { mbar_wait(&h_full[hb], (gg >> 1) & 1); TR(0x6f); }   // diagnosis: when does this chunk's accumulator complete?
+#endif
         (void)j;
       };
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
         const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
         const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
-        mbar_wait(&x1_ready[xb], xuse & 1);
-        tc_fence_after();
-        for (int j = 0; j < K::NCH; ++j) fc1(xb, g + j, j, j == K::NCH - 1);   // runs ahead as far as the two H accumulators allow
+        int slots[K::KB1];
+        fc1_acquire(g, true, slots);
+        { ISS_T0; mbar_wait(&x1_ready[xb], xuse & 1); ISS_T1(0); }
+        fc1_issue(xb, g, 0, K::NCH == 1, true, slots);
+        for (int j = 1; j < K::NCH; ++j) {   // runs ahead as far as the two H accumulators allow
+          fc1_acquire(g + j, false, slots);
+          fc1_issue(xb, g + j, j, j == K::NCH - 1, false, slots);
+        }
         g += K::NCH;
       }
+#if SUNET_KERNEL_TIMING
+      if (p.timing) {
+        it_acc[3] = clock64() - it_start;
+        for (int i = 0; i < 4; ++i) p.timing[148 * EPI_WARPS * 16 + static_cast<long long>(blockIdx.x) * 16 + i] = it_acc[i];
+      }
+#endif
     }
   } else if (warp == FC2_WARP) {
     // ------------------------------------------------------------------ proj + fc2 issuer (the r2 ring is consumed only here, in the
@@ -577,9 +658,13 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       uint32_t i2 = 0, g = 0;
       int lt = 0;
       uint32_t r2_ok = mbar_test(&r2_full[0], 0);
+#if SUNET_KERNEL_TIMING
+      long long it_acc[5] = {0, 0, 0, 0, 0};
+      const long long it_start = p.timing ? clock64() : 0;
+#endif
       auto r2_acquire = [&]() -> int {
         const int s = i2 % K::R2;
-        mbar_wait_hint(&r2_full[s], (i2 / K::R2) & 1, r2_ok);
+        { ISS_T0; mbar_wait_hint(&r2_full[s], (i2 / K::R2) & 1, r2_ok); ISS_T1(1); }
         ++i2;
         r2_ok = mbar_test(&r2_full[i2 % K::R2], (i2 / K::R2) & 1);
         tc_fence_after();
@@ -587,7 +672,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       };
       auto fc2 = [&](int yb, uint32_t gg, int j) {   // Y[yb] (+)= G_j * W2_j^T
         const uint32_t hb = gg & 1;
-        mbar_wait(&gelu_done[hb], (gg >> 1) & 1);
+        { ISS_T0; mbar_wait(&gelu_done[hb], (gg >> 1) & 1); ISS_T1(0); }
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
         for (int kb = 0; kb < 2; ++kb) {
@@ -602,14 +687,16 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         }
         tc_commit(&hs_empty[hb]);
         if (j == K::NCH - 1) tc_commit(&y_full[yb]);
+        TR(0x70 + j);
       };
       auto mma0 = [&](int lt2) {   // P = attn_out * Wp^T into the (idle) fc2 accumulator of local tile lt2
         const int xb = K::NXBUF == 2 ? (lt2 & 1) : 0;
         const uint32_t xuse = K::NXBUF == 2 ? (lt2 >> 1) : lt2;
         const int yb = K::NYBUF == 2 ? (lt2 & 1) : 0;
         const uint32_t yuse = K::NYBUF == 2 ? (lt2 >> 1) : lt2;
-        mbar_wait(&x_full[xb], xuse & 1);
-        mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
+        TR(0x5f);
+        { ISS_T0; mbar_wait(&x_full[xb], xuse & 1); ISS_T1(2); }
+        { ISS_T0; mbar_wait(&y_empty[yb], (yuse & 1) ^ 1); ISS_T1(3); }
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
         for (int kb = 0; kb < K::KB1; ++kb) {
@@ -622,124 +709,26 @@ __global__ void __launch_bounds__(PTHREADS, 1)
           tc_commit(&r2_empty[s]);
         }
         tc_commit(&p_full[yb]);
+        TR(0x60);
       };
       constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;
       if (EARLY && static_cast<int64_t>(blockIdx.x) < p.tiles) mma0(0);
       for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
         const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
-        if (!EARLY) mma0(lt);
-        for (int j = 0; j < K::NCH; ++j) {
-          if (EARLY && j == K::NCH - 1 && tile + gridDim.x < p.tiles) mma0(lt + 1);
-          fc2(yb, g + j, j);
-        }
+        // EARLY: the NEXT tile's proj goes first.  Its inputs (attn_out tile, Wp, the other fc2 accumulator - free once `out` of the
+        // previous tile has loaded it) are all there long before this tile's first GELU pass ends, so P is waiting when the epilogue
+        // gets to it (issued before the last fc2 of this tile it arrived 0.5-1.1k clk late, behind 1.7k clk of barrier round trips).
+        if (EARLY ? (tile + gridDim.x < p.tiles) : true) mma0(EARLY ? lt + 1 : lt);
+        for (int j = 0; j < K::NCH; ++j) fc2(yb, g + j, j);
         g += K::NCH;
       }
-    }
-#else
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_f16(TILE_M, NC);
-      const uint32_t idesc2 = umma_idesc_f16(TILE_M, C);
-      uint32_t i1 = 0, i2 = 0, g = 0;
-      int lt = 0;
-      // ring-slot states are looked up one slot ahead (an mbarrier test costs ~170 clk even on a completed phase; this thread's
-      // serial latency sits on the GELU -> fc2 -> next fc1 critical path)
-      uint32_t r1_ok = mbar_test(&r1_full[0], 0), r2_ok = mbar_test(&r2_full[0], 0);
-      auto r1_acquire = [&]() -> int {
-        const int s = i1 % K::R1;
-        mbar_wait_hint(&r1_full[s], (i1 / K::R1) & 1, r1_ok);
-        ++i1;
-        r1_ok = mbar_test(&r1_full[i1 % K::R1], (i1 / K::R1) & 1);
-        tc_fence_after();
-        return s;
-      };
-      auto r2_acquire = [&]() -> int {
-        const int s = i2 % K::R2;
-        mbar_wait_hint(&r2_full[s], (i2 / K::R2) & 1, r2_ok);
-        ++i2;
-        r2_ok = mbar_test(&r2_full[i2 % K::R2], (i2 / K::R2) & 1);
-        tc_fence_after();
-        return s;
-      };
-      auto fc1 = [&](int xb, uint32_t gg, int j, bool last) {   // H[gg & 1] = x1 * W1h_j^T   (gg: global chunk index)
-        const uint32_t hb = gg & 1, use = gg >> 1;
-        if (use > 0) mbar_wait(&h_empty[hb], (use - 1) & 1);   // the epilogue has loaded the previous contents of this accumulator
-        tc_fence_after();
-        const uint32_t d = tmem_base + K::TM_H + hb * 128;
-        for (int kb = 0; kb < K::KB1; ++kb) {
-          const int s = r1_acquire();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
-          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r1_empty[s]);
-        }
-        tc_commit(&h_full[hb]);
-        if (last) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
-        (void)j;
-      };
-      auto fc2 = [&](int yb, uint32_t gg, int j) {   // Y[yb] (+)= G_j * W2_j^T
-        const uint32_t hb = gg & 1;
-        mbar_wait(&gelu_done[hb], (gg >> 1) & 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
-        for (int kb = 0; kb < 2; ++kb) {
-          const int s = r2_acquire();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_HS + (hb * 2 + kb) * KBYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
-                        (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r2_empty[s]);
-        }
-        tc_commit(&hs_empty[hb]);
-        if (j == K::NCH - 1) tc_commit(&y_full[yb]);
-      };
-      auto mma0 = [&](int lt2) {   // P = attn_out * Wp^T into the (idle) fc2 accumulator of local tile lt2
-        const int xb = K::NXBUF == 2 ? (lt2 & 1) : 0;
-        const uint32_t xuse = K::NXBUF == 2 ? (lt2 >> 1) : lt2;
-        const int yb = K::NYBUF == 2 ? (lt2 & 1) : 0;
-        const uint32_t yuse = K::NYBUF == 2 ? (lt2 >> 1) : lt2;
-        mbar_wait(&x_full[xb], xuse & 1);
-        mbar_wait(&y_empty[yb], (yuse & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
-        for (int kb = 0; kb < K::KB1; ++kb) {
-          const int s = r2_acquire();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
-          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r2_empty[s]);
-        }
-        tc_commit(&p_full[yb]);
-      };
-      constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;   // see the epilogue: the next tile's proj is issued before this tile's last fc2
-      if (EARLY && static_cast<int64_t>(blockIdx.x) < p.tiles) mma0(0);
-      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-        const int xb = K::NXBUF == 2 ? (lt & 1) : 0;
-        const uint32_t xuse = K::NXBUF == 2 ? (lt >> 1) : lt;
-        const int yb = K::NYBUF == 2 ? (lt & 1) : 0;
-        if (!EARLY) mma0(lt);
-        // ---- fc1 runs two hidden chunks ahead of fc2: an fc1 accumulator is free again as soon as the epilogue has LOADED it
-        // (h_empty, early in its GELU pass), not only when the GELU output is back in shared memory (gelu_done)
-        mbar_wait(&x1_ready[xb], xuse & 1);
-        tc_fence_after();
-        fc1(xb, g, 0, K::NCH == 1);
-        if (K::NCH > 1) fc1(xb, g + 1, 1, K::NCH == 2);
-        for (int j = 0; j < K::NCH; ++j) {
-          if (j + 2 < K::NCH) fc1(xb, g + j + 2, j + 2, j + 2 == K::NCH - 1);
-          if (EARLY && j == K::NCH - 1 && tile + gridDim.x < p.tiles) mma0(lt + 1);
-          fc2(yb, g + j, j);
-        }
-        g += K::NCH;
+#if SUNET_KERNEL_TIMING
+      if (p.timing) {
+        it_acc[4] = clock64() - it_start;
+        for (int i = 0; i < 5; ++i) p.timing[148 * EPI_WARPS * 16 + static_cast<long long>(blockIdx.x) * 16 + 8 + i] = it_acc[i];
       }
-    }
 #endif
+    }
   } else if (warp < 2 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps
     const int e = warp - 2;
@@ -766,7 +755,10 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       for (int i = 0; i < K::QCH; ++i) nxt[i] = ok ? __ldg(reinterpret_cast<const uint4*>(srow + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
     };
     if (PREFETCH) fetch_shortcut(blockIdx.x);
-    uint32_t h_ok = 0;
+    // Early test results for the three waits at a tile boundary (p_full, y_full, the first h_full): a wait on an already completed
+    // phase still costs 350-450 clk - 1.4k clk right after the global stores of `out` (event trace) - a test issued a phase earlier
+    // costs nothing on the critical path.
+    uint32_t h_ok = 0, p_ok = 0, y_ok = 0;
     MLP_T_DECL;
     MLP_T_START;
     // EARLY (two token-tile buffers and two fc2 accumulators, i.e. C <= 96): x1 of the NEXT tile is built before the output of the
@@ -782,7 +774,8 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       if (!PREFETCH) fetch_shortcut(tile);
 #pragma unroll
       for (int i = 0; i < K::QCH; ++i) res[i] = nxt[i];
-      mbar_wait(&p_full[yb], yuse & 1);
+      mbar_wait_hint(&p_full[yb], yuse & 1, p_ok);
+      p_ok = 0;
       tc_fence_after();
       MLP_T(0);
       {
@@ -830,6 +823,9 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         const float nb = -mean * rstd;
         // norm2 without its affine part (folded into fc1 at pre-pack), written over the attn_out tile as the fc1 operand
         const uint32_t xs = smem_u32(smem + K::OFF_X + xb * K::KB1 * KBYTES);
+        if constexpr (EARLY) {   // `output` of the PREVIOUS local tile follows this epi0: look its accumulator up now
+          if (lt > 0) y_ok = mbar_test(&y_full[(lt - 1) & 1], ((lt - 1) >> 1) & 1);
+        }
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) {
           const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
@@ -860,7 +856,10 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
         mbar_wait_hint(&h_full[hb], ph, h_ok);
         tc_fence_after();
-        MLP_T(2);
+#if SUNET_KERNEL_TIMING
+        if (p.timing) { const long long _t = clock64(); tacc[2] += _t - tq0; tacc[8 + (j < 3 ? j : 3)] += _t - tq0; tq0 = _t;
+          if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 2 || (threadIdx.x >> 5) == 17)) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | 2, _t); }
+#endif
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);   // looked up under the TMEM load / GELU math
@@ -884,8 +883,17 @@ __global__ void __launch_bounds__(PTHREADS, 1)
           w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&p1);
         }
         MLP_T(3);
+#if SUNET_KERNEL_TIMING
+        const long long _ths0 = p.timing ? clock64() : 0;
+#endif
         mbar_wait_hint(&hs_empty[hb], ph ^ 1, hs_ok);
+#if SUNET_KERNEL_TIMING
+        if (p.timing) tacc[12 + (j < 3 ? j : 3)] += clock64() - _ths0;
+#endif
         h_ok = j + 1 < K::NCH ? mbar_test(&h_full[hb ^ 1], ((g + 1) >> 1) & 1) : 0u;   // next chunk's accumulator, looked up under the stores
+        if constexpr (EARLY) {   // last chunk: the next local tile's proj accumulator (epi0 of that tile follows)
+          if (j == K::NCH - 1 && tile + gridDim.x < p.tiles) p_ok = mbar_test(&p_full[(lt + 1) & 1], ((lt + 1) >> 1) & 1);
+        }
         const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -904,13 +912,17 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       (void)xb; (void)yb; (void)yuse;
       // ---- output: Y + b2 + x1 -> global
       {
-        mbar_wait(&y_full[yb], yuse & 1);
+        mbar_wait_hint(&y_full[yb], yuse & 1, y_ok);
+        y_ok = 0;
         tc_fence_after();
         MLP_T(6);
         const uint32_t ty = tmem_base + lane_off + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0) + quarter * K::QC;
         uint32_t y[K::QC];
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) tmem_ld8(ty + i * 8, *reinterpret_cast<uint32_t(*)[8]>(&y[i * 8]));
+        if constexpr (EARLY) {   // the first fc1 accumulator of the next local tile (its x1 was published before this `output`)
+          if (tile + gridDim.x < p.tiles) h_ok = mbar_test(&h_full[g & 1], (g >> 1) & 1);
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -972,7 +984,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
 #if SUNET_KERNEL_TIMING
     if (p.timing && lane == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 8 + i] = tacc[i];
+      for (int i = 0; i < 16; ++i) p.timing[(static_cast<long long>(blockIdx.x) * EPI_WARPS + e) * 16 + i] = tacc[i];
     }
 #endif
   }
@@ -1026,25 +1038,76 @@ __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restric
     dst[i] = __float2half_rn(src[i]);
 }
 
+static long long* mlp_trace_buf(cudaStream_t stream) {
+  static long long* buf = nullptr;
+  if (!SUNET_KERNEL_TIMING || getenv("SUNET_MLP_TRACE") == nullptr) return nullptr;
+  if (!buf && cudaMalloc(&buf, (1 + 2 * 20 * TR_SLICE) * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(buf, 0, (1 + 2 * 20 * TR_SLICE) * sizeof(long long), stream);
+  return buf;
+}
+static void mlp_trace_report(int C, const long long* buf, cudaStream_t stream) {
+  static int printed = 0;
+  if (!buf) return;
+  cudaStreamSynchronize(stream);
+  if (printed >= 2 && C == 96) return;
+  if (C == 96) ++printed;
+  static long long host[1 + 2 * 20 * TR_SLICE];
+  cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
+  const int n = 20 * TR_SLICE;
+  long long t0 = 0;
+  for (int i = 0; i < n; ++i) if (host[2 + 2 * i] != 0 && (t0 == 0 || host[2 + 2 * i] < t0)) t0 = host[2 + 2 * i];
+  fprintf(stderr, "TRACE mlp_proj_fused<%d> (t, warp, event)\n", C);
+  for (int i = 0; i < n; ++i)
+    if (host[2 + 2 * i] != 0) fprintf(stderr, "TR %lld %lld 0x%02llx\n", host[2 + 2 * i] - t0, host[1 + 2 * i] >> 8, host[1 + 2 * i] & 0xff);
+}
 static long long* mlp_timing_buf(cudaStream_t stream) {
   static long long* buf = nullptr;
   if (!SUNET_KERNEL_TIMING || getenv("SUNET_MLP_TIMING") == nullptr) return nullptr;
-  if (!buf && cudaMalloc(&buf, 148 * EPI_WARPS * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
-  cudaMemsetAsync(buf, 0, 148 * EPI_WARPS * 8 * sizeof(long long), stream);
+  if (!buf && cudaMalloc(&buf, (148 * EPI_WARPS * 16 + 148 * 16) * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(buf, 0, (148 * EPI_WARPS * 16 + 148 * 16) * sizeof(long long), stream);
   return buf;
 }
 static void mlp_timing_report(const char* what, int C, unsigned grid, const long long* buf, cudaStream_t stream) {
   if (!buf) return;
   cudaStreamSynchronize(stream);
-  static long long host[148 * EPI_WARPS * 8];
+  static long long host[148 * EPI_WARPS * 16 + 148 * 16];
   cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
-  static const char* names[8] = {"wait_x", "stats", "wait_h", "gelu", "wait_hs", "store", "wait_y", "out"};
-  double acc[8] = {0};
+  static const char* names[16] = {"wait_x", "stats", "wait_h", "gelu", "wait_hs", "store", "wait_y", "out",
+                                  "wait_h[j=0]", "wait_h[j=1]", "wait_h[j=2]", "wait_h[j>2]", "wait_hs[j=0]", "wait_hs[j=1]", "wait_hs[j=2]", "wait_hs[j>2]"};
+  double acc[16] = {0};
   for (unsigned b = 0; b < grid; ++b)
     for (int w = 0; w < EPI_WARPS; ++w)
-      for (int i = 0; i < 8; ++i) acc[i] += static_cast<double>(host[(b * EPI_WARPS + w) * 8 + i]);
+      for (int i = 0; i < 16; ++i) acc[i] += static_cast<double>(host[(b * EPI_WARPS + w) * 16 + i]);
   fprintf(stderr, "%s<%d> grid=%u cycles per epilogue warp:", what, C, grid);
-  for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %.0f", names[i], acc[i] / grid / EPI_WARPS);
+  for (int i = 0; i < 16; ++i) fprintf(stderr, " %s %.0f", names[i], acc[i] / grid / EPI_WARPS);
+  // per-CTA minimum / maximum over the 16 epilogue warps (averaged over CTAs): a wait that even the LAST warp to arrive pays is a
+  // real bubble, a wait only the first warps pay is skew between warps that share an issue port
+  fprintf(stderr, " | min/max over warps:");
+  for (int i = 0; i < 8; ++i) {
+    double mn = 0, mx = 0;
+    for (unsigned b = 0; b < grid; ++b) {
+      long long lo = host[(b * EPI_WARPS) * 16 + i], hi = lo;
+      for (int w = 1; w < EPI_WARPS; ++w) { const long long v = host[(b * EPI_WARPS + w) * 16 + i]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+      mn += lo; mx += hi;
+    }
+    fprintf(stderr, " %s %.0f/%.0f", names[i], mn / grid, mx / grid);
+  }
+  {   // total cycles per warp, and per-warp (CTA 0) wait_h to see the skew pattern
+    double tot = 0;
+    for (int i = 0; i < 8; ++i) tot += acc[i] / grid / EPI_WARPS;
+    fprintf(stderr, " | total %.0f | cta0 wait_h by warp:", tot);
+    for (int w = 0; w < EPI_WARPS; ++w) fprintf(stderr, " %lld", host[w * 16 + 2]);
+    fprintf(stderr, " | cta0 gelu by warp:");
+    for (int w = 0; w < EPI_WARPS; ++w) fprintf(stderr, " %lld", host[w * 16 + 3]);
+  }
+  // issuer threads (proj kernel): cycles spent waiting, per CTA
+  static const char* inames[16] = {"fc1:x1_ready", "fc1:h_empty", "fc1:r1_full", "fc1:total", "-", "-", "-", "-",
+                                   "fc2:gelu_done", "fc2:r2_full", "fc2:x_full", "fc2:y_empty", "fc2:total", "-", "-", "-"};
+  double iacc[16] = {0};
+  for (unsigned b = 0; b < grid; ++b)
+    for (int i = 0; i < 16; ++i) iacc[i] += static_cast<double>(host[148 * EPI_WARPS * 16 + b * 16 + i]);
+  fprintf(stderr, " | issuers:");
+  for (int i = 0; i < 16; ++i) if (inames[i][0] != '-') fprintf(stderr, " %s %.0f", inames[i], iacc[i] / grid);
   fprintf(stderr, "\n");
 }
 
@@ -1067,6 +1130,7 @@ int launch_t(const MlpFusedPack& p, const __half* x, __half* out, int64_t M, cud
   const int sms = device_sms();
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   prm.timing = mlp_timing_buf(stream);
+  prm.trace = nullptr;
   SUNET_CUDA(launch_pdl(mlp_fused_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmX, p.tmW1, p.tmW2, prm));
   mlp_timing_report("mlp_fused", C, grid, prm.timing, stream);
   return 0;
@@ -1095,8 +1159,10 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
   const int sms = device_sms();
   const unsigned grid = static_cast<unsigned>(prm.tiles < sms ? prm.tiles : sms);
   prm.timing = mlp_timing_buf(stream);
+  prm.trace = prm.timing ? mlp_trace_buf(stream) : nullptr;
   SUNET_CUDA(launch_pdl(mlp_proj_fused_kernel<C>, dim3(grid), dim3(PTHREADS), SMEM, stream, tmX, p.tmWp, p.tmW1h, p.tmW2, prm));
   mlp_timing_report("mlp_proj_fused (wait_p, epi0, wait_h, gelu, wait_hs, store, wait_y, out)", C, grid, prm.timing, stream);
+  mlp_trace_report(C, prm.trace, stream);
   return 0;
 }
 
