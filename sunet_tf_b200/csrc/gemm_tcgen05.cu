@@ -249,41 +249,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(BLOCK_M, block_n);
-      uint32_t local = 0;
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t ready = mbar_test(&full_bar[0], 0);
-      uint32_t acc_ready = mbar_test(&tmem_empty_bar[0], 1);
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const uint32_t as = local & 1;
-        const uint32_t aph = (local >> 1) & 1;
-        mbar_wait_hint(&tmem_empty_bar[as], aph ^ 1, acc_ready);   // epilogue has drained this accumulator stage
-        acc_ready = mbar_test(&tmem_empty_bar[as ^ 1], (((local + 1) >> 1) & 1) ^ 1);   // next tile's stage, looked up early
+    // MMA issuer.  The WHOLE warp runs this loop convergently and one elected lane issues: with a single-lane branch around the
+    // loop (`if (lane == 0)`) every value is thread-divergent for the compiler, which then moves each descriptor to the uniform
+    // datapath with R2UR and wraps each tcgen05.mma / commit in an ELECT loop - ~180 clk per MMA instruction, i.e. the issue thread,
+    // not the tensor pipe or the operand stream, paced every k-block (tools/gemm_dbg_big.sh: 720 clk per k-block for N = 128, 192
+    // and 256 alike with the TMA loads switched off).
+    const uint32_t idesc = umma_idesc_f16(BLOCK_M, block_n);
+    uint32_t local = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t ready = mbar_test(&full_bar[0], 0);
+    uint32_t acc_ready = mbar_test(&tmem_empty_bar[0], 1);
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const uint32_t as = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      mbar_wait_hint(&tmem_empty_bar[as], aph ^ 1, acc_ready);   // epilogue has drained this accumulator stage
+      acc_ready = mbar_test(&tmem_empty_bar[as ^ 1], (((local + 1) >> 1) & 1) ^ 1);   // next tile's stage, looked up early
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * acc_cols;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_hint(&full_bar[s], ph, ready);
+        const int s_cur = s;
+        if (++s == stages) { s = 0; ph ^= 1; }
+        ready = mbar_test(&full_bar[s], ph);   // next slot's state, looked up under this slot's MMA issue
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * acc_cols;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait_hint(&full_bar[s], ph, ready);
-          const int s_cur = s;
-          if (++s == stages) { s = 0; ph ^= 1; }
-          ready = mbar_test(&full_bar[s], ph);   // next slot's state, looked up under this slot's MMA issue
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s_cur * stage_bytes);
-          const uint32_t sb = sa + A_TILE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sb);
-          // valid K elements in this block (a K0/K1 tail shorter than 64 is zero-filled by TMA but not multiplied)
-          const int kvalid = kb < kb0 ? min(BLOCK_K, p.K0 - kb * BLOCK_K) : min(BLOCK_K, p.K1 - (kb - kb0) * BLOCK_K);
-          const int ksteps = (kvalid + 15) >> 4;
-          for (int k = 0; k < ksteps && !(p.dbg & 2); ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+        const uint32_t sa = smem_u32(smem + s_cur * stage_bytes);
+        const uint32_t sb = sa + A_TILE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sb);
+        // valid K elements in this block (a K0/K1 tail shorter than 64 is zero-filled by TMA but not multiplied)
+        const int kvalid = kb < kb0 ? min(BLOCK_K, p.K0 - kb * BLOCK_K) : min(BLOCK_K, p.K1 - (kb - kb0) * BLOCK_K);
+        const int ksteps = (p.dbg & 2) ? 0 : (kvalid + 15) >> 4;
+        if (elect_one()) {
+          // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[s_cur]);  // frees the smem slot once these MMAs have read it
+          if (kb == num_kb - 1) tc_commit(&tmem_full_bar[as]);  // accumulator of this tile complete
         }
-        tc_commit(&tmem_full_bar[as]);  // accumulator of this tile complete
+        __syncwarp();
       }
     }
   } else {
