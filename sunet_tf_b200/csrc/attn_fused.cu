@@ -515,24 +515,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       for (int m = 0; m < K::NMMA; ++m)
         tma_load_2d(smem + K::OFF_W + (kb * K::NMMA + m) * K::NPM * 128, &tmW, &w_full, kb * 64, g * K::NGC + m * K::NPM);
   };
-  auto issue_mma = [&](uint32_t it) {   // thread 0: D[128 x NGC] = X * Wg^T for work item `it`
+  // The issuing WARP runs these convergently and one elected lane issues: inside a single-thread branch every descriptor is
+  // thread-divergent for the compiler (R2UR + an ELECT loop per tcgen05.mma, ~180 clk per instruction - see gemm_tcgen05.cu).
+  auto issue_mma = [&](uint32_t it) {   // warp 0: D[128 x NGC] = X * Wg^T for work item `it`
     if (K::NG > 1 || it == 0) mbar_wait(&w_full, it & 1);   // a single head group keeps its weights for the whole kernel
     tc_fence_after();
     const uint32_t idesc = umma_idesc_f16(128, K::NPM);
+    if (elect_one()) {
 #pragma unroll
-    for (int kb = 0; kb < K::KB; ++kb) {
-      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
-      const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
+      for (int kb = 0; kb < K::KB; ++kb) {
+        const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
+        const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
 #pragma unroll
-      for (int k = 0; k < ksteps; ++k)
+        for (int k = 0; k < ksteps; ++k)
 #pragma unroll
-        for (int m = 0; m < K::NMMA; ++m) {
-          const uint64_t bdesc = umma_desc_sw128(sW + (kb * K::NMMA + m) * K::NPM * 128);
-          umma_f16_ss(tmem_base + m * K::NPM, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-        }
+          for (int m = 0; m < K::NMMA; ++m) {
+            const uint64_t bdesc = umma_desc_sw128(sW + (kb * K::NMMA + m) * K::NPM * 128);
+            umma_f16_ss(tmem_base + m * K::NPM, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+      }
+      tc_commit(&mma_done);
     }
-    tc_commit(&mma_done);
+    __syncwarp();
   };
 
   // RING mode (wide rows): the weights of a head group do not fit next to the token tile, so they stream through a ring of
@@ -548,41 +553,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     tma_load_2d(smem + K::OFF_W + slot * K::WKB_BYTES, &tmW, &rk_full[slot], kb * 64, g * K::NGC);
     ++rk_loaded;
   };
-  auto ring_mma = [&](uint32_t it) {   // D[128 x NGC] = X * Wg^T for work item `it`, k-block by k-block
-    const uint32_t idesc = umma_idesc_f16(128, K::NPM);
-    const uint32_t c0 = it * K::KB;
-    while (rk_loaded <= c0) ring_load(0u);
-    uint32_t full_ok = mbar_test(&rk_full[c0 % K::RSTAGES], (c0 / K::RSTAGES) & 1);
-#pragma unroll 1
-    for (int kb = 0; kb < K::KB; ++kb) {
-      const uint32_t c = c0 + kb, slot = c % K::RSTAGES;
-      while (rk_loaded <= c) ring_load(0u);
-      mbar_wait_hint(&rk_full[slot], (c / K::RSTAGES) & 1, full_ok);
-      // barrier states needed next are looked up now, under the MMA issue (a test costs ~170 clk even on a completed phase):
-      // the next k-block's full flag, and the empty flag of the slot the refill below will reuse
-      const uint32_t cn = c + 1;
-      full_ok = (kb + 1 < K::KB && rk_loaded > cn) ? mbar_test(&rk_full[cn % K::RSTAGES], (cn / K::RSTAGES) & 1) : 0u;
-      const bool refill = c >= 1 && rk_loaded < rk_total && rk_loaded < c + K::RSTAGES;
-      const uint32_t empty_ok = (refill && rk_loaded >= K::RSTAGES) ? mbar_test(&rk_empty[rk_loaded % K::RSTAGES], ((rk_loaded / K::RSTAGES) - 1) & 1) : 0u;
-      tc_fence_after();
-      const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
-      const uint64_t bdesc = umma_desc_sw128(sW + slot * K::WKB_BYTES);
-      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
-      for (int k = 0; k < ksteps; ++k)
-        umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-      tc_commit(&rk_empty[slot]);
-      // refill the slot used one k-block ago (its MMAs have had a k-block's time to finish)
-      if (refill) ring_load(empty_ok);
-    }
-    tc_commit(&mma_done);
-    while (rk_loaded < rk_total && rk_loaded < c0 + K::KB + K::RSTAGES - 1) ring_load(0u);   // prefetch the next item's first k-blocks
-  };
-#ifndef SUNET_AF_SPLIT
-#define SUNET_AF_SPLIT 1   // measured at C = 384 (tools/ab_af_split.sh): 55.9 -> 49.6 us per launch
-#endif
-  // RING mode with two threads (SUNET_AF_SPLIT): the ring's TMA producer is lane 0 of a second idle warp, the MMA issuer only waits
-  // for full slots, issues and commits - the k-block loop of a single producer + issuer thread (~1k clk per k-block of barrier round
-  // trips) did not fit under the core and showed up as a 10% wait for the accumulator at the top of every item.
+  // RING mode runs the ring's TMA producer (lane 0 of a second idle warp) and the MMA issuer on different warps: the issuer only
+  // waits for full slots, issues and commits - the k-block loop of a single producer + issuer thread (~1k clk per k-block of barrier
+  // round trips) did not fit under the core and showed up as a 10% wait for the accumulator at the top of every item (round 1,
+  // tools/ab_af_split.sh: 55.9 -> 49.6 us per launch at C = 384).
   auto ring_produce = [&](uint32_t upto) {   // producer thread: TMA of k-blocks [rk_loaded, min(upto, rk_total))
     while (rk_loaded < rk_total && rk_loaded < upto) ring_load(0u);
   };
@@ -599,19 +573,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       tc_fence_after();
       const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
       const uint64_t bdesc = umma_desc_sw128(sW + slot * K::WKB_BYTES);
-      const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
-      for (int k = 0; k < ksteps; ++k)
-        umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-      tc_commit(&rk_empty[slot]);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (kb < K::KB - 1 || k < K::KTAIL)
+            umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&rk_empty[slot]);
+        if (kb == K::KB - 1) tc_commit(&mma_done);
+      }
+      __syncwarp();
     }
-    tc_commit(&mma_done);
   };
   // the thread that issues TMA + MMA: lane 0 of warp 0, or in RING mode of a warp without a query tile in the core
   constexpr int ISSUER_WARP = K::RING ? K::WPU * K::GH : 0;
-  constexpr bool SPLIT = K::RING && SUNET_AF_SPLIT;
-  const bool is_producer = SPLIT && tid == (ISSUER_WARP + 1) * 32;
+  const bool is_producer = K::RING && tid == (ISSUER_WARP + 1) * 32;
   static_assert(!K::RING || (K::NU * K::WPU < 16 && ISSUER_WARP < 8), "RING mode needs an idle warp for the issuer");
-  const bool is_issuer = tid == ISSUER_WARP * 32;
+  const bool is_issuer = warp == ISSUER_WARP;   // (the whole warp; one elected lane issues)
 
   // this warp's (window, head) unit of the core pass
   const int u_hl = (warp & 7) % GH;
@@ -645,7 +622,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     if (is_producer) ring_produce(K::KB + K::RSTAGES - 1);
     if (is_issuer) {
       tc_fence_after();
-      if (SPLIT) ring_mma_only(0); else if (K::RING) ring_mma(0); else issue_mma(0);
+      if (K::RING) ring_mma_only(0); else issue_mma(0);
     }
     __syncwarp();
   }
@@ -692,7 +669,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       AF_T(8);
       if (is_producer && has_next) ring_produce((item + 2) * K::KB + K::RSTAGES - 1);
       if (is_issuer && has_next) {                     // runs on the tensor pipe while the core below runs on the CUDA cores
-        if (SPLIT) ring_mma_only(item + 1); else if (K::RING) ring_mma(item + 1); else issue_mma(item + 1);
+        if (K::RING) ring_mma_only(item + 1); else issue_mma(item + 1);
       }
       __syncwarp();
       AF_T(9);

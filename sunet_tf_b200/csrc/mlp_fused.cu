@@ -105,7 +105,7 @@ __device__ __forceinline__ void tr_log(long long* tr, unsigned& n, int ev, long 
     ++n;
   }
 }
-#define TR(ev) do { if (p.trace && blockIdx.x == 0) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | (ev), clock64()); } while (0)
+#define TR(ev) do { if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | (ev), clock64()); } while (0)
 #define MLP_T(i) do { if (p.timing) { const long long _t = clock64(); tacc[i] += _t - tq0; tq0 = _t; \
     if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 2 || (threadIdx.x >> 5) == 17)) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | (i), _t); } } while (0)
 #define MLP_T_DECL long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
@@ -571,7 +571,10 @@ __global__ void __launch_bounds__(PTHREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ fc1 issuer (the r1 ring is consumed only here)
-    if (lane == 0) {
+    // The whole warp walks the loop and waits on the barriers; one elected lane issues.  (Inside an `if (lane == 0)` every descriptor is
+    // thread-divergent for the compiler: R2UR + an ELECT loop around each tcgen05.mma / commit, ~180 clk per instruction - see
+    // gemm_tcgen05.cu.)
+    {
       const uint32_t idesc1 = umma_idesc_f16(TILE_M, NC);
       uint32_t i1 = 0, g = 0;
       int lt = 0;
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       long long it_acc[4] = {0, 0, 0, 0};
       const long long it_start = p.timing ? clock64() : 0;
 #define ISS_T0 const long long _i0 = p.timing ? clock64() : 0
-#define ISS_T1(k) do { if (p.timing) { const long long _i1 = clock64(); it_acc[k] += _i1 - _i0; if (p.trace && blockIdx.x == 0) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | 0x40 | (k), _i1); } } while (0)
+#define ISS_T1(k) do { if (p.timing) { const long long _i1 = clock64(); it_acc[k] += _i1 - _i0; if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tr_log(p.trace, trn, (static_cast<int>(threadIdx.x >> 5) << 8) | 0x40 | (k), _i1); } } while (0)
 #else
 #define ISS_T0 do { } while (0)
 #define ISS_T1(k) do { } while (0)
@@ -617,14 +620,21 @@ __global__ void __launch_bounds__(PTHREADS, 1)
           const int s = (PRE && whole) ? slots[kb] : r1_acquire();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
-          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r1_empty[s]);
+          constexpr int KS_LAST = K::KTAIL;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (kb < K::KB1 - 1 || k < KS_LAST)
+                umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r1_empty[s]);
+            if (kb == K::KB1 - 1) {
+              tc_commit(&h_full[hb]);
+              if (last) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
+            }
+          }
+          __syncwarp();
         }
-        tc_commit(&h_full[hb]);
         TR(0x50 + j);
-        if (last) tc_commit(&x_empty[xb]);   // every fc1 MMA of this tile has read x1: the buffer may be refilled
 #if SUNET_KERNEL_TIMING && defined(SUNET_MLP_DIAG_HFULL)
         if (j == 0 && p.trace && blockIdx.x == 0) { mbar_wait(&h_full[hb], (gg >> 1) & 1); TR(0x6f); }   // diagnosis: when does this chunk's accumulator complete?
 #endif
@@ -653,7 +663,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
   } else if (warp == FC2_WARP) {
     // ------------------------------------------------------------------ proj + fc2 issuer (the r2 ring is consumed only here, in the
     // producer's order: [Wp] then per chunk the two W2 k-blocks, the next tile's Wp before the last chunk when EARLY)
-    if (lane == 0) {
+    {   // (whole warp, one elected lane issues: see the fc1 issuer)
       const uint32_t idesc2 = umma_idesc_f16(TILE_M, C);
       uint32_t i2 = 0, g = 0;
       int lt = 0;
@@ -675,18 +685,24 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         { ISS_T0; mbar_wait(&gelu_done[hb], (gg >> 1) & 1); ISS_T1(0); }
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+#pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const int s = r2_acquire();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_HS + (hb * 2 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
-                        (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r2_empty[s]);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2,
+                          (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r2_empty[s]);
+            if (kb == 1) {
+              tc_commit(&hs_empty[hb]);
+              if (j == K::NCH - 1) tc_commit(&y_full[yb]);
+            }
+          }
+          __syncwarp();
         }
-        tc_commit(&hs_empty[hb]);
-        if (j == K::NCH - 1) tc_commit(&y_full[yb]);
         TR(0x70 + j);
       };
       auto mma0 = [&](int lt2) {   // P = attn_out * Wp^T into the (idle) fc2 accumulator of local tile lt2
@@ -699,16 +715,21 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         { ISS_T0; mbar_wait(&y_empty[yb], (yuse & 1) ^ 1); ISS_T1(3); }
         tc_fence_after();
         const uint32_t d = tmem_base + K::TM_Y + (K::NYBUF == 2 ? yb * 128 : 0);
+#pragma unroll
         for (int kb = 0; kb < K::KB1; ++kb) {
           const int s = r2_acquire();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R2 + s * K::R2BYTES));
-          const int ksteps = kb == K::KB1 - 1 ? K::KTAIL : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r2_empty[s]);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (kb < K::KB1 - 1 || k < K::KTAIL)
+                umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r2_empty[s]);
+            if (kb == K::KB1 - 1) tc_commit(&p_full[yb]);
+          }
+          __syncwarp();
         }
-        tc_commit(&p_full[yb]);
         TR(0x60);
       };
       constexpr bool EARLY = K::NXBUF == 2 && K::NYBUF == 2;

@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp walks the loop, one elected lane issues (a single-lane branch makes every descriptor thread-divergent
+    // for the compiler: R2UR + an ELECT loop per tcgen05.mma, ~180 clk per instruction - see gemm_tcgen05.cu)
+    {
       const uint32_t idesc = umma_idesc_f16(TILE_M, K::NH);
       int s = 0;
       uint32_t ph = 0, local = 0;
@@ -132,16 +134,19 @@ __global__ void __launch_bounds__(THREADS, 1)
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc0 = umma_desc_sw128(sa + A_BYTES);
           const uint64_t bdesc1 = umma_desc_sw128(sa + A_BYTES + K::NH * 128);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc0 + static_cast<uint64_t>(2 * k), idesc, accum);
-            umma_f16_ss(tmem_base + K::NH, adesc + static_cast<uint64_t>(2 * k), bdesc1 + static_cast<uint64_t>(2 * k), idesc, accum);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+              umma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc0 + static_cast<uint64_t>(2 * k), idesc, accum);
+              umma_f16_ss(tmem_base + K::NH, adesc + static_cast<uint64_t>(2 * k), bdesc1 + static_cast<uint64_t>(2 * k), idesc, accum);
+            }
+            tc_commit(&empty_bar[s]);
+            if (kb == K::KB - 1) tc_commit(&acc_full);
           }
-          tc_commit(&empty_bar[s]);
+          __syncwarp();
           if (++s == K::STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(&acc_full);
       }
     }
   } else {

@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues: a
+    // single-lane branch makes every descriptor thread-divergent -> R2UR + ELECT loop per tcgen05.mma, see gemm_tcgen05.cu)
+    {
       const uint32_t idesc1 = umma_idesc_f16(TILE_M, E);
       const uint32_t idesc2 = umma_idesc_f16(TILE_M, NT);
       uint32_t i1 = 0, g = 0;
@@ -155,28 +156,39 @@ __global__ void __launch_bounds__(THREADS, 1)
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_X + (xb * 2 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_R1 + s * W1KB));
-          const int ksteps = kb == 1 ? 2 : 4;   // K = 96 = 64 + 32
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&r1_empty[s]);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (kb == 0 || k < 2)   // K = 96 = 64 + 32
+                umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&r1_empty[s]);
+            if (kb == 1) {
+              tc_commit(&h_full[hb]);
+              if (last) tc_commit(&x_empty[xb]);
+            }
+          }
+          __syncwarp();
         }
-        tc_commit(&h_full[hb]);
-        if (last) tc_commit(&x_empty[xb]);
       };
       auto fc2 = [&](uint32_t gg, int j) {   // Q[:, 16 j .. 16 j + 15] = G_j * G_p^T
         const uint32_t hb = gg & 1;
         mbar_wait(&g_done[hb], (gg >> 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + TM_Y + j * NT;
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_HS + (hb * 2 + kb) * KBYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_GP + kb * NT * 128));
-          const int ksteps = kb == 1 ? 2 : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+        if (elect_one()) {
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_HS + (hb * 2 + kb) * KBYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_GP + kb * NT * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (kb == 0 || k < 2)
+                umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&hs_empty[hb]);
+          if (j == SUB - 1) tc_commit(&y_full);
         }
-        tc_commit(&hs_empty[hb]);
-        if (j == SUB - 1) tc_commit(&y_full);
+        __syncwarp();
       };
       if (p.split) {
         // fc1 only: runs ahead as far as the two H buffers allow; fc2 has its own issuing thread, so neither waits behind the
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #if SUNET_TAIL_FC1_SPLIT
   } else if (warp == FC1B_WARP) {
     // ------------------------------------------------------------------ second fc1 issuer: the odd sub-pixels (H buffer 1)
-    if (lane == 0 && p.split) {
+    if (p.split) {   // (whole warp, one elected lane issues)
       const uint32_t idesc1 = umma_idesc_f16(TILE_M, E);
       uint32_t g = 0;
       int lt = 0;
@@ -232,13 +244,19 @@ __global__ void __launch_bounds__(THREADS, 1)
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_X + (xb * 2 + kb) * KBYTES));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_R1 + s * W1KB));
-            const int ksteps = kb == 1 ? 2 : 4;
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(&r1_empty[s]);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (kb == 0 || k < 2)
+                  umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+              tc_commit(&r1_empty[s]);
+              if (kb == 1) {
+                tc_commit(&h_full[hb]);
+                if (j == SUB - 1) tc_commit(&x_empty[xb]);
+              }
+            }
+            __syncwarp();
           }
-          tc_commit(&h_full[hb]);
-          if (j == SUB - 1) tc_commit(&x_empty[xb]);
         }
         g += SUB;
       }
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #endif
   } else if (warp == FC2_WARP) {
     // ------------------------------------------------------------------ fc2 issuer (split mode)
-    if (lane == 0 && p.split) {
+    if (p.split) {   // (whole warp, one elected lane issues)
       const uint32_t idesc2 = umma_idesc_f16(TILE_M, NT);
       uint32_t g = 0;
       int lt = 0;
@@ -258,15 +276,20 @@ __global__ void __launch_bounds__(THREADS, 1)
           mbar_wait(&g_done[hb], (gg >> 1) & 1);
           tc_fence_after();
           const uint32_t d = tmem_base + TM_Y + j * NT;
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_HS + (hb * 2 + kb) * KBYTES));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_GP + kb * NT * 128));
-            const int ksteps = kb == 1 ? 2 : 4;
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t adesc = umma_desc_sw128(smem_u32(smem + OFF_HS + (hb * 2 + kb) * KBYTES));
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + OFF_GP + kb * NT * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (kb == 0 || k < 2)
+                  umma_f16_ss(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&hs_empty[hb]);
+            if (j == SUB - 1) tc_commit(&y_full);
           }
-          tc_commit(&hs_empty[hb]);
-          if (j == SUB - 1) tc_commit(&y_full);
+          __syncwarp();
         }
         g += SUB;
       }
