@@ -420,7 +420,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {   // the leader's MMA warp walks the loop convergently, one elected lane issues (see gemm_tn_f16_kernel)
       const uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, block_n);
       uint32_t it = 0;
       uint32_t local = 0;
@@ -441,12 +441,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           const uint64_t bdesc = umma_desc_sw128(sb);
           const int kvalid = kb < kb0 ? min(BLOCK_K, p.K0 - kb * BLOCK_K) : min(BLOCK_K, p.K1 - (kb - kb0) * BLOCK_K);
           const int ksteps = (kvalid + 15) >> 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                             (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit_pair(&empty_bar[s], 3);        // frees the slot in both CTAs
+          if (elect_one()) {
+            if (ksteps == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_f16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(&empty_bar[s], 3);        // frees the slot in both CTAs
+            if (kb == num_kb - 1) tc_commit_pair(&tmem_full_bar[as], 3);     // accumulator complete: wake both CTAs' epilogues
+          }
+          __syncwarp();
         }
-        tc_commit_pair(&tmem_full_bar[as], 3);     // accumulator complete: wake both CTAs' epilogues
       }
     }
   } else {
