@@ -592,3 +592,31 @@ def test_any_resolution_2048_vs_oracle_tile_subset_and_fold(dev):
         acc = tiles.fold_tiles(outs[lo:hi].contiguous(), lo, size, size, acc)
     assert seen == n * n
     assert torch.allclose(tiles.finish(acc, size, size), full, atol=1e-6)
+
+
+def test_graph_replay_matches_eager_forward(dev, model_init):
+    """sunet_tf_b200.graph.GraphedForward: one CUDA-graph replay of the 215 launches is bit-identical to the eager forward."""
+    from sunet_tf_b200.graph import GraphedForward
+    noisy, _ = Wt.awgn_input(3, seed=5)
+    x = noisy.to(dev)
+    ref = model_init(x).clone()
+    g = GraphedForward(model_init, 3)
+    assert torch.equal(g(x), ref)
+    x2 = x.flip(0).contiguous()
+    assert torch.equal(g(x2), model_init(x2))
+    grey = GraphedForward(model_init, 1, in_chans=1)
+    assert torch.equal(grey(x[:1, :1].contiguous()), model_init(x[:1, :1].contiguous()))
+    # the automatic form: repeated calls with the same input / output buffers are captured on the second call and replayed after
+    net = model_init.swin_unet
+    xin, o = x.clone(), torch.empty_like(ref)
+    ref2 = model_init(x2).clone()
+    for i in range(4):
+        xin.copy_(x if i % 2 == 0 else x2)
+        model_init(xin, out=o)
+        assert torch.equal(o, ref if i % 2 == 0 else ref2), f"call {i}"
+    assert any(k[0] == xin.data_ptr() and k[1] == o.data_ptr() for k in net._graphs), "the repeated buffer pair was not captured"
+    # a re-pack (parameters changed) drops the captured forwards
+    with torch.no_grad():
+        net.norm.weight.add_(0.0)
+    model_init(xin, out=o)
+    assert len(net._graphs) == 0
