@@ -439,6 +439,7 @@ struct ProjParams {
   long long* trace;    // see Params::trace
 };
 
+// 19 warps put 5 on one scheduler: 96 registers per thread is the cap of a 16K-register SM sub-partition (104 is unlaunchable)
 template <int C>
 __global__ void __launch_bounds__(PTHREADS, 1)
     mlp_proj_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWp,

@@ -17,6 +17,7 @@
 #include "error.h"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
+#include "mlp_row.cuh"
 #include "proj_ln.cuh"
 #include "tail_fused.cuh"
 
@@ -214,6 +215,8 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
   AttnFusedPack af;     // norm1 + shift/partition + qkv + attention core + reverse/un-shift as one kernel
   bool use_af = false;
   bool use_proj_ln = false, use_row_gemm = false;   // C = 384 whole-row kernels (proj + shortcut + norm2; fc2 + residual)
+  MlpRowPack mr;        // C = 384: fc1 + GELU + fc2 + residual as one whole-row kernel (the hidden activation stays on the SM)
+  bool use_row_mlp = false;
   int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, int heads_, int shift_, double qk_scale,
            cudaStream_t s) {
     dim = dim_; H = H_; W = W_; heads = heads_; shift = shift_;
@@ -266,6 +269,17 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     // kernel selection is fixed here, once per pre-pack: the forward never consults the environment
     use_proj_ln = !use_mf && proj_ln_supported(dim) && getenv("SUNET_NO_PROJ_LN") == nullptr;
     use_row_gemm = row_gemm_supported(dim, 4 * dim) && getenv("SUNET_NO_ROW_GEMM") == nullptr;
+    use_row_mlp = use_proj_ln && mlp_row_supported(dim) && getenv("SUNET_NO_ROW_MLP") == nullptr;
+    if (use_row_mlp) {
+      Linear fc1h;   // 0.5 * fc1 (weights and bias): the GELU epilogue of the whole-row kernel takes u = x / 2
+      SUNET_TRY(pack_linear(ar, P, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias", 4 * dim, dim, &fc1h, s, 4 * dim, 0.5f));
+      if (!fc1h.b) {
+        SUNET_TRY(ar.alloc_t(&fc1h.b, static_cast<size_t>(4) * dim));
+        SUNET_CUDA(cudaMemsetAsync(fc1h.b, 0, static_cast<size_t>(4) * dim * sizeof(float), s));
+      }
+      mr.C = dim; mr.w1h = fc1h.w; mr.hbias = fc1h.b; mr.w2 = mlp.fc2.w; mr.b2 = mlp.fc2.b;
+      SUNET_TRY(mlp_row_prepare(&mr));
+    }
     return 0;
   }
   // The window-attention part of the block up to the per-head attention output O (norm1, shift, partition, qkv, QK^T + bias +
@@ -293,7 +307,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     SUNET_TRY(c.sc.take_t(&T, (use_af && use_mf) ? 0 : M * dim));
     SUNET_TRY(c.sc.take_t(&QKV, use_af ? 0 : M * 3 * dim));
     SUNET_TRY(c.sc.take_t(&O, M * dim));
-    SUNET_TRY(c.sc.take_t(&Hd, use_mf ? 0 : M * 4 * dim));
+    SUNET_TRY(c.sc.take_t(&Hd, (use_mf || use_row_mlp) ? 0 : M * 4 * dim));
     SUNET_TRY(attention_part(c, x_in, O, T, QKV, B));
     if (use_mf && mf.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one kernel
       RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim, mlp_proj_fused_launch(mf, O, x_in, x_out, M, c.stream));
@@ -304,6 +318,10 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       ProjLnPack pl;
       pl.w = attn.proj.w; pl.bias = attn.proj.b; pl.gamma = g2; pl.beta = b2; pl.C = dim;
       RUN(c, K_GEMM, 2.0 * M * dim * dim, 8.0 * M * dim + 2.0 * dim * dim, proj_ln_launch(pl, O, x_in, x_out, T, M, c.stream));
+      if (use_row_mlp) {   // :19-22, :262: fc1 + GELU + fc2 + second residual, the hidden activation never leaves the SM
+        RUN(c, K_MLP_FUSED, 16.0 * M * dim * dim, 6.0 * M * dim + 16.0 * dim * dim, mlp_row_launch(mr, T, x_out, x_out, M, c.stream));
+        return 0;
+      }
       SUNET_TRY(run_linear(c, mlp.fc1, T, dim, M, Hd, 4 * dim, ACT_GELU));                       // :19-20
       if (use_row_gemm) {
         RUN(c, K_GEMM, 8.0 * M * dim * dim, 12.0 * M * dim + 8.0 * dim * dim,
