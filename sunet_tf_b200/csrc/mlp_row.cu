@@ -82,13 +82,15 @@ struct Cfg {
 struct Params {
   const float* hbias;
   const float* b2;
-  const __half* R;
+  const float* bp;    // PROJ: attn.proj.bias [C] or null
+  const __half* R;    // residual of the second add (plain form) / block input = shortcut of the first add (PROJ form)
   __half* X;
   int64_t M;
   int64_t tiles;      // 128-row tiles; a pair takes tiles 2 c and 2 c + 1 of its cluster-strided sequence
   const void* w1;     // weight images, for the L2 prefetch of the prologue
   const void* w2;
-  uint32_t wbytes;    // bytes of each
+  const void* wp;     // PROJ
+  uint32_t wbytes;    // bytes of w1 / w2
   long long* timing;  // optional [grid][19 warps][8] phase cycle counters (timing builds, SUNET_MLP_TIMING)
 };
 
@@ -109,15 +111,19 @@ struct Params {
 
 __device__ __forceinline__ uint32_t stg_off(int row, int ch) { return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)); }
 
-template <int C>
+// PROJ: the token tile the kernel loads is the attention output; attn.proj runs first (its [C/2][64] weight k-blocks ride the fc2
+// ring, its accumulator is the - still idle - fc2 accumulator), the epilogue warps build x1 = P + bp + shortcut, store it, take the
+// LayerNorm statistics (two passes over x1 parked in TMEM, as proj_ln.cu) and write the normalised rows over the token tile as the
+// fc1 operand (norm2's affine part is folded into the fc1 weights at pre-pack).  SUNet_detail.py:136, :261-262.
 // 19 warps = 5 on one scheduler: 96 registers per thread is what a 16K-register SM sub-partition allows (more is unlaunchable)
+template <int C, bool PROJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     mlp_row_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmW1,
-                   const __grid_constant__ CUtensorMap tmW2, const Params p) {
+                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmWp, const Params p) {
   using K = Cfg<C>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t t_full, t_empty, r1_full[K::R1], r1_empty[K::R1], r2_full[K::R2], r2_empty[K::R2];
-  __shared__ __align__(8) uint64_t h_full, h_empty, g_full[2], g_empty[2], y_full, y_empty;
+  __shared__ __align__(8) uint64_t h_full, h_empty, g_full[2], g_empty[2], y_full, y_empty, p_full, x1_ready;
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,6 +140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     tma_prefetch_desc(&tmT);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    if (PROJ) tma_prefetch_desc(&tmWp);
     mbar_init(&t_full, 1);
     mbar_init(&t_empty, 1);
     for (int i = 0; i < K::R1; ++i) { mbar_init(&r1_full[i], 1); mbar_init(&r1_empty[i], 1); }
@@ -143,6 +150,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 2 * EPI_WARPS); mbar_init(&g_empty[i], 1); }
     mbar_init(&y_full, 1);
     mbar_init(&y_empty, 2 * EPI_WARPS);
+    mbar_init(&p_full, 1);
+    mbar_init(&x1_ready, 2 * EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -153,15 +162,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     float* b2s = reinterpret_cast<float*>(smem + K::OFF_B2);
     for (int i = threadIdx.x; i < C; i += THREADS) b2s[i] = p.b2 != nullptr ? __ldg(p.b2 + i) : 0.f;
   }
-  if (warp == 2 && lane < 2) {
+  if (warp == 2 && lane < (PROJ ? 3 : 2)) {
     // The weights of a block are cold (the model's 200 MB of parameters do not stay in the 126 MB L2 between forwards), and the rings
     // hold one chunk: without this every chunk exposes an HBM round trip (51 us per launch in the model against 37 us with the weights
-    // L2-resident).  Every CTA asks for 1/grid of both matrices up front - parameters, so ahead of the dependency wait.
-    const uint32_t per = ((p.wbytes + gridDim.x - 1) / gridDim.x + 127u) & ~127u;
+    // L2-resident).  Every CTA asks for 1/grid of the matrices up front - parameters, so ahead of the dependency wait.
+    const uint32_t total = lane == 2 ? p.wbytes / 4 : p.wbytes;   // Wp is C x C, fc1 / fc2 are 4C x C
+    const uint32_t per = ((total + gridDim.x - 1) / gridDim.x + 127u) & ~127u;
     const uint32_t off = blockIdx.x * per;
-    if (off < p.wbytes) {
-      const uint32_t n = min(per, p.wbytes - off);
-      const char* src = static_cast<const char*>(lane == 0 ? p.w1 : p.w2) + off;
+    if (off < total) {
+      const uint32_t n = min(per, total - off);
+      const char* src = static_cast<const char*>(lane == 0 ? p.w1 : (lane == 1 ? p.w2 : p.wp)) + off;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n) : "memory");
     }
   }
@@ -214,9 +224,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
                              half * K::NH + static_cast<int>(rank) * K::W2ROWS);
         }
       };
-      int pre = 0;
-      if (pair_id < pair_tiles)
-        for (; pre < 2; ++pre) load_w1(0, pre);   // parameters: issued ahead of the dependency wait
+      auto load_wp = [&](int kb) {   // attn.proj weights, k-block kb: same slot shape as an fc2 k-block (both output halves)
+        const int s = i2 % K::R2;
+        ROW_T(2);
+        mbar_wait(&r2_empty[s], ((i2 / K::R2) & 1) ^ 1);
+        ROW_T(1);
+        if (rank == 0) mbar_arrive_expect_tx(&r2_full[s], 2 * K::S2BYTES);
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d_pair(smem + K::OFF_R2 + s * K::S2BYTES + half * K::W2BYTES, &tmWp, &r2_full[s], kb * 64,
+                           half * K::NH + static_cast<int>(rank) * K::W2ROWS);
+        ++i2;
+      };
+      int pre = 0, prep = 0;
+      if (pair_id < pair_tiles) {   // parameters: issued ahead of the dependency wait
+        if (PROJ) for (; prep < K::R2; ++prep) load_wp(prep);
+        for (; pre < 2; ++pre) load_w1(0, pre);
+      }
       pdl_wait();
       for (int64_t pt = pair_id; pt < pair_tiles; pt += n_pairs, ++lt) {
         const int64_t tile = 2 * pt + rank;
@@ -224,6 +248,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         if (rank == 0) mbar_arrive_expect_tx(&t_full, 2 * K::KB1 * KBYTES);
         for (int kb = 0; kb < K::KB1; ++kb)
           tma_load_2d_pair(smem + K::OFF_T + kb * KBYTES, &tmT, &t_full, kb * 64, static_cast<int>(tile * TILE_M));   // rows beyond M: zero fill
+        if (PROJ)
+          for (int kb = lt == 0 ? prep : 0; kb < K::KB1; ++kb) load_wp(kb);
 #pragma unroll 1
         for (int s = 0; s <= K::NCH; ++s) {
           if (s < K::NCH)
@@ -257,7 +283,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
       };
       for (int64_t pt = pair_id; pt < pair_tiles; pt += n_pairs, ++lt) {
         ROW_T(5);
-        mbar_wait(&t_full, lt & 1);
+        if (PROJ) mbar_wait(&x1_ready, lt & 1);   // both CTAs' epilogues have written norm2(x1) over the token tiles
+        else mbar_wait(&t_full, lt & 1);
         ROW_T(4);
         tc_fence_after();
 #pragma unroll 1
@@ -314,11 +341,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         return s;
       };
       for (int64_t pt = pair_id; pt < pair_tiles; pt += n_pairs, ++lt) {
+        if (PROJ) {   // P = attn_out * Wp^T into the (idle) fc2 accumulator
+          ROW_T(5);
+          mbar_wait(&t_full, lt & 1);
+          if (lt > 0) mbar_wait(&y_empty, (lt - 1) & 1);   // the previous tile's output passes have drained Y
+          ROW_T(4);
+          tc_fence_after();
+#pragma unroll 1
+          for (int kb = 0; kb < K::KB1; ++kb) {
+            const int slot = r2_acquire();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_T + kb * KBYTES));
+            const uint32_t b0 = smem_u32(smem + K::OFF_R2 + slot * K::S2BYTES);
+            if (elect_one()) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint64_t bdesc = umma_desc_sw128(b0 + half * K::W2BYTES);
+                const uint32_t d = tmem_base + K::TM_Y + half * K::NH;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_ss_pair(d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+              tc_commit_pair(&r2_empty[slot], 3);
+              if (kb == K::KB1 - 1) tc_commit_pair(&p_full, 3);
+            }
+            __syncwarp();
+          }
+        }
 #pragma unroll 1
         for (int j = 0; j < K::NCH; ++j) {   // fc2 of chunk j: Y (+)= G * W2_j^T
           const uint32_t gg = g + j;
           ROW_T(5);
-          if (j == 0 && lt > 0) mbar_wait(&y_empty, (lt - 1) & 1);
+          if (!PROJ && j == 0 && lt > 0) mbar_wait(&y_empty, (lt - 1) & 1);
           ROW_T(4);   // the previous tile's output passes have drained Y
 #pragma unroll 1
           for (int kb2 = 0; kb2 < 2; ++kb2) {
@@ -366,6 +419,106 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     ROW_T_DECL;
     for (int64_t pt = pair_id; pt < pair_tiles; pt += n_pairs, ++lt) {
       const int64_t tile = 2 * pt + rank;
+      float ln_a = 1.f, ln_b = 0.f;   // PROJ: rstd and -mean * rstd of this thread's row
+      if constexpr (PROJ) {
+        // ---- x1 = P + bp + shortcut -> X (global) and, as fp16, over the attention-output tile: the RAW x1 is the fc1 operand.
+        // norm2 is folded into fc1 (exact algebra, as mlp_fused.cu):  0.5 fc1(LN(x1))_n = rstd (D_n - mean s_n) + c_n  with
+        // D = x1 W1hg^T, W1hg = fp16(0.5 W1 gamma), s_n = sum_k W1hg[n,k] (the rounded weights), c_n = 0.5 (b1_n + W1 beta), so the
+        // row statistics are not needed before the first GELU pass and their exchange runs under the first fc1 MMAs.
+        constexpr int NPASS = K::CQ / 32;
+        const int64_t m_base = tile * TILE_M + q * 32;
+        const int rows_valid = static_cast<int>(min(static_cast<int64_t>(32), p.M - m_base));
+        const int col0 = quarter * K::CQ;
+        uint4 rpre[NPASS][4];   // shortcut rows of this warp's 32 x CQ block, whole 64-byte row segments per 4 lanes
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ++ps) {
+          const __half* rbase = p.R + m_base * C + col0 + ps * 32;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + cr;
+            rpre[ps][it] = r < rows_valid ? *(reinterpret_cast<const uint4*>(rbase + static_cast<int64_t>(r) * C) + cch) : make_uint4(0u, 0u, 0u, 0u);   // plain load: X may alias R
+          }
+        }
+        mbar_wait(&p_full, lt & 1);
+        tc_fence_after();
+        const uint32_t ty = tmem_base + lane_off + K::TM_Y + col0;
+        const uint32_t ts = smem_u32(smem + K::OFF_T) + row * 128;
+        float s1 = 0.f, s2 = 0.f, k0 = 0.f;   // shifted sums over this thread's CQ columns (shift = its first value)
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ++ps) {
+          const int cc = ps * 32;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) sts128(stg + stg_off(it * 8 + cr, cch), rpre[ps][it]);
+          uint32_t v[32];
+          tmem_ld32(ty + cc, v);
+          tmem_ld_wait();
+          __syncwarp();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint4 rr = lds128(stg + stg_off(lane, ch));
+            const __half2* r2 = reinterpret_cast<const __half2*>(&rr);
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (p.bp != nullptr) {
+              b0 = __ldg(reinterpret_cast<const float4*>(p.bp + col0 + cc + ch * 8));
+              b1 = __ldg(reinterpret_cast<const float4*>(p.bp + col0 + cc + ch * 8 + 4));
+            }
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 o;
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 r = __half22float2(r2[t]);
+              const __half2 h = __floats2half2_rn(__uint_as_float(v[ch * 8 + 2 * t]) + bb[2 * t] + r.x,
+                                                  __uint_as_float(v[ch * 8 + 2 * t + 1]) + bb[2 * t + 1] + r.y);
+              const float2 f = __half22float2(h);   // statistics on the rounded stream values, as a stand-alone LayerNorm reads them
+              if (ps == 0 && ch == 0 && t == 0) k0 = f.x;
+              const float d0 = f.x - k0, d1 = f.y - k0;
+              s1 += d0 + d1;
+              s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+              ow[t] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            sts128(stg + stg_off(lane, ch), o);
+            const int gi = (col0 + cc) / 8 + ch;   // 16-byte chunk of the row inside the [128][C] SW128 tile
+            sts128(ts + (gi >> 3) * KBYTES + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4), o);
+          }
+          __syncwarp();
+          __half* xbase = p.X + m_base * C + col0 + cc;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + cr;
+            if (r < rows_valid) *(reinterpret_cast<uint4*>(xbase + static_cast<int64_t>(r) * C) + cch) = lds128(stg + stg_off(r, cch));
+          }
+          __syncwarp();
+        }
+        // P has been read and x1 is in place: fc1 of the first chunk may start
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&x1_ready, 0);
+        // per-quarter (mean, M2) around the quarter's own shift, merged over the four column-quarter warps of this lane quarter
+        // (parallel variance) through their - now idle - staging tiles: float2 [32] at offset 0 of each
+        const float mq = k0 + s1 * (1.0f / K::CQ);
+        const float m2q = s2 - s1 * s1 * (1.0f / K::CQ);
+        const uint32_t xq = smem_u32(smem + K::OFF_G + ((q + 2) & 3) * STG_BYTES);   // staging tile of the quarter-0 warp of this lane quarter (e = warp - 2)
+        named_bar_sync(2 + q, 128);   // all four warps are done with their staging tiles
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stg + lane * 8), "f"(mq), "f"(m2q) : "memory");
+        named_bar_sync(2 + q, 128);
+        float mean = 0.f, m2 = 0.f, mqs[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float vx, vy;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(vx), "=f"(vy) : "r"(xq + t * 4 * STG_BYTES + lane * 8) : "memory");
+          mqs[t] = vx; mean += vx; m2 += vy;
+        }
+        mean *= 0.25f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) m2 = fmaf(static_cast<float>(K::CQ) * (mqs[t] - mean), mqs[t] - mean, m2);
+        ln_a = rsqrtf(fmaxf(m2 * (1.0f / C), 0.f) + 1e-5f);
+        ln_b = -mean * ln_a;
+        // The staging tiles are part of the G buffer, whose next writers are the GELU stores of chunk 0 - of ANY warp, ~3k clk after the
+        // last x1_ready arrive, which precedes these reads: every epilogue warp must be past its reads before any of them moves on.
+        named_bar_sync(1, EPI_THREADS);
+      }
       // ---- GELU passes
 #pragma unroll 1
       for (int j = 0; j < K::NCH; ++j, ++g) {
@@ -386,16 +539,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         // u = 0.5 * fc1(T) = D + hbias (fc1 weights and bias are pre-scaled by 0.5); GELU(2u) = u + u * tanh(u * P(u^2))
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const float4* hb4 = reinterpret_cast<const float4*>(p.hbias + j * NC + hh * 64 + quarter * 16);
           uint32_t w[8];
+          if constexpr (PROJ) {
+            const float4* hc4 = reinterpret_cast<const float4*>(p.hbias) + (j * NC + hh * 64 + quarter * 16) / 2;   // (s, c) pairs
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bq = __ldg(hb4 + i);   // warp-uniform address: broadcast
-            const float g0 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 0]) + bq.x), g1 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 1]) + bq.y);
-            const float g2 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 2]) + bq.z), g3 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 3]) + bq.w);
-            const __half2 p0 = __floats2half2_rn(g0, g1), p1 = __floats2half2_rn(g2, g3);
-            w[2 * i] = *reinterpret_cast<const uint32_t*>(&p0);
-            w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+            for (int i = 0; i < 8; ++i) {
+              const float4 c2 = __ldg(hc4 + i);   // (s, c) of two consecutive hidden columns; warp-uniform address: broadcast
+              const float g0 = gelu_half_arg(fmaf(ln_a, __uint_as_float(v[hh][2 * i + 0]), fmaf(ln_b, c2.x, c2.y)));
+              const float g1 = gelu_half_arg(fmaf(ln_a, __uint_as_float(v[hh][2 * i + 1]), fmaf(ln_b, c2.z, c2.w)));
+              const __half2 p0 = __floats2half2_rn(g0, g1);
+              w[i] = *reinterpret_cast<const uint32_t*>(&p0);
+            }
+          } else {
+            const float4* hb4 = reinterpret_cast<const float4*>(p.hbias + j * NC + hh * 64 + quarter * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bq = __ldg(hb4 + i);   // warp-uniform address: broadcast
+              const float g0 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 0]) + bq.x), g1 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 1]) + bq.y);
+              const float g2 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 2]) + bq.z), g3 = gelu_half_arg(__uint_as_float(v[hh][4 * i + 3]) + bq.w);
+              const __half2 p0 = __floats2half2_rn(g0, g1), p1 = __floats2half2_rn(g2, g3);
+              w[2 * i] = *reinterpret_cast<const uint32_t*>(&p0);
+              w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+            }
           }
           ROW_T(2);
           if (g > 0) mbar_wait_hint(&g_empty[hh], (g - 1) & 1, g_ok);   // fc2 of the previous chunk has consumed this k-block of G
@@ -425,7 +590,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         uint4 rpre[NPASS][4];
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
-          const __half* rbase = p.R + m_base * C + col0 + ps * 32;
+          const __half* rbase = (PROJ ? p.X : p.R) + m_base * C + col0 + ps * 32;   // PROJ: x1, stored by this very thread above
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + cr;
@@ -546,28 +711,51 @@ static void row_timing_report(int C, unsigned grid, const long long* buf, cudaSt
   }
 }
 
-template <int C>
+template <int C, bool PROJ>
 int launch_t(const MlpRowPack& pk, const __half* T, const __half* R, __half* X, int64_t M, cudaStream_t stream) {
   using K = Cfg<C>;
   static DeviceOnce once;   // the shared-memory opt-in is per device
   if (once.need()) {
-    SUNET_CUDA(cudaFuncSetAttribute(mlp_row_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    SUNET_CUDA(cudaFuncSetAttribute((mlp_row_kernel<C, PROJ>), cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     once.done();
   }
   alignas(64) CUtensorMap tmT;
   SUNET_TRY(make_tmap_2d_f16(&tmT, T, C, M, C, TILE_M));
   Params p;
-  p.hbias = pk.hbias; p.b2 = pk.b2; p.R = R; p.X = X; p.M = M;
+  p.hbias = PROJ ? pk.hbiasg : pk.hbias; p.b2 = pk.b2; p.bp = pk.bp; p.R = R; p.X = X; p.M = M;
   p.tiles = (M + TILE_M - 1) / TILE_M;
   const int64_t pair_tiles = (p.tiles + 1) / 2;
   const int64_t clusters = device_sms() / 2;
   const unsigned grid = static_cast<unsigned>(2 * (pair_tiles < clusters ? pair_tiles : clusters));
-  p.w1 = pk.w1h; p.w2 = pk.w2; p.wbytes = static_cast<uint32_t>(4u * C * C * sizeof(__half));
+  p.w1 = PROJ ? pk.w1hg : pk.w1h; p.w2 = pk.w2; p.wp = pk.wp; p.wbytes = static_cast<uint32_t>(4u * C * C * sizeof(__half));
   p.timing = row_timing_buf(stream);
-  SUNET_CUDA(launch_pdl(mlp_row_kernel<C>, dim3(grid), dim3(THREADS), K::SMEM, stream, tmT, pk.tmW1, pk.tmW2, p));
+  SUNET_CUDA(launch_pdl((mlp_row_kernel<C, PROJ>), dim3(grid), dim3(THREADS), K::SMEM, stream, tmT, PROJ ? pk.tmW1g : pk.tmW1, pk.tmW2,
+                        PROJ ? pk.tmWp : pk.tmW2, p));
   SUNET_CHECK_LAUNCH();
   row_timing_report(C, grid, p.timing, stream);
   return 0;
+}
+
+// pre-pack of the PROJ form: w1hg = fp16(0.5 * W1 * gamma), hconst[n] = (s_n, c_n) with s_n = sum_k w1hg[n,k] (the ROUNDED weights the
+// MMA multiplies) and c_n = 0.5 * (b1 + W1 beta); one warp per hidden unit
+__global__ void row_fold_ln_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, __half* __restrict__ w1hg, float2* __restrict__ hconst, int HID, int C) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= HID) return;
+  float bb = 0.f, ss = 0.f;
+  for (int k = lane; k < C; k += 32) {
+    const float w = w1[static_cast<size_t>(n) * C + k];
+    const __half h = __float2half_rn(0.5f * w * gamma[k]);
+    w1hg[static_cast<size_t>(n) * C + k] = h;
+    ss += __half2float(h);
+    bb = fmaf(w, beta[k], bb);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) hconst[n] = make_float2(ss, 0.5f * (bb + (b1 ? b1[n] : 0.f)));
 }
 
 }  // namespace
@@ -583,13 +771,38 @@ int mlp_row_prepare(MlpRowPack* p) {
   return 0;
 }
 
+int mlp_row_set_proj(MlpRowPack* p, const __half* wp, const float* bp, const float* gamma, const float* beta, const float* w1, const float* b1,
+                     __half* w1hg, float* hbiasg, cudaStream_t stream) {
+  if (!mlp_row_supported(p->C)) return fail(SUNET_E_SHAPE, "mlp_row: C=%d not instantiated (384)", p->C);
+  if (!wp || !gamma || !beta || !w1 || !w1hg || !hbiasg) return fail(SUNET_E_ARG, "mlp_row: proj pack buffers not set");
+  const int C = p->C, HID = 4 * C;
+  row_fold_ln_kernel<<<(HID + 7) / 8, 256, 0, stream>>>(w1, b1, gamma, beta, w1hg, reinterpret_cast<float2*>(hbiasg), HID, C);
+  SUNET_CHECK_LAUNCH();
+  p->wp = wp; p->bp = bp; p->w1hg = w1hg; p->hbiasg = hbiasg;
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW1g, w1hg, C, HID, C, NC / 2));
+  SUNET_TRY(make_tmap_2d_f16(&p->tmWp, wp, C, C, C, C / 4));
+  p->has_proj = 1;
+  return 0;
+}
+
+int mlp_row_proj_launch(const MlpRowPack& p, const __half* attn_out, const __half* shortcut, __half* X, int64_t M, cudaStream_t stream) {
+  if (!p.has_proj) return fail(SUNET_E_STATE, "mlp_row: proj weights not packed");
+  if (M <= 0) return 0;
+  if (M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "mlp_row: M too large for 32-bit TMA coordinates");
+  if ((reinterpret_cast<uintptr_t>(attn_out) | reinterpret_cast<uintptr_t>(shortcut) | reinterpret_cast<uintptr_t>(X)) & 15)
+    return fail(SUNET_E_ALIGN, "mlp_row: operands must be 16-byte aligned");
+  if (attn_out == X) return fail(SUNET_E_ARG, "mlp_row: X must not alias attn_out (tiles of other CTAs are still being read)");
+  if (p.C == 384) return launch_t<384, true>(p, attn_out, shortcut, X, M, stream);
+  return fail(SUNET_E_SHAPE, "mlp_row: C=%d not instantiated", p.C);
+}
+
 int mlp_row_launch(const MlpRowPack& p, const __half* T, const __half* R, __half* X, int64_t M, cudaStream_t stream) {
   if (M <= 0) return 0;
   if (M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "mlp_row: M too large for 32-bit TMA coordinates");
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(X)) & 15)
     return fail(SUNET_E_ALIGN, "mlp_row: operands must be 16-byte aligned");
   if (T == X) return fail(SUNET_E_ARG, "mlp_row: X must not alias T (tiles of other CTAs are still being read)");
-  if (p.C == 384) return launch_t<384>(p, T, R, X, M, stream);
+  if (p.C == 384) return launch_t<384, false>(p, T, R, X, M, stream);
   return fail(SUNET_E_SHAPE, "mlp_row: C=%d not instantiated", p.C);
 }
 

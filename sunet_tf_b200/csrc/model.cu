@@ -279,6 +279,17 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       }
       mr.C = dim; mr.w1h = fc1h.w; mr.hbias = fc1h.b; mr.w2 = mlp.fc2.w; mr.b2 = mlp.fc2.b;
       SUNET_TRY(mlp_row_prepare(&mr));
+      if (getenv("SUNET_NO_ROW_PROJ") == nullptr) {   // attn.proj + first residual + norm2 ride in front of the same kernel
+        const float *gw, *gb, *w1, *b1v = nullptr;
+        SUNET_TRY(P.get(pre + "norm2.weight", dim, &gw));
+        SUNET_TRY(P.get(pre + "norm2.bias", dim, &gb));
+        SUNET_TRY(P.get(pre + "mlp.fc1.weight", static_cast<int64_t>(4) * dim * dim, &w1));
+        if (P.has(pre + "mlp.fc1.bias")) SUNET_TRY(P.get(pre + "mlp.fc1.bias", 4 * dim, &b1v));
+        __half* w1hg; float* hbg;
+        SUNET_TRY(ar.alloc_t(&w1hg, static_cast<size_t>(4) * dim * dim));
+        SUNET_TRY(ar.alloc_t(&hbg, static_cast<size_t>(8) * dim));
+        SUNET_TRY(mlp_row_set_proj(&mr, attn.proj.w, attn.proj.b, gw, gb, w1, b1v, w1hg, hbg, s));
+      }
     }
     return 0;
   }
@@ -304,13 +315,17 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     ScratchMark mk(c.sc);
     const int64_t M = static_cast<int64_t>(B) * H * W;
     __half *T, *QKV, *O, *Hd;
-    SUNET_TRY(c.sc.take_t(&T, (use_af && use_mf) ? 0 : M * dim));
+    SUNET_TRY(c.sc.take_t(&T, (use_af && (use_mf || (use_row_mlp && mr.has_proj))) ? 0 : M * dim));
     SUNET_TRY(c.sc.take_t(&QKV, use_af ? 0 : M * 3 * dim));
     SUNET_TRY(c.sc.take_t(&O, M * dim));
     SUNET_TRY(c.sc.take_t(&Hd, (use_mf || use_row_mlp) ? 0 : M * 4 * dim));
     SUNET_TRY(attention_part(c, x_in, O, T, QKV, B));
     if (use_mf && mf.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one kernel
       RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim, mlp_proj_fused_launch(mf, O, x_in, x_out, M, c.stream));
+      return 0;
+    }
+    if (use_row_mlp && mr.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one CTA-pair whole-row kernel
+      RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim + 18.0 * dim * dim, mlp_row_proj_launch(mr, O, x_in, x_out, M, c.stream));
       return 0;
     }
     if (use_proj_ln) {

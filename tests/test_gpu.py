@@ -204,6 +204,33 @@ def test_proj_ln_kernel_agrees_with_separate_kernels(dev, batch, monkeypatch):
     report(f"proj_ln-vs-separate batch{batch}", y_fused, y_plain.cpu(), MODULE_TOL)
 
 
+@pytest.mark.parametrize("grid,batch", [(8, 5), (16, 1), (16, 80)])
+def test_row_mlp_kernel_agrees_with_separate_kernels(dev, grid, batch, monkeypatch):
+    """C = 384: the back half of the block as ONE CTA-pair whole-row kernel (mlp_row.cu: proj + shortcut + norm2 folded into fc1 +
+    GELU + fc2 + residual, hidden activation on chip) against (a) proj_ln + the same kernel without its proj front (SUNET_NO_ROW_PROJ),
+    (b) proj_ln + two GEMMs (SUNET_NO_ROW_MLP) and the oracle.  grid 8 / batch 5 = 320 rows = 3 row tiles: the second pair's peer CTA
+    owns a tile wholly beyond M and the last valid tile is half empty; batch 80 = 80 pair tiles on 74 clusters: the multi-tile path
+    (token-tile / accumulator hand-back, output staging inside the G buffer); the block writes in place over its input."""
+    from sunet_tf_b200 import SwinTransformerBlock
+    dim, shift = 384, 4
+    sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, shift), seed=4321, style="stress")
+    x = module_input((batch, grid * grid, dim), seed=4322)
+
+    def build():
+        return load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
+
+    y_row = build()(x.to(dev))
+    monkeypatch.setenv("SUNET_NO_ROW_PROJ", "1")
+    y_noproj = build()(x.to(dev))
+    monkeypatch.setenv("SUNET_NO_ROW_MLP", "1")
+    y_gemm = build()(x.to(dev))
+    nref = min(batch, 4)
+    ref = O.swin_block(sd, "", x[:nref], grid, grid, 8, shift, 8)
+    report(f"row-mlp-vs-oracle grid{grid} batch{batch}", y_row[:nref], ref, MODULE_TOL)
+    report(f"row-mlp-vs-row-mlp-without-proj grid{grid} batch{batch}", y_row, y_noproj.cpu(), MODULE_TOL)
+    report(f"row-mlp-vs-gemms grid{grid} batch{batch}", y_row, y_gemm.cpu(), MODULE_TOL)
+
+
 def test_swin_block_default_scale_and_rect_grid(dev):
     """qk_scale=None -> head_dim**-0.5 (SUNet_detail.py:80); rectangular token grid"""
     from sunet_tf_b200 import SwinTransformerBlock
