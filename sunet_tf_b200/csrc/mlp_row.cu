@@ -164,16 +164,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   }
   if (warp == 2 && lane < (PROJ ? 3 : 2)) {
     // The weights of a block are cold (the model's 200 MB of parameters do not stay in the 126 MB L2 between forwards), and the rings
-    // hold one chunk: without this every chunk exposes an HBM round trip (51 us per launch in the model against 37 us with the weights
-    // L2-resident).  Every CTA asks for 1/grid of the matrices up front - parameters, so ahead of the dependency wait.
-    const uint32_t total = lane == 2 ? p.wbytes / 4 : p.wbytes;   // Wp is C x C, fc1 / fc2 are 4C x C
-    const uint32_t per = ((total + gridDim.x - 1) / gridDim.x + 127u) & ~127u;
-    const uint32_t off = blockIdx.x * per;
-    if (off < total) {
-      const uint32_t n = min(per, total - off);
-      const char* src = static_cast<const char*>(lane == 0 ? p.w1 : (lane == 1 ? p.w2 : p.wp)) + off;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n) : "memory");
-    }
+    // hold one chunk: without this every chunk exposes an HBM round trip (51 us per launch in the model against 44 us).  Every CTA
+    // asks for 1/grid of the matrices up front - parameters, so ahead of the dependency wait.
+    l2_prefetch_slice(lane == 0 ? p.w1 : (lane == 1 ? p.w2 : p.wp), lane == 2 ? p.wbytes / 4 : p.wbytes);   // Wp is C x C, fc1 / fc2 are 4C x C
   }
   tc_fence_before();
   cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / peer TMA completion

@@ -136,6 +136,23 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of this CTA's 1/gridDim.x slice of a parameter block (no shared memory, no completion to wait for).  The model's
+// ~200 MB of fp16 weights do not survive in the 126 MB L2 from one forward to the next, so every launch finds its weights cold;
+// issued in the prologue, ahead of griddepcontrol.wait, the fetch runs under the predecessor's tail.  Pays where a kernel consumes
+// its weights serially through a shallow ring (mlp_row.cu: 51 -> 44 us per launch when timed alone, +0.15% end to end); in the GEMMs and attn_fused<384>, whose first
+// wave touches every weight block at once anyway, the same prefetch measured -2.2% end to end (tools/ab_variants.py) and is not used.
+__device__ __forceinline__ void l2_prefetch_slice(const void* base, uint32_t bytes) {
+#ifdef SUNET_NO_L2_PREFETCH   // A/B switch (tools/build_variant.py)
+  return;
+#endif
+  if (base == nullptr || bytes == 0) return;
+  const uint32_t per = ((bytes + gridDim.x - 1) / gridDim.x + 127u) & ~127u;
+  const uint32_t off = blockIdx.x * per;
+  if (off < bytes) {
+    const uint32_t n = (min(per, bytes - off)) & ~15u;
+    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(base) + off), "r"(n) : "memory");
+  }
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
