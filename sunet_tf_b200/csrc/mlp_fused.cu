@@ -874,6 +874,9 @@ __global__ void __launch_bounds__(PTHREADS, 1)
       const uint32_t yuse = K::NYBUF == 2 ? (lt >> 1) : lt;
       (void)xb; (void)yb; (void)yuse;
       // ---- GELU passes
+      // (EARLY: the next tile's shortcut is requested here, once per tile and outside the chunk loop - inside it the compiler
+      // predicates the ~90 address / load instructions instead of branching, and every chunk pays their issue slots)
+      if (PREFETCH && EARLY) fetch_shortcut(tile + gridDim.x);
       for (int j = 0; j < K::NCH; ++j, ++g) {
         const uint32_t hb = g & 1, ph = (g >> 1) & 1;
         mbar_wait_hint(&h_full[hb], ph, h_ok);
@@ -885,7 +888,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + K::TM_H + hb * 128 + quarter * 32, v);
         const uint32_t hs_ok = mbar_test(&hs_empty[hb], ph ^ 1);   // looked up under the TMEM load / GELU math
-        if (PREFETCH && j == (EARLY ? 0 : K::NCH - 2)) fetch_shortcut(tile + gridDim.x);   // next tile's shortcut, well ahead of its use
+        if (PREFETCH && !EARLY && j == K::NCH - 2) fetch_shortcut(tile + gridDim.x);   // next tile's shortcut, well ahead of its use
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
