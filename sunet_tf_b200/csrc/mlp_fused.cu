@@ -781,6 +781,12 @@ __global__ void __launch_bounds__(PTHREADS, 1)
     // phase still costs 350-450 clk - 1.4k clk right after the global stores of `out` (event trace) - a test issued a phase earlier
     // costs nothing on the critical path.
     uint32_t h_ok = 0, p_ok = 0, y_ok = 0;
+    // GELU store addresses of this thread inside a hidden buffer: computed once (left to itself the compiler rematerialises the
+    // swizzle arithmetic in every chunk - the kernel is issue-bound, ~45 integer instructions per chunk)
+    uint32_t hs_row = smem_u32(smem + K::OFF_HS + (quarter >> 1) * KBYTES) + row * 128;
+    uint32_t hs_x0 = ((static_cast<uint32_t>((quarter & 1) * 4 + 0)) ^ sw) << 4, hs_x1 = ((static_cast<uint32_t>((quarter & 1) * 4 + 1)) ^ sw) << 4;
+    uint32_t hs_x2 = ((static_cast<uint32_t>((quarter & 1) * 4 + 2)) ^ sw) << 4, hs_x3 = ((static_cast<uint32_t>((quarter & 1) * 4 + 3)) ^ sw) << 4;
+    if constexpr (C <= 96) asm volatile("" : "+r"(hs_row), "+r"(hs_x0), "+r"(hs_x1), "+r"(hs_x2), "+r"(hs_x3));
     MLP_T_DECL;
     MLP_T_START;
     // EARLY (two token-tile buffers and two fc2 accumulators, i.e. C <= 96): x1 of the NEXT tile is built before the output of the
@@ -919,10 +925,18 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         if constexpr (EARLY) {   // last chunk: the next local tile's proj accumulator (epi0 of that tile follows)
           if (j == K::NCH - 1 && tile + gridDim.x < p.tiles) p_ok = mbar_test(&p_full[(lt + 1) & 1], ((lt + 1) >> 1) & 1);
         }
-        const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
+        if constexpr (PREFETCH) {   // C = 96: the precomputed addresses fit the register budget (at C = 192 they spill)
+          const uint32_t hs = hs_row + hb * (2 * KBYTES);
+          sts128(hs + hs_x0, make_uint4(w[0], w[1], w[2], w[3]));
+          sts128(hs + hs_x1, make_uint4(w[4], w[5], w[6], w[7]));
+          sts128(hs + hs_x2, make_uint4(w[8], w[9], w[10], w[11]));
+          sts128(hs + hs_x3, make_uint4(w[12], w[13], w[14], w[15]));
+        } else {
+          const uint32_t hs = smem_u32(smem + K::OFF_HS + (hb * 2 + (quarter >> 1)) * KBYTES) + row * 128;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          sts128(hs + (((static_cast<uint32_t>((quarter & 1) * 4 + i)) ^ sw) << 4), make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+          for (int i = 0; i < 4; ++i)
+            sts128(hs + (((static_cast<uint32_t>((quarter & 1) * 4 + i)) ^ sw) << 4), make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
