@@ -836,7 +836,10 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         const float m2q = s2 - s1 * s1 * (1.0f / K::QC);
         float2* st = stats + (lt & 1) * 4 * 128;
         st[quarter * 128 + row] = make_float2(mq, m2q);
-        named_bar_sync(1, EPI_THREADS);
+        // only the 4 column-quarter warps of a row quadrant exchange statistics.  Without EARLY this barrier is also the one that
+        // separates the staging reads of the previous tile's `output` from this tile's GELU stores into the same buffers: CTA-wide.
+        if constexpr (EARLY) named_bar_sync(2 + q, 128);
+        else named_bar_sync(1, EPI_THREADS);
         float mean = 0.f, m2 = 0.f;
         float mqs[4];
 #pragma unroll
