@@ -41,6 +41,12 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 // barrier round trips.  Measured against a single issuing thread (round 1, tools/ab_mlp_split.sh): 3.30 -> 3.21 ms over the
 // 32 launches of a forward; an idle 19th warp alone costs +2.6%, the split itself gains 6%.
 constexpr int PTHREADS = THREADS + 32;
+// A/B switch (tools/build_variant.py): 0 = CTA-wide barriers on the tile path, 1 = per-row-quadrant statistics barrier,
+// 2 = + output staging inside the quadrant's own pieces of the hidden buffers (no CTA-wide barrier left on the tile path)
+// Measured in one call on one box (tools/ab_variants.py, whole forward): 8.388 / 8.362 / 8.373 ms for 0 / 1 / 2 - boxes differ by ~1%.
+#ifndef SUNET_MLP_QSYNC
+#define SUNET_MLP_QSYNC 1
+#endif
 constexpr int FC2_WARP = 2 + EPI_WARPS;
 
 template <int C>
@@ -836,9 +842,10 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         const float m2q = s2 - s1 * s1 * (1.0f / K::QC);
         float2* st = stats + (lt & 1) * 4 * 128;
         st[quarter * 128 + row] = make_float2(mq, m2q);
-        // only the 4 column-quarter warps of a row quadrant exchange statistics.  Without EARLY this barrier is also the one that
-        // separates the staging reads of the previous tile's `output` from this tile's GELU stores into the same buffers: CTA-wide.
-        if constexpr (EARLY) named_bar_sync(2 + q, 128);
+        // only the 4 column-quarter warps of a row quadrant exchange statistics (a CTA-wide barrier made all 16 wait for the slowest).
+        // Without EARLY this barrier is also the one that separates the staging reads of the previous tile's `output` from this
+        // tile's GELU stores into the same buffers: CTA-wide there.
+        if constexpr (EARLY && SUNET_MLP_QSYNC >= 1) named_bar_sync(2 + q, 128);
         else named_bar_sync(1, EPI_THREADS);
         float mean = 0.f, m2 = 0.f;
         float mqs[4];
@@ -971,8 +978,16 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         if (lane == 0) mbar_arrive(&y_empty[yb]);
         // Stage the 32 x C fp16 block of this row quadrant through the (now idle) GELU buffers so that global stores cover whole
         // rows: a thread-per-row store touches 32 different 128-byte lines per instruction and is LSU-bound (measured).
+        // The staging rows of quadrant q live ONLY in bytes that the GELU stores of quadrant q's own rows write (rows 32 q .. 32 q + 31
+        // of each of the four [128][64] hidden k-block buffers, 4 KB apiece), so the hazard between these staging accesses and the next
+        // tile's GELU stores is confined to the 4 warps of the quadrant: no CTA-wide barrier on the tile path.
         constexpr int PITCH = C * 2 + 16;   // bytes; the 16-byte pad makes 8 consecutive rows hit 8 distinct bank groups
-        const uint32_t stg = smem_u32(smem + K::OFF_HS) + static_cast<uint32_t>(q) * (32 * PITCH);
+        // (SUNET_MLP_QSYNC = 2, EARLY configs only; measured no better than the CTA-wide barrier it removes, so off by default)
+        constexpr bool QSTG = EARLY && SUNET_MLP_QSYNC >= 2;
+        constexpr int RP = QSTG ? 16 : 32;   // staging rows per piece
+        static_assert(!QSTG || 16 * PITCH <= 4096, "output staging must fit the quadrant's own pieces of the hidden buffers");
+        const uint32_t stg = smem_u32(smem + K::OFF_HS) + static_cast<uint32_t>(q) * (QSTG ? 4096 : 32 * PITCH);
+        auto stg_row = [&](int r) -> uint32_t { return stg + static_cast<uint32_t>(r / RP) * KBYTES + static_cast<uint32_t>(r % RP) * PITCH; };
 #pragma unroll
         for (int i = 0; i < K::QCH; ++i) {
           const __half2* r2 = reinterpret_cast<const __half2*>(&res[i]);
@@ -985,7 +1000,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
             o2[t] = __floats2half2_rn(__uint_as_float(y[i * 8 + 2 * t]) + bb[2 * t] + r.x,
                                       __uint_as_float(y[i * 8 + 2 * t + 1]) + bb[2 * t + 1] + r.y);
           }
-          sts128(stg + lane * PITCH + (quarter * K::QCH + i) * 16, o);
+          sts128(stg_row(lane) + (quarter * K::QCH + i) * 16, o);
         }
         named_bar_sync(2 + q, 128);   // the 4 column-quarter warps of this row quadrant
         {
@@ -996,11 +1011,11 @@ __global__ void __launch_bounds__(PTHREADS, 1)
             const int idx = kk * 32 + lane;
             const int r = idx / CPR, ch = idx - r * CPR;
             if (idx < 8 * CPR && m0 + r < p.M)
-              *reinterpret_cast<uint4*>(p.out + (m0 + r) * C + ch * 8) = lds128(stg + (quarter * 8 + r) * PITCH + ch * 16);
+              *reinterpret_cast<uint4*>(p.out + (m0 + r) * C + ch * 8) = lds128(stg_row(quarter * 8 + r) + ch * 16);
           }
         }
-        // EARLY: no other block-wide barrier separates these staging reads from the next tile's GELU stores into the same buffers
-        if constexpr (EARLY) named_bar_sync(1, EPI_THREADS);
+        if constexpr (QSTG) named_bar_sync(2 + q, 128);   // the staging reads above against the quadrant's next GELU stores into the same bytes
+        else if constexpr (EARLY) named_bar_sync(1, EPI_THREADS);
         MLP_T(7);
       }
         };
