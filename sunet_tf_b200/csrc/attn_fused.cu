@@ -696,7 +696,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       }
       AF_T(4);
       const uint32_t md_next = has_next ? mbar_test(&mma_done, (item + 1) & 1) : 0u;   // looked up under the scatter (a test costs ~170 clk)
-      __syncthreads();   // (C) O rows of every unit parked in the q tiles
+      // (C) O rows of every unit parked in the q tiles.  The scatter of a window reads only what the 8 core warps of the same window
+      // (warps 8 wi .. 8 wi + 7, the very warps that scatter it) have written: a per-window barrier, so a window with cheaper units
+      // (no mask) does not wait for the other one.
+#ifndef SUNET_AF_CWIN
+#define SUNET_AF_CWIN 1
+#endif
+      if (SUNET_AF_CWIN) named_bar_sync(1 + wi, 256);
+      else __syncthreads();
       AF_T(5);
       // ---- scatter (heads are concatenated in order, :135; window_reverse + un-roll through the row map): the 4 threads
       // of a token write consecutive vectors, so every store instruction covers whole 32-byte sectors
