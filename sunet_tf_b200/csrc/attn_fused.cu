@@ -727,7 +727,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       }
       AF_T(6);
       md_ok = md_next;
-      __syncthreads();   // (D) q tiles free for the next drain
+      // (D) q tiles free for the next drain.  The drain of a warp overwrites the q / k / v rows of ONE window - the one its TMEM lane
+      // quadrant holds (rows 32 q4 .. 32 q4 + 31, window q4 >> 1) - so it has to wait for the scatter of that window only: the 8
+      // scatter warps of window w and the 4 warps of the other half that drain w's rows meet on barrier 3 + w (12 warps); a warp that
+      // scatters w but drains the other window only arrives.
+      // Measured SLOWER than the CTA-wide barrier (in-call A/B, whole forward: 8.374 vs 8.316 ms; C = 96 113.0 vs 111.0 us): off.
+#ifndef SUNET_AF_DWIN
+#define SUNET_AF_DWIN 0
+#endif
+      if (SUNET_AF_DWIN) {
+        const int wd = q4 >> 1;   // window whose rows this warp drains
+        if (wd == wi) {
+          named_bar_sync(3 + wi, 384);
+        } else {
+          asm volatile("bar.arrive %0, %1;" ::"r"(3 + wi), "r"(384) : "memory");
+          named_bar_sync(3 + wd, 384);
+        }
+      } else {
+        __syncthreads();
+      }
       AF_T(7);
       if (last_g) geo = geo_next;
     }
