@@ -55,6 +55,14 @@ struct Cfg {
   static constexpr int NCH = HID / NC;                     // hidden chunks per tile
   static constexpr int KB1 = (C + 63) / 64;                // k-blocks of fc1 (K = C)
   static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;  // k-steps in the last fc1 k-block
+  // proj kernel: the fc1 bias rides the MMA when the last k-block has a spare 16-column k-step (C = 96): x1[:, C] = x1[:, C + 1] = 1
+  // against two extra weight columns holding the bias as an fp16 (hi, lo) pair - the GELU pass loses its bias loads and adds
+  // (40 of ~400 instructions per chunk in an issue-bound loop) for one more k-step of an idle tensor pipe.
+#ifndef SUNET_MLP_BIASK
+#define SUNET_MLP_BIASK 1
+#endif
+  static constexpr bool BIASK = SUNET_MLP_BIASK && (C % 64) != 0 && (C % 64) <= 48;
+  static constexpr int W1PITCH = BIASK ? KB1 * 64 : C;       // row pitch (elements) of the packed proj-variant fc1 weights
   static constexpr int NXBUF = C <= 96 ? 2 : 1;            // token-tile buffers
   static constexpr int NYBUF = C <= 128 ? 2 : 1;           // fc2 accumulators in TMEM
   // C = 96 ring depths: 2 fc1 slots + 4 fc2 / proj slots (80 KB) instead of 3 + 3 (84 KB): the fc2 ring is the one whose refill
@@ -627,7 +635,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
           const int s = (PRE && whole) ? slots[kb] : r1_acquire();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + K::OFF_X + (xb * K::KB1 + kb) * KBYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + K::OFF_R1 + s * KBYTES));
-          constexpr int KS_LAST = K::KTAIL;
+          constexpr int KS_LAST = K::KTAIL + (K::BIASK ? 1 : 0);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -877,6 +885,12 @@ __global__ void __launch_bounds__(PTHREADS, 1)
           const int gi = quarter * K::QCH + i;
           sts128(xs + (gi >> 3) * KBYTES + row * 128 + ((static_cast<uint32_t>(gi & 7) ^ sw) << 4), o);
         }
+        if constexpr (K::BIASK) {   // columns C, C + 1 = 1.0 (fp16 0x3C00), C + 2 .. C + 7 = 0: the bias k-step (its other 8 columns are the TMA zero fill)
+          if (quarter == 3) {
+            constexpr int gb = C / 8;
+            sts128(xs + (gb >> 3) * KBYTES + row * 128 + ((static_cast<uint32_t>(gb & 7) ^ sw) << 4), make_uint4(0x3C003C00u, 0u, 0u, 0u));
+          }
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -916,7 +930,8 @@ __global__ void __launch_bounds__(PTHREADS, 1)
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 bq = hb4[i];   // warp-uniform address: broadcast
+          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (!K::BIASK) bq = hb4[i];   // warp-uniform address: broadcast  (BIASK: the bias is already in the accumulator)
           const float g0 = gelu_half_arg(__uint_as_float(v[4 * i + 0]) + bq.x), g1 = gelu_half_arg(__uint_as_float(v[4 * i + 1]) + bq.y);
           const float g2 = gelu_half_arg(__uint_as_float(v[4 * i + 2]) + bq.z), g3 = gelu_half_arg(__uint_as_float(v[4 * i + 3]) + bq.w);
           const __half2 p0 = __floats2half2_rn(g0, g1), p1 = __floats2half2_rn(g2, g3);
@@ -1074,20 +1089,28 @@ __global__ void mlp_fold_ln_kernel(const float* __restrict__ w1, const float* __
   if (lane == 0) hconst[n] = make_float2(s, bb + (b1 ? b1[n] : 0.f));
 }
 
-// proj variant: W1h = fp16(0.5 * W1 * gamma), hbias = 0.5 * (b1 + W1 beta)  (LayerNorm runs in the kernel, GELU takes u = x / 2)
+// proj variant: W1h = fp16(0.5 * W1 * gamma), hbias = 0.5 * (b1 + W1 beta)  (LayerNorm runs in the kernel, GELU takes u = x / 2).
+// pitch > C (BIASK): rows are padded to whole 64-column k-blocks, columns C / C + 1 hold hbias as an fp16 (hi, lo) pair, the rest 0.
 __global__ void mlp_fold_half_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, __half* __restrict__ w1h, float* __restrict__ hbias, int HID, int C) {
+                                     const float* __restrict__ beta, __half* __restrict__ w1h, float* __restrict__ hbias, int HID, int C, int pitch) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= HID) return;
   float bb = 0.f;
   for (int k = lane; k < C; k += 32) {
     const float w = w1[static_cast<size_t>(n) * C + k];
-    w1h[static_cast<size_t>(n) * C + k] = __float2half_rn(0.5f * w * gamma[k]);
+    w1h[static_cast<size_t>(n) * pitch + k] = __float2half_rn(0.5f * w * gamma[k]);
     bb = fmaf(w, beta[k], bb);
   }
   for (int o = 16; o > 0; o >>= 1) bb += __shfl_xor_sync(0xffffffffu, bb, o);
-  if (lane == 0) hbias[n] = 0.5f * (bb + (b1 ? b1[n] : 0.f));
+  const float hb = 0.5f * (bb + (b1 ? b1[n] : 0.f));
+  if (lane == 0) hbias[n] = hb;
+  if (pitch > C) {
+    const __half hi = __float2half_rn(hb);
+    const __half lo = __float2half_rn(hb - __half2float(hi));
+    for (int k = C + lane; k < pitch; k += 32)
+      w1h[static_cast<size_t>(n) * pitch + k] = k == C ? hi : (k == C + 1 ? lo : __float2half_rn(0.f));
+  }
 }
 
 __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
@@ -1226,6 +1249,13 @@ int launch_proj_t(const MlpFusedPack& p, const __half* attn_out, const __half* s
 }  // namespace
 
 bool mlp_fused_supported(int C) { return C == 96 || C == 192; }
+int mlp_fused_w1h_pitch(int C) {
+  switch (C) {
+    case 96: return Cfg<96>::W1PITCH;
+    case 192: return Cfg<192>::W1PITCH;
+    default: return C;
+  }
+}
 
 int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* beta, const float* w1, const float* b1,
                       const float* w2, const float* b2, cudaStream_t stream) {
@@ -1248,9 +1278,10 @@ int mlp_fused_set_proj(MlpFusedPack* p, const float* wp, const float* bp, const 
                        const float* b1, cudaStream_t stream) {
   if (!p->wp || !p->bp || !p->w1h || !p->hbias) return fail(SUNET_E_ARG, "fused mlp: proj pack buffers not allocated");
   const int C = p->C;
-  mlp_fold_half_kernel<<<(4 * C + 7) / 8, 256, 0, stream>>>(w1, b1, gamma, beta, p->w1h, p->hbias, 4 * C, C);
+  const int pitch = mlp_fused_w1h_pitch(C);
+  mlp_fold_half_kernel<<<(4 * C + 7) / 8, 256, 0, stream>>>(w1, b1, gamma, beta, p->w1h, p->hbias, 4 * C, C, pitch);
   SUNET_CHECK_LAUNCH();
-  SUNET_TRY(make_tmap_2d_f16(&p->tmW1h, p->w1h, C, 4 * C, C, NC));
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW1h, p->w1h, pitch, 4 * C, pitch, NC));
   cast_f16_kernel<<<148, 256, 0, stream>>>(wp, p->wp, static_cast<size_t>(C) * C);
   SUNET_CHECK_LAUNCH();
   if (bp) SUNET_CUDA(cudaMemcpyAsync(p->bp, bp, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));

@@ -19,7 +19,7 @@ struct MlpFusedPack {
   float* b2 = nullptr;       // [C]
   __half* wp = nullptr;      // [C][C]   fp16( attn.proj.weight )   (proj + shortcut + MLP variant)
   float* bp = nullptr;       // [C]      attn.proj.bias
-  __half* w1h = nullptr;     // [4C][C]  fp16( 0.5 * fc1.weight * gamma[k] )   (proj variant: LayerNorm runs in the kernel)
+  __half* w1h = nullptr;     // [4C][mlp_fused_w1h_pitch(C)]  fp16( 0.5 * fc1.weight * gamma[k] )  (+ the bias columns)   (proj variant: LayerNorm runs in the kernel)
   float* hbias = nullptr;    // [4C]     0.5 * (fc1.bias + fc1.weight beta)
   int has_proj = 0;
   alignas(64) CUtensorMap tmW1;
@@ -29,6 +29,8 @@ struct MlpFusedPack {
 };
 
 bool mlp_fused_supported(int C);
+// row pitch (elements) of the w1h pack buffer: C, or C rounded up to whole 64-column k-blocks when the fc1 bias rides the MMA (C = 96)
+int mlp_fused_w1h_pitch(int C);
 // fp32 parameters (device) -> pack; w1g / w2 / hconst / b2 must already be allocated by the caller
 int mlp_fused_prepack(MlpFusedPack* p, int C, const float* gamma, const float* beta, const float* w1, const float* b1,
                       const float* w2, const float* b2, cudaStream_t stream);

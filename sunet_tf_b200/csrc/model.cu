@@ -259,7 +259,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
         if (P.has(pre + "attn.proj.bias")) SUNET_TRY(P.get(pre + "attn.proj.bias", dim, &bp));
         SUNET_TRY(ar.alloc_t(&mf.wp, static_cast<size_t>(dim) * dim));
         SUNET_TRY(ar.alloc_t(&mf.bp, dim));
-        SUNET_TRY(ar.alloc_t(&mf.w1h, static_cast<size_t>(4) * dim * dim));
+        SUNET_TRY(ar.alloc_t(&mf.w1h, static_cast<size_t>(4) * dim * mlp_fused_w1h_pitch(dim)));
         SUNET_TRY(ar.alloc_t(&mf.hbias, static_cast<size_t>(4) * dim));
         SUNET_TRY(mlp_fused_set_proj(&mf, wp, bp, gw, gb, w1, b1, s));
       }
