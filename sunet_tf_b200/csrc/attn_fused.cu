@@ -97,6 +97,14 @@ struct FCfg {
   static constexpr int NPM = NGC / NMMA;
   static constexpr int KB = (C + 63) / 64;       // 64-wide k-blocks (one 128-byte swizzle row each)
   static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;
+  // The qkv bias rides the MMA where the last k-block has a spare 16-column k-step (C = 96): token columns C, C + 1 hold 1.0 against
+  // two extra weight columns with the folded bias as an fp16 (hi, lo) pair; the drain then is TMEM -> fp16 -> smem with no bias loads
+  // or adds (90 of its ~160 instructions per tile and thread).
+#ifndef SUNET_AF_BIASK
+#define SUNET_AF_BIASK 1
+#endif
+  static constexpr bool BIASK = SUNET_AF_BIASK && (C % 64) != 0 && (C % 64) <= 48;
+  static constexpr int WPITCH = BIASK ? KB * 64 : C;   // row pitch (elements) of the packed weights
   static constexpr int RB = HD_PAD * 2;          // bytes per q/k/v operand row
   static constexpr int UNIT_BYTES = 64 * RB;     // one (q|k|v, window, head) operand tile
   static constexpr int NU = 2 * GH;              // (window, head) units per pass
@@ -127,6 +135,7 @@ struct FCfg {
   static_assert(WPU >= 1 && WPU <= 4 && WPU * NU <= 16 && MT * WPU == 4, "warp / unit split");
   static_assert(!RING || NMMA == 1, "the k-block ring carries one MMA-wide sub-tile per stage");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(!BIASK || !RING, "the bias k-step is only wired into the whole-buffer weight path");
 };
 
 // byte offset of 16-byte chunk `ch` of row `row` inside a [64][HD_PAD] operand tile: consecutive rows are RB bytes apart and
@@ -295,13 +304,15 @@ __device__ __forceinline__ void drain_store(const uint32_t (&v)[BATCH], int c0, 
     const bool wide = SUNET_AF_DRAIN128 && (d % 8 == 0) && (d + 8 <= K::HD) && (i + 8 <= BATCH);
     const bool second = SUNET_AF_DRAIN128 && (d % 8 == 4) && (d + 4 <= K::HD) && (i >= 4);   // upper half of a chunk stored by the previous step
     if (second) continue;
-    const float4 b4 = *reinterpret_cast<const float4*>(bf + n);
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (!K::BIASK) b4 = *reinterpret_cast<const float4*>(bf + n);   // (BIASK: the bias is already in the accumulator)
     const uint32_t dst = d_base + (m * K::NU + hl) * K::UNIT_BYTES + (d & 7) * 2 + ((static_cast<uint32_t>(d >> 3) << 4) ^ d_sx);
     const uint32_t lo0 = pack_half2(__uint_as_float(v[i + 0]) + b4.x, __uint_as_float(v[i + 1]) + b4.y);
     const uint32_t lo1 = pack_half2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w);
     if (wide) {
       const int i4 = (i + 4 < BATCH) ? i + 4 : i;   // (always i + 4 when wide; keeps the index in range for the discarded branch)
-      const float4 c4 = *reinterpret_cast<const float4*>(bf + n + 4);
+      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (!K::BIASK) c4 = *reinterpret_cast<const float4*>(bf + n + 4);
       sts128(dst, make_uint4(lo0, lo1, pack_half2(__uint_as_float(v[i4 + 0]) + c4.x, __uint_as_float(v[i4 + 1]) + c4.y),
                              pack_half2(__uint_as_float(v[i4 + 2]) + c4.z, __uint_as_float(v[i4 + 3]) + c4.w)));
     } else {
@@ -395,6 +406,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       const uint32_t addr = sQKV + unit * K::UNIT_BYTES + op_off<RB>(r, d >> 3) + (d & 7) * 2;
       const uint32_t val = (unit / K::NU == 2 && w == 0) ? 0x00003C00u : 0u;
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+    }
+  }
+  if constexpr (K::BIASK) {
+    // bias k-step of the token tile, written once: columns C, C + 1 = 1.0 (fp16 0x3C00), C + 2 .. C + 15 = 0.  The gather and the
+    // LayerNorm only ever touch the C / 8 data chunks of a row.
+    if (tid < 128) {
+      constexpr int gb = C / 8;
+      const uint32_t rowb = sX + (gb >> 3) * 16384 + tid * 128;
+      sts128(rowb + ((static_cast<uint32_t>(gb & 7) ^ static_cast<uint32_t>(tid & 7)) << 4), make_uint4(0x3C003C00u, 0u, 0u, 0u));
+      sts128(rowb + ((static_cast<uint32_t>((gb + 1) & 7) ^ static_cast<uint32_t>(tid & 7)) << 4), make_uint4(0u, 0u, 0u, 0u));
+      fence_proxy_async_smem();
     }
   }
   tc_fence_before();
@@ -524,7 +546,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     if (elect_one()) {
 #pragma unroll
       for (int kb = 0; kb < K::KB; ++kb) {
-        const int ksteps = kb == K::KB - 1 ? K::KTAIL : 4;
+        const int ksteps = kb == K::KB - 1 ? K::KTAIL + (K::BIASK ? 1 : 0) : 4;
         const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
 #pragma unroll
         for (int k = 0; k < ksteps; ++k)
@@ -767,7 +789,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
 // ---- pre-pack: permuted rows, W * gamma (q rows additionally * qscale), row sums of the rounded weights, folded bias
 __global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __restrict__ bqkv, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ wp, float* __restrict__ hconst, int C, int HD,
-                                 int GH, float qscale) {
+                                 int GH, float qscale, int pitch) {
   const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pr >= 3 * C) return;
@@ -779,11 +801,18 @@ __global__ void attn_fold_kernel(const float* __restrict__ wqkv, const float* __
   float bb = 0.f;
   for (int k = lane; k < C; k += 32) {
     const float w = wqkv[static_cast<size_t>(o) * C + k];
-    wp[static_cast<size_t>(pr) * C + k] = __float2half_rn(w * gamma[k] * sc);
+    wp[static_cast<size_t>(pr) * pitch + k] = __float2half_rn(w * gamma[k] * sc);
     bb = fmaf(w, beta[k], bb);
   }
   for (int off = 16; off > 0; off >>= 1) bb += __shfl_xor_sync(0xffffffffu, bb, off);
-  if (lane == 0) hconst[pr] = (bb + (bqkv ? bqkv[o] : 0.f)) * sc;
+  const float hb = (bb + (bqkv ? bqkv[o] : 0.f)) * sc;
+  if (lane == 0) hconst[pr] = hb;
+  if (pitch > C) {   // bias k-step: (hi, lo) fp16 pair at columns C, C + 1, zeros up to the pitch
+    const __half hi = __float2half_rn(hb);
+    const __half lo = __float2half_rn(hb - __half2float(hi));
+    for (int k = C + lane; k < pitch; k += 32)
+      wp[static_cast<size_t>(pr) * pitch + k] = k == C ? hi : (k == C + 1 ? lo : __float2half_rn(0.f));
+  }
 }
 
 template <int C, int GH>
@@ -835,6 +864,14 @@ constexpr int group_heads(int C) { return C == 96 ? 8 : (C == 192 ? 2 : 1); }
 }  // namespace
 
 bool attn_fused_supported(int C, int heads) { return heads == 8 && (C == 96 || C == 192 || C == 384); }
+int attn_fused_w_pitch(int C) {
+  switch (C) {
+    case 96: return FCfg<96, group_heads(96)>::WPITCH;
+    case 192: return FCfg<192, group_heads(192)>::WPITCH;
+    case 384: return FCfg<384, group_heads(384)>::WPITCH;
+    default: return C;
+  }
+}
 
 int attn_fused_prepack(AttnFusedPack* p, int C, int heads, float qscale, const float* gamma, const float* beta, const float* wqkv,
                        const float* bqkv, const float* table, cudaStream_t stream) {
@@ -842,11 +879,12 @@ int attn_fused_prepack(AttnFusedPack* p, int C, int heads, float qscale, const f
   if (!p->w || !p->hconst) return fail(SUNET_E_ARG, "fused attention: pack buffers not allocated");
   p->C = C; p->heads = heads; p->table = table;
   const int GH = group_heads(C), HD = C / heads;
-  attn_fold_kernel<<<(3 * C + 7) / 8, 256, 0, stream>>>(wqkv, bqkv, gamma, beta, p->w, p->hconst, C, HD, GH, qscale);
+  const int pitch = attn_fused_w_pitch(C);
+  attn_fold_kernel<<<(3 * C + 7) / 8, 256, 0, stream>>>(wqkv, bqkv, gamma, beta, p->w, p->hconst, C, HD, GH, qscale, pitch);
   SUNET_CHECK_LAUNCH();
   const int NGC = 3 * GH * HD;
   const int NPM = NGC > 256 ? NGC / 3 : NGC;
-  SUNET_TRY(make_tmap_2d_f16(&p->tmW, p->w, C, 3 * C, C, NPM));
+  SUNET_TRY(make_tmap_2d_f16(&p->tmW, p->w, pitch, 3 * C, pitch, NPM));
   return 0;
 }
 

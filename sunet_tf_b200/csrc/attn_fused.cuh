@@ -12,13 +12,15 @@ namespace sunet {
 
 struct AttnFusedPack {
   int C = 0, heads = 0;
-  __half* w = nullptr;          // [3C][C] qkv weight: rows permuted to [head group][q|k|v][head][d], LN gamma folded, q rows scaled
+  __half* w = nullptr;          // [3C][attn_fused_w_pitch(C)] qkv weight (+ the bias columns): rows permuted to [head group][q|k|v][head][d], LN gamma folded, q rows scaled
   float* hconst = nullptr;      // float [3C]: folded bias (b + W beta, q rows scaled) in the same row order
   const float* table = nullptr; // relative_position_bias_table fp32 [225][heads] (device)
   alignas(64) CUtensorMap tmW;
 };
 
 bool attn_fused_supported(int C, int heads);
+// row pitch (elements) of the packed weight buffer w: C, or C rounded up to whole 64-column k-blocks where the qkv bias rides the MMA (C = 96)
+int attn_fused_w_pitch(int C);
 // gamma/beta: norm1; wqkv [3C][C], bqkv [3C] or null; qscale = qk_scale * log2(e)
 int attn_fused_prepack(AttnFusedPack* p, int C, int heads, float qscale, const float* gamma, const float* beta, const float* wqkv,
                        const float* bqkv, const float* table, cudaStream_t stream);

@@ -235,7 +235,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       SUNET_TRY(P.get(pre + "norm1.bias", dim, &gb));
       SUNET_TRY(P.get(pre + "attn.qkv.weight", static_cast<int64_t>(3) * dim * dim, &wq));
       if (P.has(pre + "attn.qkv.bias")) SUNET_TRY(P.get(pre + "attn.qkv.bias", 3 * dim, &bq));
-      SUNET_TRY(ar.alloc_t(&af.w, static_cast<size_t>(3) * dim * dim));
+      SUNET_TRY(ar.alloc_t(&af.w, static_cast<size_t>(3) * dim * attn_fused_w_pitch(dim)));
       SUNET_TRY(ar.alloc_t(&af.hconst, static_cast<size_t>(6) * dim));
       SUNET_TRY(attn_fused_prepack(&af, dim, heads, attn.scale * 1.4426950408889634f, gw, gb, wq, bq, attn.table, s));
     }
