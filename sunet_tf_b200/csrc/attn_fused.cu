@@ -95,15 +95,19 @@ struct FCfg {
   static constexpr int NGC = 3 * BR;             // accumulator columns per head group
   static constexpr int NMMA = NGC > 256 ? 3 : 1; // tcgen05.mma instructions per k-step (N <= 256 each)
   static constexpr int NPM = NGC / NMMA;
-  static constexpr int KB = (C + 63) / 64;       // 64-wide k-blocks (one 128-byte swizzle row each)
+  static constexpr int KBD = (C + 63) / 64;      // 64-wide k-blocks of token data (one 128-byte swizzle row each)
   static constexpr int KTAIL = (C % 64) ? (C % 64) / 16 : 4;
-  // The qkv bias rides the MMA where the last k-block has a spare 16-column k-step (C = 96): token columns C, C + 1 hold 1.0 against
-  // two extra weight columns with the folded bias as an fp16 (hi, lo) pair; the drain then is TMEM -> fp16 -> smem with no bias loads
-  // or adds (90 of its ~160 instructions per tile and thread).
+  // The qkv bias rides the MMA: token columns C, C + 1 hold 1.0 against two extra weight columns with the folded bias as an fp16
+  // (hi, lo) pair, in the spare 16-column k-step of the last k-block (BIASK 1: C = 96) or in one more k-block of which a single
+  // k-step is multiplied (BIASK 2: C = 192, where shared memory has room for it).  The drain then is TMEM -> fp16 -> smem with no
+  // bias loads or adds (90 of its ~160 instructions per thread and 72 columns).
 #ifndef SUNET_AF_BIASK
 #define SUNET_AF_BIASK 1
 #endif
-  static constexpr bool BIASK = SUNET_AF_BIASK && (C % 64) != 0 && (C % 64) <= 48;
+  static constexpr int BIASK = !SUNET_AF_BIASK ? 0
+                               : ((C % 64) != 0 && (C % 64) <= 48) ? 1
+                               : ((C % 64) == 0 && (KBD + 1) * NGC * 128 <= 80 * 1024) ? 2 : 0;
+  static constexpr int KB = KBD + (BIASK == 2 ? 1 : 0);   // k-blocks of the token tile / weight buffer / MMA loop
   static constexpr int WPITCH = BIASK ? KB * 64 : C;   // row pitch (elements) of the packed weights
   static constexpr int RB = HD_PAD * 2;          // bytes per q/k/v operand row
   static constexpr int UNIT_BYTES = 64 * RB;     // one (q|k|v, window, head) operand tile
@@ -136,6 +140,7 @@ struct FCfg {
   static_assert(!RING || NMMA == 1, "the k-block ring carries one MMA-wide sub-tile per stage");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(!BIASK || !RING, "the bias k-step is only wired into the whole-buffer weight path");
+  static_assert(!RING || KB == KBD, "RING mode streams data k-blocks only");
 };
 
 // byte offset of 16-byte chunk `ch` of row `row` inside a [64][HD_PAD] operand tile: consecutive rows are RB bytes apart and
@@ -546,7 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
     if (elect_one()) {
 #pragma unroll
       for (int kb = 0; kb < K::KB; ++kb) {
-        const int ksteps = kb == K::KB - 1 ? K::KTAIL + (K::BIASK ? 1 : 0) : 4;
+        const int ksteps = kb < K::KBD - 1 ? 4 : (kb == K::KBD - 1 ? K::KTAIL + (K::BIASK == 1 ? 1 : 0) : 1);   // (kb == KBD: the bias k-block, one k-step)
         const uint64_t adesc = umma_desc_sw128(sX + kb * 16384);
 #pragma unroll
         for (int k = 0; k < ksteps; ++k)
