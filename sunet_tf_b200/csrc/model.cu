@@ -217,6 +217,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
   bool use_proj_ln = false, use_row_gemm = false;   // C = 384 whole-row kernels (proj + shortcut + norm2; fc2 + residual)
   MlpRowPack mr;        // C = 384: fc1 + GELU + fc2 + residual as one whole-row kernel (the hidden activation stays on the SM)
   bool use_row_mlp = false;
+  int64_t row_min_m = 2048;   // rows below which the C = 384 back half runs as proj_ln + GEMMs (SUNET_ROW_MLP_MIN_M at pre-pack: tests force 0)
   int pack(Arena& ar, const Params& P, const std::string& pre, int dim_, int H_, int W_, int heads_, int shift_, double qk_scale,
            cudaStream_t s) {
     dim = dim_; H = H_; W = W_; heads = heads_; shift = shift_;
@@ -270,6 +271,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     use_proj_ln = !use_mf && proj_ln_supported(dim) && getenv("SUNET_NO_PROJ_LN") == nullptr;
     use_row_gemm = row_gemm_supported(dim, 4 * dim) && getenv("SUNET_NO_ROW_GEMM") == nullptr;
     use_row_mlp = use_proj_ln && mlp_row_supported(dim) && getenv("SUNET_NO_ROW_MLP") == nullptr;
+    if (const char* e = getenv("SUNET_ROW_MLP_MIN_M")) row_min_m = atoll(e);
     if (use_row_mlp) {
       Linear fc1h;   // 0.5 * fc1 (weights and bias): the GELU epilogue of the whole-row kernel takes u = x / 2
       SUNET_TRY(pack_linear(ar, P, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias", 4 * dim, dim, &fc1h, s, 4 * dim, 0.5f));
@@ -315,16 +317,20 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     ScratchMark mk(c.sc);
     const int64_t M = static_cast<int64_t>(B) * H * W;
     __half *T, *QKV, *O, *Hd;
-    SUNET_TRY(c.sc.take_t(&T, (use_af && (use_mf || (use_row_mlp && mr.has_proj))) ? 0 : M * dim));
+    // The whole-row kernel runs one tile per CTA pair, twelve hidden chunks in sequence: ~40 us however few rows there are.  Below
+    // 2048 rows (batch < 8 at stage 2) the proj_ln + two-GEMM path, which spreads a small M over all SMs, has the lower latency
+    // (batch 1: 2.27 -> 2.16 ms per forward, profiles/r06_latency.json).
+    const bool row_mlp = use_row_mlp && M >= row_min_m;
+    SUNET_TRY(c.sc.take_t(&T, (use_af && (use_mf || (row_mlp && mr.has_proj))) ? 0 : M * dim));
     SUNET_TRY(c.sc.take_t(&QKV, use_af ? 0 : M * 3 * dim));
     SUNET_TRY(c.sc.take_t(&O, M * dim));
-    SUNET_TRY(c.sc.take_t(&Hd, (use_mf || use_row_mlp) ? 0 : M * 4 * dim));
+    SUNET_TRY(c.sc.take_t(&Hd, (use_mf || row_mlp) ? 0 : M * 4 * dim));
     SUNET_TRY(attention_part(c, x_in, O, T, QKV, B));
     if (use_mf && mf.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one kernel
       RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim, mlp_proj_fused_launch(mf, O, x_in, x_out, M, c.stream));
       return 0;
     }
-    if (use_row_mlp && mr.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one CTA-pair whole-row kernel
+    if (row_mlp && mr.has_proj) {   // :136 proj, :261 shortcut add, :262 norm2 + Mlp + residual: one CTA-pair whole-row kernel
       RUN(c, K_MLP_FUSED, 18.0 * M * dim * dim, 6.0 * M * dim + 18.0 * dim * dim, mlp_row_proj_launch(mr, O, x_in, x_out, M, c.stream));
       return 0;
     }
@@ -333,7 +339,7 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       ProjLnPack pl;
       pl.w = attn.proj.w; pl.bias = attn.proj.b; pl.gamma = g2; pl.beta = b2; pl.C = dim;
       RUN(c, K_GEMM, 2.0 * M * dim * dim, 8.0 * M * dim + 2.0 * dim * dim, proj_ln_launch(pl, O, x_in, x_out, T, M, c.stream));
-      if (use_row_mlp) {   // :19-22, :262: fc1 + GELU + fc2 + second residual, the hidden activation never leaves the SM
+      if (row_mlp) {   // :19-22, :262: fc1 + GELU + fc2 + second residual, the hidden activation never leaves the SM
         RUN(c, K_MLP_FUSED, 16.0 * M * dim * dim, 6.0 * M * dim + 16.0 * dim * dim, mlp_row_launch(mr, T, x_out, x_out, M, c.stream));
         return 0;
       }

@@ -215,6 +215,7 @@ def test_row_mlp_kernel_agrees_with_separate_kernels(dev, grid, batch, monkeypat
     dim, shift = 384, 4
     sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, shift), seed=4321, style="stress")
     x = module_input((batch, grid * grid, dim), seed=4322)
+    monkeypatch.setenv("SUNET_ROW_MLP_MIN_M", "0")   # below 2048 rows the block would take the GEMM path on its own (latency)
 
     def build():
         return load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=shift, qk_scale=8), sd, dev)
