@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fused_kernel(const __grid_co
       sTbl[h * TBL + e] = __ldg(p.table + i) * LOG2E;
     }
   }
-  for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
+  if constexpr (!K::BIASK)   // (BIASK: the folded bias is in the weights, the drain does not read this table)
+    for (int i = tid; i < 3 * C; i += NTHREADS) reinterpret_cast<float*>(smem + K::OFF_HC)[i] = __ldg(p.hconst + i);
   if constexpr (K::HD_PAD != HD) {
     // pad columns of every operand tile: 0 for q / k, V column HD = 1.0 (softmax denominator through the MMA); the drain and
     // the O store only ever write columns < HD, so this survives the whole kernel

@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(PTHREADS, 1)
   }
   {
     float* hb = reinterpret_cast<float*>(smem + K::OFF_HC);
-    for (int i = threadIdx.x; i < K::HID; i += PTHREADS) hb[i] = __ldg(p.hbias + i);
+    if constexpr (!K::BIASK)   // (BIASK: the bias is in the weights, nothing reads this table)
+      for (int i = threadIdx.x; i < K::HID; i += PTHREADS) hb[i] = __ldg(p.hbias + i);
     float* b2s = reinterpret_cast<float*>(smem + K::OFF_B2);
     float* bps = reinterpret_cast<float*>(smem + OFF_BP);
     for (int i = threadIdx.x; i < C; i += PTHREADS) { b2s[i] = __ldg(p.b2 + i); bps[i] = __ldg(p.bp + i); }
