@@ -18,7 +18,7 @@ OBJ_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libsunet_b200.so")
 STAMP_PATH = os.path.join(OBJ_DIR, "flags.stamp")
 LOCK_PATH = os.path.join(HERE, ".build.lock")
-SOURCES = ["error.cu", "gemm_tcgen05.cu", "attn_core.cu", "attn_fused.cu", "mlp_fused.cu", "mlp_row.cu", "proj_ln.cu", "tail_fused.cu", "elementwise.cu", "tiles.cu", "model.cu"]
+SOURCES = ["error.cu", "gemm_tcgen05.cu", "attn_core.cu", "attn_core_tc.cu", "attn_fused.cu", "mlp_fused.cu", "mlp_row.cu", "proj_ln.cu", "tail_fused.cu", "elementwise.cu", "tiles.cu", "model.cu"]
 BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -12,6 +12,7 @@
 
 #include "../../include/sunet_b200.h"
 #include "attn_core.cuh"
+#include "attn_core_tc.cuh"
 #include "attn_fused.cuh"
 #include "elementwise.cuh"
 #include "error.h"
@@ -214,6 +215,8 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
   bool use_mf = false;
   AttnFusedPack af;     // norm1 + shift/partition + qkv + attention core + reverse/un-shift as one kernel
   bool use_af = false;
+  float* bias_exp = nullptr;   // [heads][64][64] relative-position bias, times log2(e): the tcgen05 attention core reads whole rows
+  bool use_tc_core = false;    // head_dim 96 on a one-window grid (stage 3): QK^T and PV on tcgen05 (attn_core_tc.cu)
   bool use_proj_ln = false, use_row_gemm = false;   // C = 384 whole-row kernels (proj + shortcut + norm2; fc2 + residual)
   MlpRowPack mr;        // C = 384: fc1 + GELU + fc2 + residual as one whole-row kernel (the hidden activation stays on the SM)
   bool use_row_mlp = false;
@@ -239,6 +242,11 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
       SUNET_TRY(ar.alloc_t(&af.w, static_cast<size_t>(3) * dim * attn_fused_w_pitch(dim)));
       SUNET_TRY(ar.alloc_t(&af.hconst, static_cast<size_t>(6) * dim));
       SUNET_TRY(attn_fused_prepack(&af, dim, heads, attn.scale * 1.4426950408889634f, gw, gb, wq, bq, attn.table, s));
+    }
+    use_tc_core = !use_af && attn_core_tc_supported(dim, heads, H, W, shift) && getenv("SUNET_NO_TC_CORE") == nullptr;
+    if (use_tc_core) {
+      SUNET_TRY(ar.alloc_t(&bias_exp, static_cast<size_t>(heads) * 4096));
+      SUNET_TRY(attn_core_tc_expand_bias(attn.table, heads, bias_exp, s));
     }
     use_mf = mlp_fused_supported(dim) && getenv("SUNET_NO_FUSED_MLP") == nullptr;
     if (use_mf) {
@@ -305,6 +313,10 @@ struct BlockPack {  // SwinTransformerBlock (SUNet_detail.py:176-225)
     } else {
       RUN(c, K_LAYERNORM, 0.0, 4.0 * M * dim, layernorm_f16(x_in, dim, T, dim, g1, b1, M, dim, c.stream));                     // :233
       SUNET_TRY(run_linear(c, attn.qkv, T, dim, M, QKV, 3 * dim));                             // :114
+      if (use_tc_core) {   // one window per image, no shift: q/k/v tiles by TMA, S and O in TMEM
+        RUN(c, K_ATTN, 256.0 * M * dim, 8.0 * M * dim, attn_core_tc_launch(QKV, 3 * dim, O, dim, M, dim, heads, bias_exp, c.stream));   // :118-135
+        return 0;
+      }
       AttnCoreArgs a;
       a.qkv = QKV; a.ld = 3 * dim; a.out = O; a.ldo = dim; a.B = B; a.H = H; a.W = W; a.C = dim; a.heads = heads;
       a.shift = shift; a.bias_table = attn.table; a.mask_mode = shift > 0 ? 1 : 0;

@@ -232,6 +232,29 @@ def test_row_mlp_kernel_agrees_with_separate_kernels(dev, grid, batch, monkeypat
     report(f"row-mlp-vs-gemms grid{grid} batch{batch}", y_row, y_gemm.cpu(), MODULE_TOL)
 
 
+@pytest.mark.parametrize("batch", [1, 3, 64, 300])
+def test_tcgen05_attention_core_agrees_with_mma_sync_core(dev, batch, monkeypatch):
+    """C = 768 on the 8x8 grid of stage 3 (one window per image, shift forced to 0 by SUNet_detail.py:186-189): QK^T + bias, softmax
+    and PV on tcgen05 with S / O in TMEM (attn_core_tc.cu) against the register-resident mma.sync core (SUNET_NO_TC_CORE) and the
+    oracle.  The kernel works on pairs of images: batch 1 and 3 end in a half-empty pair, batch 300 = 600 units on 148 CTAs is the
+    multi-unit path (barrier phases, output staging handed back to the next unit's loads)."""
+    from sunet_tf_b200 import SwinTransformerBlock
+    dim, grid = 768, 8
+    sd = Wt.synth_state_dict(Wt.block_spec("", dim, grid, grid, 4), seed=768, style="stress")
+    x = module_input((batch, grid * grid, dim), seed=769)
+
+    def build():
+        return load_sd(SwinTransformerBlock(dim, (grid, grid), 8, window_size=8, shift_size=4, qk_scale=8), sd, dev)
+
+    y_tc = build()(x.to(dev))
+    monkeypatch.setenv("SUNET_NO_TC_CORE", "1")
+    y_mma = build()(x.to(dev))
+    nref = min(batch, 3)
+    ref = O.swin_block(sd, "", x[:nref], grid, grid, 8, 0, 8)
+    report(f"tc-core-vs-oracle batch{batch}", y_tc[:nref], ref, MODULE_TOL)
+    report(f"tc-core-vs-mma-core batch{batch}", y_tc, y_mma.cpu(), MODULE_TOL)
+
+
 def test_swin_block_default_scale_and_rect_grid(dev):
     """qk_scale=None -> head_dim**-0.5 (SUNet_detail.py:80); rectangular token grid"""
     from sunet_tf_b200 import SwinTransformerBlock

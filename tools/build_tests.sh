@@ -9,3 +9,5 @@ $NV -o build/test_units sunet_tf_b200/csrc/tests/test_units.cu
 echo built build/test_gemm build/test_units
 $NV -o build/test_ingest sunet_tf_b200/csrc/tests/test_ingest.cu -lcuda
 echo built build/test_ingest
+$NV -o build/test_attn_tc sunet_tf_b200/csrc/tests/test_attn_tc.cu sunet_tf_b200/csrc/attn_core_tc.cu sunet_tf_b200/csrc/attn_core.cu sunet_tf_b200/csrc/gemm_tcgen05.cu sunet_tf_b200/csrc/error.cu -lcuda
+echo built build/test_attn_tc
