@@ -477,7 +477,7 @@ struct TailPack {
     SUNET_TRY(ar.alloc_t(&gb.w, static_cast<size_t>(NT) * E));
     SUNET_TRY(fold_tail_taps(wo, up.Ap, gp.w, OC, E, NT, s));
     SUNET_TRY(fold_tail_taps(wo, up.Ab, gb.w, OC, E, NT, s));
-    fused = tail_up_fused_supported(E, NT) && getenv("SUNET_NO_FUSED_TAIL") == nullptr;
+    fused = tail_up_fused_supported(E, NT, W) && getenv("SUNET_NO_FUSED_TAIL") == nullptr;
     return 0;
   }
   int forward(Ctx& c, const __half* x, void* out, int B) const {
@@ -486,18 +486,21 @@ struct TailPack {
     __half *Pb, *Bb;
     float *Qp, *Rb;
     SUNET_TRY(c.sc.take_t(&Pb, fused ? 0 : M * 16 * E));
-    SUNET_TRY(c.sc.take_t(&Qp, M * 16 * NT));
+    SUNET_TRY(c.sc.take_t(&Qp, fused ? tail_strips_floats(M) : M * 16 * NT));
     SUNET_TRY(c.sc.take_t(&Bb, M * E));
     SUNET_TRY(c.sc.take_t(&Rb, M * NT));
-    if (fused) {   // up_p[0..1] and the folded taps in one kernel: the [M][16 * 96] activation stays on the SM
-      RUN(c, K_TAIL_FUSED, 2.0 * M * 16 * E * E + 2.0 * M * 16 * NT * E, 2.0 * M * E + 4.0 * M * 16 * NT,
-          tail_up_fused_launch(x, up.p0.w, gp.w, up.slope_p, Qp, M, c.stream));
-    } else {
-      SUNET_TRY(run_linear(c, up.p0, x, E, M, Pb, 16 * E, ACT_PRELU, up.slope_p));
-      SUNET_TRY(run_linear(c, gp, Pb, E, M * 16, Qp, NT, ACT_NONE, nullptr, nullptr, 0, 1));
-    }
     SUNET_TRY(run_linear(c, up.b0, x, E, M, Bb, E, ACT_PRELU, up.slope_b));
     SUNET_TRY(run_linear(c, gb, Bb, E, M, Rb, NT, ACT_NONE, nullptr, nullptr, 0, 1));
+    if (fused) {
+      // up_p[0..1], the folded taps, the bilinear branch and the per-token part of the 3x3 stencil in one kernel: neither the
+      // [M][16 * 96] activation nor the [M * 16][16] tap values reach HBM, only 96 floats of partial output sums per token
+      RUN(c, K_TAIL_FUSED, 2.0 * M * 16 * E * E + 2.0 * M * 16 * NT * E, 2.0 * M * E + 4.0 * M * NT + 4.0 * M * 96,
+          tail_up_fused_launch(x, up.p0.w, gp.w, up.slope_p, Rb, Qp, B, H, W, c.stream));
+      RUN(c, K_TAIL, 0.0, 4.0 * M * 96 + (c.out_fmt == IMG_U8_NHWC ? 1.0 : 4.0) * M * 16 * OC, tail_finish(Qp, out, c.out_fmt, c.ev, B, H, W, c.stream));
+      return 0;
+    }
+    SUNET_TRY(run_linear(c, up.p0, x, E, M, Pb, 16 * E, ACT_PRELU, up.slope_p));
+    SUNET_TRY(run_linear(c, gp, Pb, E, M * 16, Qp, NT, ACT_NONE, nullptr, nullptr, 0, 1));
     RUN(c, K_TAIL, 0.0, 4.0 * M * NT * 17 + (c.out_fmt == IMG_U8_NHWC ? 1.0 : 4.0) * M * 16 * OC,
         tail_stencil(Qp, Rb, out, c.out_fmt, c.ev, B, H, W, OC, NT, c.stream));
     return 0;

@@ -9,8 +9,15 @@
 //   MMA1 : H   = T_tile * W_p0[ij]^T     (tcgen05, N = 96, fp32 in TMEM, double-buffered, issued two sub-pixels ahead)
 //   EPI  : G   = fp16(PReLU(H))          TMEM -> registers -> SW128 smem (A operand of MMA2)
 //   MMA2 : Q[:, 16 ij .. 16 ij + 15] = G * G_p^T    (tcgen05, N = 16; G_p stays resident in smem)
-// and after the 16 sub-pixels the 128 x 256 fp32 tile goes out with 16-byte stores (1 KB contiguous per token).
+// After the 16 sub-pixels the 128 x 256 fp32 tile of tap values does NOT go to HBM (it used to: 268 MB written, 285 MB re-read by the
+// 9-tap stencil).  The thread that owns (token, sub-pixel row sy) first adds the bilinear branch - its four sub-pixels' interpolated
+// tap maps from the per-token Rb (SUNet_detail.py:360-362, evaluated exactly as the stencil did: rows, then columns) - and then sums
+// its 4 x 9 tap values into the 3 x 6 patch of OUTPUT pixels they land on (output rows 4 ty + sy - 1 .. + 1, columns 4 tx - 1 .. 4 tx + 4).
+// These "strips" (96 bytes per thread, 100 MB per batch of 64) are all that leaves the SM; tail_finish_kernel adds the 3 - 6 strips
+// that overlap each output pixel in a fixed order.
 #include "tail_fused.cuh"
+
+#include "elementwise.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -44,7 +51,10 @@ constexpr int OFF_X = 0;                // 2 token-tile buffers x 2 k-blocks
 constexpr int OFF_HS = OFF_X + 2 * 2 * KBYTES;
 constexpr int OFF_R1 = OFF_HS + 2 * 2 * KBYTES;
 constexpr int OFF_GP = OFF_R1 + R1 * W1KB;       // [2 k-blocks][16 rows][64]
-constexpr int SMEM = OFF_GP + 2 * NT * 128 + 1024;
+constexpr int RB_MAX_W = 128;                    // widest token grid the staged bilinear taps are sized for
+constexpr int RB_TOKENS = TILE_M + 2 * RB_MAX_W + 2;
+constexpr int OFF_RB = OFF_GP + 2 * NT * 128;    // [tokens of the tile +- one image row][12] fp32: the used 9 (+3) of the 16 tap maps of Rb
+constexpr int SMEM = OFF_RB + RB_TOKENS * 48 + 1024;
 constexpr uint32_t TM_Y = 0;            // Q tile: 256 columns
 constexpr uint32_t TM_H = 256;          // H[b] at 256 + 128 b
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -58,14 +68,37 @@ static_assert(SMEM <= 227 * 1024, "shared memory budget");
 #define TF_T(i) do { } while (0)
 #endif
 
+// align_corners=False taps of the x4 bilinear up-sample along one axis (nn.Upsample, SUNet_detail.py:351 / :362); the same
+// expression as bilinear_tap() in elementwise.cu, so the interpolation weights are bit-identical to the stencil path's
+__device__ __forceinline__ void tail_bilinear_tap(int d, int n, int& i0, int& i1, float& lam) {
+  const float src = fmaxf((d + 0.5f) / 4 - 0.5f, 0.f);
+  i0 = static_cast<int>(src);
+  i1 = min(i0 + 1, n - 1);
+  lam = src - i0;
+}
+
 struct Params {
   long long* timing;    // SUNET_KERNEL_TIMING builds: [grid][16 warps][8] phase cycles
   const float* slope;   // PReLU slope (device scalar)
-  float* out;           // [M * 16][16] fp32 == [M][256]
+  float* strips;        // [M / 32][4 sub-pixel rows][32 tokens][3][8] fp32 partial output sums (see tail_finish_kernel)
+  const float* Rb;      // [M][16] fp32 tap maps of the bilinear branch at token resolution
+  int H, W;             // token grid
   int64_t M;
   int64_t tiles;
   int split;            // 1: fc2 MMAs are issued by their own thread (warp FC2_WARP), 0: interleaved with fc1 by warp 1
 };
+
+// token m (image-order index, < 2^31) and sub-pixel row sy -> its column tx, the token index of its image's first token, and the
+// vertical bilinear taps of hi-res row 4 ty + sy (32-bit arithmetic: 64-bit divisions cost ~150 instructions apiece)
+__device__ __forceinline__ unsigned tail_geo(const Params& p, unsigned m, int sy, int& tx, int& y0, int& y1, float& ly) {
+  const unsigned hw = static_cast<unsigned>(p.H * p.W);
+  const unsigned b = m / hw;
+  const unsigned rem = m - b * hw;
+  const unsigned ty = rem / static_cast<unsigned>(p.W);
+  tx = static_cast<int>(rem - ty * p.W);
+  tail_bilinear_tap(4 * static_cast<int>(ty) + sy, p.H, y0, y1, ly);
+  return b * hw;
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
     tail_up_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -315,6 +348,20 @@ __global__ void __launch_bounds__(THREADS, 1)
     // group runs under the other group's, instead of all 16 warps waiting through the same round trips together.
     const uint32_t grp = static_cast<uint32_t>(quarter >> 1), half = static_cast<uint32_t>(quarter & 1);
     for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+      // The output pass reads the bilinear branch's tap maps of the 2 x 3 tokens around every (token, sub-pixel row): the tokens of this
+      // tile and of one image row either side are staged in shared memory with coalesced 16-byte copies (a direct per-thread read
+      // touches 16 lines per instruction: 4.6k L1 wavefronts per tile, measured as +3k clk per tile), 16 sub-pixels ahead of their use
+      const int rb_lo = static_cast<int>(max(tile * TILE_M - p.W - 1, static_cast<int64_t>(0)));
+      {
+        const int rb_hi = static_cast<int>(min(tile * TILE_M + TILE_M + p.W + 1, p.M));
+        const int n4 = (rb_hi - rb_lo) * 3;
+        const float4* src = reinterpret_cast<const float4*>(p.Rb + static_cast<int64_t>(rb_lo) * NT);
+        for (int i = e * 32 + lane; i < n4; i += EPI_WARPS * 32) {
+          const int tok = i / 3, part = i - tok * 3;
+          const float4 v = __ldg(src + tok * 4 + part);
+          sts128(smem_u32(smem + OFF_RB) + i * 16, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+        }
+      }
       for (int j = static_cast<int>(grp); j < SUB; j += 2) {
         const uint32_t gg = g + static_cast<uint32_t>(j);
         const uint32_t hb = grp, ph = (gg >> 1) & 1;   // g is a multiple of 16: gg & 1 == grp
@@ -357,35 +404,98 @@ __global__ void __launch_bounds__(THREADS, 1)
         TF_T(4);
       }
       g += SUB;
-      // ---- output: Q tile columns [64 quarter, +64) of this row = sub-pixels 4 quarter .. 4 quarter + 3, 16 taps each
+      // ---- output: Q tile columns [64 quarter, +64) of this row = sub-pixels 4 quarter .. 4 quarter + 3, 16 taps each (9 used)
+      const uint32_t stg = smem_u32(smem + OFF_HS) + static_cast<uint32_t>(e) * 4096;
+      const int64_t m_warp = tile * TILE_M + q * 32;
+      const int64_t m = m_warp + lane;
+      const bool live = m_warp < p.M;   // (M is a multiple of 64: whole warps)
+      // bilinear branch: vertical taps of this thread's sub-pixel row over the three token columns the four sub-pixels can reach.
+      // Nothing here depends on the accumulator: the loads are issued before the wait for the last fc2 and land under it.
+      named_bar_sync(2, EPI_WARPS * 32);   // the staged taps of every warp are in place
+      float V[3][9] = {};
+      int tx = 0;
+      if (live) {
+        int y0, y1;
+        float ly;
+        const unsigned tokrow0 = tail_geo(p, static_cast<unsigned>(m), quarter, tx, y0, y1, ly);   // token index of (image, row 0, column 0)
+        const float ly1 = 1.f - ly;
+        const uint32_t row0 = smem_u32(smem + OFF_RB) + static_cast<uint32_t>(static_cast<int>(tokrow0) + y0 * p.W - rb_lo) * 48u;
+        const uint32_t row1 = smem_u32(smem + OFF_RB) + static_cast<uint32_t>(static_cast<int>(tokrow0) + y1 * p.W - rb_lo) * 48u;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int xc = min(max(tx - 1 + c, 0), p.W - 1);
+          const uint4 ua0 = lds128(row0 + xc * 48), ua1 = lds128(row0 + xc * 48 + 16);
+          const uint4 ub0 = lds128(row1 + xc * 48), ub1 = lds128(row1 + xc * 48 + 16);
+          float a2, b2;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(row0 + xc * 48 + 32));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b2) : "r"(row1 + xc * 48 + 32));
+          const float4 a0 = make_float4(__uint_as_float(ua0.x), __uint_as_float(ua0.y), __uint_as_float(ua0.z), __uint_as_float(ua0.w));
+          const float4 a1 = make_float4(__uint_as_float(ua1.x), __uint_as_float(ua1.y), __uint_as_float(ua1.z), __uint_as_float(ua1.w));
+          const float4 b0 = make_float4(__uint_as_float(ub0.x), __uint_as_float(ub0.y), __uint_as_float(ub0.z), __uint_as_float(ub0.w));
+          const float4 b1 = make_float4(__uint_as_float(ub1.x), __uint_as_float(ub1.y), __uint_as_float(ub1.z), __uint_as_float(ub1.w));
+          const float ra[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2};
+          const float rb[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2};
+#pragma unroll
+          for (int t = 0; t < 9; ++t) V[c][t] = ra[t] * ly1 + rb[t] * ly;
+        }
+      }
       mbar_wait(&y_full, lt & 1);
       tc_fence_after();
       TF_T(5);
-      // staged through this warp's 4 KB slice of the (idle) G buffers, 32 columns per pass: the warp then writes 4 whole 128-byte
-      // row segments per instruction instead of 32 different lines (a thread-per-row store is LSU-bound, measured)
-      const uint32_t stg = smem_u32(smem + OFF_HS) + static_cast<uint32_t>(e) * 4096;
-      const int64_t m_warp = tile * TILE_M + q * 32;
+      uint32_t y[4][9];
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t y[32];
-        tmem_ld32(tmem_base + lane_off + TM_Y + quarter * 64 + c, y);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          sts128(stg + lane * 128 + ((static_cast<uint32_t>(i) ^ static_cast<uint32_t>(lane & 7)) << 4), make_uint4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]));
-        __syncwarp();
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const int r = kk * 4 + (lane >> 3), ch = lane & 7;
-          if (m_warp + r < p.M)
-            *reinterpret_cast<uint4*>(p.out + (m_warp + r) * (SUB * NT) + quarter * 64 + c + ch * 4) =
-                lds128(stg + r * 128 + ((static_cast<uint32_t>(ch) ^ static_cast<uint32_t>(r & 7)) << 4));
-        }
-        __syncwarp();
+      for (int sx = 0; sx < 4; ++sx) {
+        tmem_ld8(tmem_base + lane_off + TM_Y + quarter * 64 + sx * 16, *reinterpret_cast<uint32_t(*)[8]>(&y[sx][0]));
+        tmem_ld1(tmem_base + lane_off + TM_Y + quarter * 64 + sx * 16 + 8, y[sx][8]);
       }
+      tmem_ld_wait();
+      float strip[3][6];
+#pragma unroll
+      for (int ry = 0; ry < 3; ++ry)
+#pragma unroll
+        for (int cx = 0; cx < 6; ++cx) strip[ry][cx] = 0.f;
+#pragma unroll
+      for (int sx = 0; sx < 4; ++sx) {
+        // horizontal taps: sub-pixels 0, 1 interpolate between token columns tx - 1 and tx, sub-pixels 2, 3 between tx and tx + 1
+        // (the clamped column loads above make the border cases come out as align_corners=False prescribes)
+        int x0, x1;
+        float lx;
+        tail_bilinear_tap(4 * tx + sx, p.W, x0, x1, lx);
+        const float lx1 = 1.f - lx;
+        const int c0 = sx < 2 ? 0 : 1;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int t = dy * 3 + dx;
+            // tap (dy, dx) of pixel (sy, sx) lands on output pixel (sy - dy + 1, sx - dx + 1)
+            float& acc = strip[2 - dy][sx - dx + 2];
+            acc += __uint_as_float(y[sx][t]);
+            acc = fmaf(V[c0][t], lx1, acc);
+            acc = fmaf(V[c0 + 1][t], lx, acc);
+          }
+      }
+      // every TMEM read of this warp is complete: hand the Q accumulator back before the stores
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&y_empty);
+      // staged through this warp's 4 KB slice of the (idle) G buffers (112-byte lane pitch: conflict-free 16-byte stores), then
+      // written as one contiguous 3 KB block per warp
+#pragma unroll
+      for (int ry = 0; ry < 3; ++ry) {
+        sts128(stg + lane * 112 + ry * 32, make_uint4(__float_as_uint(strip[ry][0]), __float_as_uint(strip[ry][1]), __float_as_uint(strip[ry][2]), __float_as_uint(strip[ry][3])));
+        sts128(stg + lane * 112 + ry * 32 + 16, make_uint4(__float_as_uint(strip[ry][4]), __float_as_uint(strip[ry][5]), 0u, 0u));
+      }
+      __syncwarp();
+      if (live) {
+        float* dst = p.strips + ((m_warp >> 5) * 4 + quarter) * (32 * 24);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int idx = k * 32 + lane;
+          const int tok = idx / 6, part = idx - tok * 6;
+          *reinterpret_cast<uint4*>(dst + idx * 4) = lds128(stg + tok * 112 + part * 16);
+        }
+      }
       named_bar_sync(1, EPI_WARPS * 32);   // every warp is done with its staging slice before the next tile's G stores reuse the buffers
       TF_T(6);
     }
@@ -402,13 +512,132 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ strips -> image
+// out(Y, X) = sum over the sub-pixel rows y' = Y - 1 .. Y + 1 (in image) of the strip of (token column X / 4, row y') at (ry = Y - y' + 1,
+// cx = X % 4 + 1), plus - for the first / last pixel column of a token - the halo column (cx = 5 / 0) of the left / right token's strip;
+// this is SUNet_detail.py:753's zero-padded 3x3 conv over conv(cat(up_p, up_b)) with everything linear folded into the tap maps.
+// CTA = 8 x 8 tokens = 32 x 32 output pixels; the strips of the 10 x 10 token neighbourhood are staged in shared memory (only the
+// parts the tile can reach: the last / first sub-pixel row of the tokens above / below, the halo columns of the tokens left / right),
+// token stride 100 words so that the 8 tokens of a pixel row hit 8 different bank groups.  The sum order is fixed (deterministic).
+// MODE 0: fp32 NCHW; 1: 8-bit NHWC, rint(clamp(v, 0, 1) * 255); 2: fp32 NCHW + validation epilogue (EvalEpilogue), as tail_stencil.
+constexpr int TF_T8 = 8;        // tokens per tile side
+constexpr int TF_N = TF_T8 + 2; // staged tokens per side
+constexpr int TF_STRIDE = 100;  // words per staged token: 4 sub-pixel rows x [3][8] + 4 pad
+
+template <int MODE>
+__global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restrict__ S, void* __restrict__ out_v, EvalEpilogue ev, int H, int W) {
+  __shared__ __align__(16) float sS[TF_N * TF_N * TF_STRIDE];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int OW = 4 * W, OH = 4 * H;
+  const int tiles_x = (W + TF_T8 - 1) / TF_T8, tiles_y = (H + TF_T8 - 1) / TF_T8;
+  const int64_t b = blockIdx.x / (tiles_x * tiles_y);
+  const int trem = blockIdx.x % (tiles_x * tiles_y);
+  const int th0 = (trem / tiles_x) * TF_T8, tw0 = (trem % tiles_x) * TF_T8;
+  const int tid = threadIdx.x;
+  {
+    constexpr int TOTAL = TF_N * TF_N * 24, BATCH = 5;   // 16-byte vectors: [token][sub-pixel row][6]
+#pragma unroll 1
+    for (int i0 = 0; i0 < TOTAL; i0 += 256 * BATCH) {
+      float4 q[BATCH];
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {   // all loads of a batch are in flight before the first shared-memory store
+        const int i = i0 + k * 256 + tid;
+        const int tokl = i / 24, r = i - tokl * 24;
+        const int sy = r / 6, v = r - sy * 6;
+        const int tr = tokl / TF_N, tc = tokl - tr * TF_N;
+        const int ty = th0 - 1 + tr, tx = tw0 - 1 + tc;
+        bool need = i < TOTAL && ty >= 0 && ty < H && tx >= 0 && tx < W;
+        need = need && (tr != 0 || sy == 3) && (tr != TF_N - 1 || sy == 0) && (tc != 0 || (v & 1) == 1) && (tc != TF_N - 1 || (v & 1) == 0);
+        q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (need) {
+          const int64_t tok = (b * H + ty) * W + tx;
+          q[k] = __ldg(reinterpret_cast<const float4*>(S + (((tok >> 5) * 4 + sy) * 32 + (tok & 31)) * 24) + v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        const int i = i0 + k * 256 + tid;
+        if (i < TOTAL) {
+          const int tokl = i / 24, r = i - tokl * 24;
+          *reinterpret_cast<float4*>(sS + tokl * TF_STRIDE + r * 4) = q[k];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  double part[4] = {0.0, 0.0, 0.0, 0.0};
+  const int lx_ = tid & 31;
+  const int tcl = (lx_ >> 2) + 1, cx = (lx_ & 3) + 1;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int ly_ = (tid >> 5) + 8 * k;
+    const int y = 4 * th0 + ly_, x = 4 * tw0 + lx_;
+    if (y >= OH || x >= OW) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yl = ly_ + dy + 3;                   // staged sub-pixel row of y' = y + dy - 1 (row 0 = first row of the token above)
+      const float* base = sS + ((yl >> 2) * TF_N) * TF_STRIDE + (yl & 3) * 24 + (2 - dy) * 8;
+      if ((lx_ & 3) == 0) acc += base[(tcl - 1) * TF_STRIDE + 5];
+      acc += base[tcl * TF_STRIDE + cx];
+      if ((lx_ & 3) == 3) acc += base[(tcl + 1) * TF_STRIDE];
+    }
+    if (MODE == 1) {
+      static_cast<uint8_t*>(out_v)[(b * OH + y) * OW + x] = static_cast<uint8_t>(__float2int_rn(fminf(fmaxf(acc, 0.f), 1.f) * 255.f));
+      continue;
+    }
+    static_cast<float*>(out_v)[(b * OH + y) * OW + x] = acc;
+    if (MODE == 2) {
+      // train.py:437-443: luminance target, prob = sigmoid(logits), se = (logits - target)^2, weighted sums, Charbonnier
+      const int64_t plane = static_cast<int64_t>(OH) * OW, pix = static_cast<int64_t>(y) * OW + x;
+      const float w = ev.weight ? __ldg(ev.weight + b * plane + pix) : 1.f;
+      float t;
+      if (ev.target_chans == 1) {
+        t = __ldg(ev.target + b * plane + pix);
+      } else {   // 3 -> 1
+        const float* tp = ev.target + b * 3 * plane + pix;
+        t = 0.2989f * __ldg(tp) + 0.5870f * __ldg(tp + plane) + 0.1140f * __ldg(tp + 2 * plane);
+      }
+      if (ev.prob) ev.prob[b * plane + pix] = 1.f / (1.f + expf(-acc));
+      const float d = acc - t, se = d * d;
+      part[0] += se;
+      part[1] += static_cast<double>(se * w);
+      part[2] += w;
+      part[3] += static_cast<double>(sqrtf(se + ev.eps * ev.eps) * w);
+    }
+  }
+  if (MODE == 2) {
+    __shared__ double red[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+      if (lane == 0) red[k][warp] = part[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int wi = 0; wi < 8; ++wi) t += red[threadIdx.x][wi];
+      atomicAdd(ev.sums + threadIdx.x, t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 4) atomicAdd(ev.sums + 4, static_cast<double>(gridDim.x / (tiles_x * tiles_y)) * OH * OW);
+  }
+}
+
 }  // namespace
 
-bool tail_up_fused_supported(int E_, int NT_) { return E_ == E && NT_ == NT; }
+bool tail_up_fused_supported(int E_, int NT_, int W) { return E_ == E && NT_ == NT && W <= RB_MAX_W; }
 
-int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p, const float* slope, float* out, int64_t M, cudaStream_t stream) {
-  if (M <= 0 || M > (int64_t)0x7fffff00) return fail(SUNET_E_SHAPE, "fused tail: bad row count %lld", (long long)M);
-  if ((reinterpret_cast<uintptr_t>(T) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(SUNET_E_ALIGN, "fused tail: T/out must be 16-byte aligned");
+int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p, const float* slope, const float* Rb, float* strips, int B,
+                         int H, int W, cudaStream_t stream) {
+  const int64_t M = static_cast<int64_t>(B) * H * W;
+  if (W > RB_MAX_W) return fail(SUNET_E_SHAPE, "fused tail: token grid wider than %d (got %d)", RB_MAX_W, W);
+  if (M <= 0 || M > (int64_t)0x7fffff00 || (static_cast<int64_t>(H) * W) % 64) return fail(SUNET_E_SHAPE, "fused tail: bad token grid %d x %d x %d", B, H, W);
+  if ((reinterpret_cast<uintptr_t>(T) & 15) || (reinterpret_cast<uintptr_t>(strips) & 15) || (reinterpret_cast<uintptr_t>(Rb) & 15))
+    return fail(SUNET_E_ALIGN, "fused tail: T / Rb / strips must be 16-byte aligned");
   static DeviceOnce once;   // the shared-memory opt-in is per device
   if (once.need()) {
     SUNET_CUDA(cudaFuncSetAttribute(tail_up_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -430,7 +659,10 @@ int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p,
   }
 #endif
   prm.slope = slope;
-  prm.out = out;
+  prm.strips = strips;
+  prm.Rb = Rb;
+  prm.H = H;
+  prm.W = W;
   prm.M = M;
   prm.tiles = (M + TILE_M - 1) / TILE_M;
   static const bool no_split = getenv("SUNET_TAIL_NO_SPLIT") != nullptr;   // read once per process
@@ -452,6 +684,23 @@ int tail_up_fused_launch(const __half* T, const __half* w_p0, const __half* g_p,
     fprintf(stderr, "\n");
   }
 #endif
+  return 0;
+}
+
+int tail_finish(const float* strips, void* out, int out_fmt, const EvalEpilogue* ev, int B, int H, int W, cudaStream_t s) {
+  const dim3 grid(static_cast<unsigned>(B) * ((H + TF_T8 - 1) / TF_T8) * ((W + TF_T8 - 1) / TF_T8)), block(256);
+  EvalEpilogue e;
+  if (ev) {
+    if (out_fmt != IMG_F32_NCHW) return fail(SUNET_E_ARG, "tail: the validation epilogue needs fp32 output");
+    if (!ev->target || !ev->sums) return fail(SUNET_E_ARG, "tail: validation epilogue without target / sums");
+    if (ev->target_chans != 1 && ev->target_chans != 3) return fail(SUNET_E_SHAPE, "tail: target has %d channels, output 1", ev->target_chans);
+    e = *ev;
+    SUNET_CUDA(launch_pdl(tail_finish_kernel<2>, grid, block, 0, s, strips, out, e, H, W));
+  } else if (out_fmt == IMG_U8_NHWC) {
+    SUNET_CUDA(launch_pdl(tail_finish_kernel<1>, grid, block, 0, s, strips, out, e, H, W));
+  } else {
+    SUNET_CUDA(launch_pdl(tail_finish_kernel<0>, grid, block, 0, s, strips, out, e, H, W));
+  }
   return 0;
 }
 
