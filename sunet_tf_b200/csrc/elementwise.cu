@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   int64_t mb = 0, mh = 0, mw = 0;
   if (active) {
     if (MERGE) {
-      const int W2 = W >> 1, H2 = H >> 1;
-      mw = row % W2; mh = (row / W2) % H2; mb = row / (static_cast<int64_t>(W2) * H2);
+      // (32-bit arithmetic: the callers bound M below 2^31; a 64-bit division is ~150 emulated instructions)
+      const unsigned W2 = static_cast<unsigned>(W >> 1), H2 = static_cast<unsigned>(H >> 1), r32 = static_cast<unsigned>(row);
+      const unsigned rw = r32 / W2, bb = rw / H2;
+      mw = r32 - rw * W2; mh = rw - bb * H2; mb = bb;
     } else {
       src_row = in + row * ld_in;
     }
@@ -176,6 +178,7 @@ int merge_gather_ln_f16(const __half* in, __half* out, const float* gamma, const
   if ((H & 1) || (W & 1)) return fail(SUNET_E_SHAPE, "patch merging: grid %dx%d must be even", H, W);
   if (C % 8) return fail(SUNET_E_SHAPE, "patch merging: C=%d must be a multiple of 8", C);
   const int64_t M = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+  if (M >= (static_cast<int64_t>(1) << 31)) return fail(SUNET_E_SHAPE, "patch merging: %lld rows exceed the 32-bit row arithmetic", (long long)M);
   return launch_ln<true>(in, 0, out, 4 * C, gamma, beta, M, 4 * C, H, W, C, s);
 }
 
@@ -542,19 +545,27 @@ __device__ __forceinline__ void bilinear_tap(int d, int r, int n, int& i0, int& 
   lam = src - i0;
 }
 
+// IdxT = unsigned when the element count fits 32 bits (every SUNet shape): the five divisions of the index decomposition are
+// ~20 instructions apiece in 32 bits and ~150 in 64 (emulated) - the 64-bit form was issue-bound at 2.3 TB/s
+template <typename IdxT>
 __global__ void __launch_bounds__(256) upsample_combine_kernel(const __half* __restrict__ Yp, const __half* __restrict__ Z,
                                                                void* __restrict__ out, int out_f32, int H, int W, int Co, int r,
                                                                int64_t total) {
   pdl_wait();
   pdl_launch_dependents();
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int nv = Co >> 3;
-  const int v = static_cast<int>(i % nv);
-  const int64_t pix = i / nv;
-  const int OW = W * r, OH = H * r;
-  const int X = static_cast<int>(pix % OW), Y = static_cast<int>((pix / OW) % OH);
-  const int64_t b = pix / (static_cast<int64_t>(OW) * OH);
+  const int64_t i64 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i64 >= total) return;
+  const IdxT i = static_cast<IdxT>(i64);
+  const IdxT nv = static_cast<IdxT>(Co >> 3);
+  const IdxT pix_t = i / nv;
+  const int v = static_cast<int>(i - pix_t * nv);
+  const IdxT OWt = static_cast<IdxT>(W * r), OHt = static_cast<IdxT>(H * r);
+  const IdxT rowt = pix_t / OWt;
+  const int X = static_cast<int>(pix_t - rowt * OWt);
+  const IdxT bt = rowt / OHt;
+  const int Y = static_cast<int>(rowt - bt * OHt);
+  const int64_t pix = static_cast<int64_t>(pix_t);
+  const int64_t b = static_cast<int64_t>(bt);
   const int h = Y / r, ii = Y % r, w = X / r, jj = X % r;
   const uint4 yp = __ldg(reinterpret_cast<const uint4*>(Yp + (((b * H + h) * W + w) * (r * r) + ii * r + jj) * Co + (v << 3)));
   int y0, y1, x0, x1;
@@ -596,7 +607,10 @@ __global__ void __launch_bounds__(256) upsample_combine_kernel(const __half* __r
 int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, int B, int H, int W, int Co, int r, cudaStream_t s) {
   if (Co % 8) return fail(SUNET_E_SHAPE, "upsample: Co=%d must be a multiple of 8", Co);
   const int64_t total = static_cast<int64_t>(B) * H * r * W * r * (Co / 8);
-  SUNET_CUDA(launch_pdl(upsample_combine_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, s, Yp, Z, out, out_f32, H, W, Co, r, total));
+  if (total < (static_cast<int64_t>(1) << 31))
+    SUNET_CUDA(launch_pdl(upsample_combine_kernel<unsigned>, dim3(blocks_for(total, 256)), dim3(256), 0, s, Yp, Z, out, out_f32, H, W, Co, r, total));
+  else
+    SUNET_CUDA(launch_pdl(upsample_combine_kernel<unsigned long long>, dim3(blocks_for(total, 256)), dim3(256), 0, s, Yp, Z, out, out_f32, H, W, Co, r, total));
   SUNET_CHECK_LAUNCH();
   return 0;
 }

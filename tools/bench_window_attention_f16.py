@@ -81,7 +81,7 @@ for C, G, B, shift in CASES:
                  "us": ms * 1e3, "windows_per_s": windows / ms * 1e3, "algorithmic_tflops": flops / ms * 1e-9,
                  "frac_of_burst_tensor_peak": flops / ms * 1e-9 / peak, "stream_gbs": 4.0 * M * C / ms * 1e-6,
                  "launches": 1 if C <= 384 else 3,
-                 "kernels": "attn_fused" if C <= 384 else "layernorm + qkv GEMM (tcgen05) + attn_core"})
+                 "kernels": "attn_fused" if C <= 384 else ("layernorm + qkv GEMM (tcgen05) + attn_core_tc (QK^T / PV on tcgen05, S / O in TMEM)" if G == 8 else "layernorm + qkv GEMM (tcgen05) + attn_core (mma.sync; 16x16 grid, not a SUNet shape)")})
     del blk, xs, out, ws
 if not args.once:
     print(json.dumps({"what": "window-attention part of a Swin block (norm1 .. attention output, without proj), fp16 token stream, stand-alone",

@@ -7,9 +7,9 @@ import csv
 import json
 import sys
 
-FAMILIES = (("gemm_tn_f16", "gemm_tcgen05"), ("proj_ln_kernel", "gemm_tcgen05"), ("patch_embed_mma_kernel", "patch_embed_conv"), ("attn_fused_kernel", "attn_fused"), ("attn_core_kernel", "attn_core"), ("mlp_proj_fused", "mlp_fused"), ("mlp_row_kernel", "mlp_fused"),
+FAMILIES = (("gemm_tn_f16", "gemm_tcgen05"), ("proj_ln_kernel", "gemm_tcgen05"), ("patch_embed_mma_kernel", "patch_embed_conv"), ("attn_fused_kernel", "attn_fused"), ("attn_core_kernel", "attn_core"), ("attn_core_tc_kernel", "attn_core"), ("mlp_proj_fused", "mlp_fused"), ("mlp_row_kernel", "mlp_fused"),
             ("mlp_fused_kernel", "mlp_fused"), ("layernorm_kernel", "layernorm"), ("patch_embed_kernel", "patch_embed_conv"),
-            ("upsample_combine", "upsample_combine"), ("tail_stencil", "tail_stencil"), ("tail_up_fused", "tail_up_fused"))
+            ("upsample_combine", "upsample_combine"), ("tail_stencil", "tail_stencil"), ("tail_finish", "tail_stencil"), ("tail_up_fused", "tail_up_fused"))
 
 rows = []
 with open(sys.argv[1]) as fh:
