@@ -260,7 +260,10 @@ __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
   }
-  const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
+  // (MUFU.RCP: the IEEE form is eight instructions plus a slow-path call per reciprocal; 1 ulp is far below the fp16 rounding of O)
+  float inv0, inv1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(sum0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(sum1));
   // normalise and park O in this tile's own q rows (already consumed into registers by every lane of this warp)
   __syncwarp();
   const int i0 = mt * 16 + g, i1 = i0 + 8;

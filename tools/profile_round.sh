@@ -16,7 +16,7 @@ if [ "$what" != full ]; then
 fi
 if [ "$what" != launches ]; then
   for k in ${KERNELS:-attn_fused_kernel:attn96:0 attn_fused_kernel:attn192:8 attn_fused_kernel:attn384:16 mlp_proj_fused_kernel:mlp96:0 \
-           mlp_proj_fused_kernel:mlp192:8 proj_ln_kernel:projln:0 proj_ln_kernel:rowgemm:1 patch_embed_mma:patchembed:1 \
+           mlp_proj_fused_kernel:mlp192:8 patch_embed_mma:patchembed:1 \
            tail_finish:tailfinish:1 tail_up_fused:tailup:1 attn_core_tc:attntc:8 mlp_row_kernel:mlprow:16 gemm_tn_f16_kernel:gemm:40}; do
     IFS=: read -r name short skip <<< "$k"
     ncu --set full --clock-control none --import-source on -k regex:"$name" -s $skip -c 1 \
