@@ -312,17 +312,24 @@ __device__ __forceinline__ void drain_store(const uint32_t (&v)[BATCH], int c0, 
     const bool wide = SUNET_AF_DRAIN128 && (d % 8 == 0) && (d + 8 <= K::HD) && (i + 8 <= BATCH);
     const bool second = SUNET_AF_DRAIN128 && (d % 8 == 4) && (d + 4 <= K::HD) && (i >= 4);   // upper half of a chunk stored by the previous step
     if (second) continue;
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (!K::BIASK) b4 = *reinterpret_cast<const float4*>(bf + n);   // (BIASK: the bias is already in the accumulator)
+    // (BIASK: the bias is already in the accumulator; the add is compiled out rather than fed zeros - `x + 0.f` is not a no-op the
+    // compiler may drop (signed zeros) and cost one FADD per drained element)
+    float q0 = __uint_as_float(v[i + 0]), q1 = __uint_as_float(v[i + 1]), q2 = __uint_as_float(v[i + 2]), q3 = __uint_as_float(v[i + 3]);
+    if constexpr (!K::BIASK) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bf + n);
+      q0 += b4.x; q1 += b4.y; q2 += b4.z; q3 += b4.w;
+    }
     const uint32_t dst = d_base + (m * K::NU + hl) * K::UNIT_BYTES + (d & 7) * 2 + ((static_cast<uint32_t>(d >> 3) << 4) ^ d_sx);
-    const uint32_t lo0 = pack_half2(__uint_as_float(v[i + 0]) + b4.x, __uint_as_float(v[i + 1]) + b4.y);
-    const uint32_t lo1 = pack_half2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w);
+    const uint32_t lo0 = pack_half2(q0, q1);
+    const uint32_t lo1 = pack_half2(q2, q3);
     if (wide) {
       const int i4 = (i + 4 < BATCH) ? i + 4 : i;   // (always i + 4 when wide; keeps the index in range for the discarded branch)
-      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (!K::BIASK) c4 = *reinterpret_cast<const float4*>(bf + n + 4);
-      sts128(dst, make_uint4(lo0, lo1, pack_half2(__uint_as_float(v[i4 + 0]) + c4.x, __uint_as_float(v[i4 + 1]) + c4.y),
-                             pack_half2(__uint_as_float(v[i4 + 2]) + c4.z, __uint_as_float(v[i4 + 3]) + c4.w)));
+      float r0 = __uint_as_float(v[i4 + 0]), r1 = __uint_as_float(v[i4 + 1]), r2 = __uint_as_float(v[i4 + 2]), r3 = __uint_as_float(v[i4 + 3]);
+      if constexpr (!K::BIASK) {
+        const float4 c4 = *reinterpret_cast<const float4*>(bf + n + 4);
+        r0 += c4.x; r1 += c4.y; r2 += c4.z; r3 += c4.w;
+      }
+      sts128(dst, make_uint4(lo0, lo1, pack_half2(r0, r1), pack_half2(r2, r3)));
     } else {
       sts64(dst, lo0, lo1);
     }
