@@ -65,6 +65,15 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// D = A B + C with C in its own (read-only) registers: the first k-step of a score tile takes the relative-position bias slice
+// straight from the registers that hold it for the whole kernel - no per-score copy into the accumulator (one MOV / FADD per score,
+// ~10% of the instructions of attn_fused<96>, ncu source page r07)
+__device__ __forceinline__ void mma_16816_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1, float c2,
+                                            float c3) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -186,14 +195,6 @@ __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v
         s[nt][2 + e] = tb[e][2 * MI + 1 - nt + 7] + fminf(rm1, cm[e]);
       }
     }
-  } else {
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        s[nt][e] = tb[e][2 * MI + 0 - nt + 7];
-        s[nt][2 + e] = tb[e][2 * MI + 1 - nt + 7];
-      }
   }
 #pragma unroll
   for (int nt = 0; nt < 8; nt += 2) {
@@ -201,8 +202,15 @@ __device__ __forceinline__ void attn_tile(uint32_t q_h, uint32_t k_h, uint32_t v
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t kb[4];   // (nt, k lo), (nt, k hi), (nt+1, k lo), (nt+1, k hi)
       ldsm_x4(kb, k_h + op_off<RB>((nt + (lane >> 4)) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
-      mma_16816(s[nt], qa[ks], kb[0], kb[1]);
-      mma_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
+      if (!MASK && ks == 0) {   // accumulators start from the bias: C operand = the bias registers themselves
+        mma_16816_c(s[nt], qa[0], kb[0], kb[1], tb[0][2 * MI + 0 - nt + 7], tb[1][2 * MI + 0 - nt + 7], tb[0][2 * MI + 1 - nt + 7],
+                    tb[1][2 * MI + 1 - nt + 7]);
+        mma_16816_c(s[nt + 1], qa[0], kb[2], kb[3], tb[0][2 * MI + 0 - (nt + 1) + 7], tb[1][2 * MI + 0 - (nt + 1) + 7],
+                    tb[0][2 * MI + 1 - (nt + 1) + 7], tb[1][2 * MI + 1 - (nt + 1) + 7]);
+      } else {
+        mma_16816(s[nt], qa[ks], kb[0], kb[1]);
+        mma_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
+      }
     }
   }
   // softmax over the 64 keys (a row lives in the 4 lanes of a quad); logits are already in the exp2 domain
