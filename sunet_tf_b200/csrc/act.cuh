@@ -20,15 +20,29 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(h, th, h);
 }
 
-// GELU(x) from u = x / 2 (the caller pre-scales):  u + u * tanh(u * (2 c0 + 8 c1 u^2 + 32 c2 u^4)), same fit as gelu_fast;
-// 7 FMA-pipe instructions + one MUFU per element, all fp32.
+// GELU(x) from u = x / 2 (the caller pre-scales), in the fused MLP kernels whose GELU pass is FMA-issue-bound.
+// SUNET_GELU_TERMS 3:  u + u * tanh(u * (2 c0 + 8 c1 u^2 + 32 c2 u^4)), the fit of gelu_fast (max |dGELU| 2.5e-5): 6 FMA-pipe
+//                      instructions + one MUFU per element (the clamp keeps the odd polynomial monotone);
+// SUNET_GELU_TERMS 2:  u + u * tanh(u * (a + b u^2)) with the minimax pair (a, b) = (1.60031416, 0.27760715): max |dGELU| 2.7e-4 over
+//                      all x - below the 4.9e-4 half-ulp of the fp16 hidden activation it is stored in around |x| ~ 1.7 where the
+//                      maximum sits - monotone without a clamp: 4 FMA-pipe instructions + one MUFU per element.
+#ifndef SUNET_GELU_TERMS
+#define SUNET_GELU_TERMS 2   // measured: 7.756 -> 7.619 ms per batch; whole-model max-abs 3.0e-4 / 3.4e-4 / 4.0e-4 / 1.0e-3 (init, stress, 64 distinct, outlier) against 3.3e-4 / 3.1e-4 / 4.7e-4 / 8.6e-4 with 3 terms (bar 2e-3)
+#endif
 __device__ __forceinline__ float gelu_half_arg(float u) {
+#if SUNET_GELU_TERMS == 2
+  const float p = fmaf(u * u, 2.7760715e-01f, 1.60031416f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
+  return fmaf(u, th, u);
+#else
   const float t = fminf(u * u, 12.25f);
   float p = fmaf(t, -1.1248591167e-02f, 2.9604525738e-01f);
   p = fmaf(t, p, 1.5950157421f);
   float th;
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u * p));
   return fmaf(u, th, u);
+#endif
 }
 
 // Packed-half2 variant for the fc1 epilogue (the result is stored as fp16 anyway): 5 instructions per element.
