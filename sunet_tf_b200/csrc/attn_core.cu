@@ -182,8 +182,9 @@ __device__ __forceinline__ void attn_tile(const __half* q_h, const __half* k_h, 
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
   }
-  inv0 = __frcp_rn(sum0);
-  inv1 = __frcp_rn(sum1);
+  // (MUFU.RCP; the IEEE reciprocal is eight inline instructions plus a slow-path call - see attn_fused.cu)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv0) : "f"(sum0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1) : "f"(sum1));
   // ---- normalise and park O in this tile's own Q rows (already consumed into registers)
   __syncwarp();
   const int i0 = mt * 16 + g, i1 = i0 + 8;

@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_before();          // the S reads above are complete: O may overwrite the columns
       fence_proxy_async_smem();   // P row visible to the tensor core's operand reads
       mbar_arrive(&p_full[g]);
-      const float inv = __frcp_rn(sum);
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sum));
       mbar_wait(&o_full[g], par);
       tc_fence_after();
       // O_g: 96 valid columns from column 0 (head A) or 32 (head B); they are columns 96 g .. 96 g + 95 of the unit's output tile,
