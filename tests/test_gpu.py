@@ -323,6 +323,34 @@ def test_grey_input_and_batch_invariance(dev, model_init):
     assert torch.equal(y_full[0], y_full[3]) and torch.equal(y_full[1], y_full[2])
 
 
+def test_fused_tail_agrees_with_gemm_stencil_path(dev, monkeypatch):
+    """The x4 tail as tail_up_fused + tail_finish (per-token strips of partial output sums, bilinear branch added on the SM; the
+    [tokens * 16][16] tap tensor never reaches HBM) against the pre-fusion sequence - two GEMMs, the tap tensor, the 9-tap tail_stencil
+    (SUNET_NO_FUSED_TAIL at pre-pack) - on the same weights and images: two independent CUDA implementations of
+    SUNet_detail.py:742-753, fp32 output and the 8-bit output edge, an odd batch (image-boundary rows of the strips) included."""
+    from sunet_tf_b200 import SUNet_model
+    from sunet_tf_b200.default_config import DEFAULT_OPT
+    sd = Wt.synth_state_dict(Wt.sunet_spec(), seed=0, style="stress")
+    noisy, _ = Wt.awgn_input(3, seed=5)
+
+    def build():
+        m = SUNet_model(DEFAULT_OPT)
+        m.load_state_dict(sd, strict=True)
+        return m.to(dev).eval()
+
+    fused = build()
+    y_fused = fused(noisy.to(dev)).clone()
+    x8 = (noisy.permute(0, 2, 3, 1) * 255).round().clamp(0, 255).to(torch.uint8).contiguous().to(dev)
+    u_fused = fused.forward_u8(x8).clone()
+    monkeypatch.setenv("SUNET_NO_FUSED_TAIL", "1")
+    plain = build()
+    y_plain = plain(noisy.to(dev))
+    u_plain = plain.forward_u8(x8)
+    report("fused tail vs GEMM + stencil tail", y_fused, y_plain.cpu(), 2e-6, relative=False)   # measured 4.5e-8: fp32 summation order only
+    dl = (u_fused.int() - u_plain.int()).abs()
+    assert dl.max().item() <= 1 and (dl != 0).float().mean().item() < 1e-3, "8-bit outputs of the two tail paths differ by more than rounding ties"
+
+
 def test_full_batch64_properties(dev, model_init):
     """BASELINE config 2 size (B=64): replicas of the 2 golden inputs must reproduce the golden in every slot."""
     g = load_golden("sunet_model_init.npz")
