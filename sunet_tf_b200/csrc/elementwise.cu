@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     if (MERGE) {
       // (32-bit arithmetic: the callers bound M below 2^31; a 64-bit division is ~150 emulated instructions)
       const unsigned W2 = static_cast<unsigned>(W >> 1), H2 = static_cast<unsigned>(H >> 1), r32 = static_cast<unsigned>(row);
-      const unsigned rw = r32 / W2, bb = rw / H2;
+      // power-of-two grids (every SUNet stage) take shifts: the kernel is issue-bound and a 32-bit division is ~20 instructions
+      const bool p2 = ((W2 & (W2 - 1)) | (H2 & (H2 - 1))) == 0;
+      const unsigned rw = p2 ? r32 >> (__ffs(W2) - 1) : r32 / W2, bb = p2 ? rw >> (__ffs(H2) - 1) : rw / H2;
       mw = r32 - rw * W2; mh = rw - bb * H2; mb = bb;
     } else {
       src_row = in + row * ld_in;
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
       const __half* p;
       if (MERGE) {
         const int col = v << 3;
-        const int q = col / Csrc, off = col - q * Csrc;   // segment order TL, BL, TR, BR (SUNet_detail.py:312-316)
+        const int q = (col >= Csrc) + (col >= 2 * Csrc) + (col >= 3 * Csrc), off = col - q * Csrc;   // segment order TL, BL, TR, BR (SUNet_detail.py:312-316); col < 4 Csrc
         const int64_t y = 2 * mh + (q & 1), xx = 2 * mw + (q >> 1);
         p = in + ((mb * H + y) * W + xx) * Csrc + off;
       } else {
@@ -283,6 +285,9 @@ __device__ __forceinline__ void pe_mma(float (&d)[4], const uint32_t (&a)[4], ui
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+#ifndef SUNET_PE_VEC
+#define SUNET_PE_VEC 1   // 16-byte image staging in patch_embed_mma_kernel (0: the 4-byte per-pixel form, for A/B runs)
+#endif
 constexpr int PE_KP = 112;   // 108 taps padded to 7 k-steps
 constexpr int PE_WP = 120;   // weight row pitch in halves (240 B: the 8 rows of an ldmatrix land in 8 different 16-byte columns)
 constexpr int PE_IP = 72;    // image row pitch in floats
@@ -296,11 +301,33 @@ __device__ __forceinline__ void pe_cp_async4(uint32_t dst, const void* src, int 
 
 // The pixels of one 8 x 16-token tile (3 x 34 x 66, zero outside the image) into a staging buffer.  fp32 input goes through cp.async
 // (in flight while the previous tile is computed); 8-bit input is loaded, scaled by 1/255 (TF.to_tensor, demo.py:71) and stored.
-template <bool U8>
+// VEC (fp32 input, 16-byte aligned image rows): the tile is staged from the aligned column x_base - 3 in 16-byte chunks - 3 x 34 x 18
+// cp.async instead of 3 x 34 x 66 four-byte ones, with 32-bit index arithmetic inside the image (the per-pixel form spent 58% of the
+// kernel's instructions on this staging loop, ncu source page r09); the consumer then finds pixel x_base at column PE_XOFF = 3.
+constexpr int PE_XOFF = 3;
+__device__ __forceinline__ void pe_cp_async16(uint32_t dst, const void* src, int src_bytes) {   // src_bytes 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+template <bool U8, bool VEC>
 __device__ __forceinline__ void pe_stage_tile(const void* __restrict__ img_v, int img_chans, int Himg, int Wimg, int b, int y_base, int x_base,
                                               float* buf, int tid) {
   constexpr int NPIX = 3 * 34 * 66;
-  if (!U8) {
+  if (!U8 && VEC) {
+    static_assert(PE_IP == 72, "18 chunks of 4 floats per staged row");
+    constexpr int NCHUNK = 3 * 34 * 18;
+    const float* img_b = static_cast<const float*>(img_v) + static_cast<int64_t>(b) * img_chans * Himg * Wimg;
+    const uint32_t dst0 = smem_u32(buf);
+    const int x_al = x_base - PE_XOFF;   // a multiple of 4 (x_base = 64 tx - 1)
+    for (int i = tid; i < NCHUNK; i += 256) {
+      const int c = i / (34 * 18), rem = i - c * (34 * 18), r = rem / 18, ch = rem - r * 18;
+      const int y = y_base + r, x = x_al + 4 * ch;
+      // (Wimg is a multiple of 4: an aligned chunk lies wholly inside or wholly outside the image)
+      const bool in = y >= 0 && y < Himg && x >= 0 && x < Wimg;
+      const int cs = img_chans == 1 ? 0 : c;   // grey input is repeated to 3 channels (model/SUNet.py:27-28)
+      const float* src = in ? img_b + static_cast<uint32_t>((cs * Himg + y) * Wimg + x) : img_b;
+      pe_cp_async16(dst0 + ((c * 34 + r) * PE_IP + 4 * ch) * 4, src, in ? 16 : 0);
+    }
+  } else if (!U8) {
     const float* img = static_cast<const float*>(img_v);
     const uint32_t dst0 = smem_u32(buf);
     for (int i = tid; i < NPIX; i += 256) {
@@ -338,7 +365,7 @@ __device__ __forceinline__ void pe_stage_tile(const void* __restrict__ img_v, in
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int EPL, bool U8>
+template <int EPL, bool U8, bool VEC>
 __global__ void __launch_bounds__(256, 2) patch_embed_mma_kernel(const void* __restrict__ img_v, int img_chans, int Himg, int Wimg,
                                                                  const __half* __restrict__ wpk, const float* __restrict__ bfold,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -385,7 +412,7 @@ __global__ void __launch_bounds__(256, 2) patch_embed_mma_kernel(const void* __r
   int buf = 0;
   if (static_cast<int>(blockIdx.x) < tiles_total) {
     const int t = blockIdx.x, b = t / tiles_img, trem = t - b * tiles_img;
-    pe_stage_tile<U8>(img_v, img_chans, Himg, Wimg, b, 32 * (trem / tiles_x) - 1, 64 * (trem % tiles_x) - 1, s_img, tid);
+    pe_stage_tile<U8, VEC>(img_v, img_chans, Himg, Wimg, b, 32 * (trem / tiles_x) - 1, 64 * (trem % tiles_x) - 1, s_img, tid);
   }
   for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, buf ^= 1) {
     const int b = tile / tiles_img;
@@ -396,18 +423,24 @@ __global__ void __launch_bounds__(256, 2) patch_embed_mma_kernel(const void* __r
     const int next = tile + gridDim.x;
     if (next < tiles_total) {
       const int nb = next / tiles_img, nrem = next - nb * tiles_img;
-      pe_stage_tile<U8>(img_v, img_chans, Himg, Wimg, nb, 32 * (nrem / tiles_x) - 1, 64 * (nrem % tiles_x) - 1, s_img + (buf ^ 1) * PE_IMG, tid);
+      pe_stage_tile<U8, VEC>(img_v, img_chans, Himg, Wimg, nb, 32 * (nrem / tiles_x) - 1, 64 * (nrem % tiles_x) - 1, s_img + (buf ^ 1) * PE_IMG, tid);
     }
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-    const float* a_base = s_img + buf * PE_IMG + (4 * warp) * PE_IP + 4 * g;   // token (row warp, col g); col g + 8 is 32 floats further
+    // token (row warp, col g); col g + 8 is 32 floats further.  VEC: the tile starts PE_XOFF columns to the left, so a k-pair sits at
+    // an odd column and is read as two 32-bit loads instead of one 64-bit load
+    const float* a_base = s_img + buf * PE_IMG + (4 * warp) * PE_IP + 4 * g + (VEC ? PE_XOFF : 0);
+    auto ld_pair = [](const float* q) {
+      if constexpr (VEC) return make_float2(q[0], q[1]);
+      else return *reinterpret_cast<const float2*>(q);
+    };
 #pragma unroll
     for (int ks = 0; ks < 7; ++ks) {
-      const float2 f0 = *reinterpret_cast<const float2*>(a_base + aoff[ks][0]);
-      const float2 f1 = *reinterpret_cast<const float2*>(a_base + 32 + aoff[ks][0]);
-      const float2 f2 = *reinterpret_cast<const float2*>(a_base + aoff[ks][1]);
-      const float2 f3 = *reinterpret_cast<const float2*>(a_base + 32 + aoff[ks][1]);
+      const float2 f0 = ld_pair(a_base + aoff[ks][0]);
+      const float2 f1 = ld_pair(a_base + 32 + aoff[ks][0]);
+      const float2 f2 = ld_pair(a_base + aoff[ks][1]);
+      const float2 f3 = ld_pair(a_base + 32 + aoff[ks][1]);
       uint32_t a[4];
       {
         const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f1.x, f1.y);
@@ -477,13 +510,15 @@ int patch_embed_fused(const void* img, int img_fmt, int img_chans, int B, int Hi
     const int tiles = B * (Himg / 32) * (Wimg / 64);
     const int sms = device_sms();
     const unsigned grid = static_cast<unsigned>(tiles < 2 * sms ? tiles : 2 * sms);
-#define PE_MMA_T(EPL, U8)                                                                                                    \
+#define PE_MMA_T(EPL, U8, VEC)                                                                                               \
   {                                                                                                                          \
-    SUNET_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<EPL, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, pe_mma_smem<EPL>())); \
-    SUNET_CUDA(launch_pdl(patch_embed_mma_kernel<EPL, U8>, dim3(grid), dim3(256), pe_mma_smem<EPL>(), s, img, img_chans, Himg, Wimg,  \
+    SUNET_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<EPL, U8, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pe_mma_smem<EPL>())); \
+    SUNET_CUDA(launch_pdl(patch_embed_mma_kernel<EPL, U8, VEC>, dim3(grid), dim3(256), pe_mma_smem<EPL>(), s, img, img_chans, Himg, Wimg,  \
                           wpk, bfold, gamma, beta, out, tiles));                                                          \
   }
-#define PE_MMA(EPL) if (img_fmt == IMG_U8_NHWC) PE_MMA_T(EPL, true) else PE_MMA_T(EPL, false)
+    // 16-byte staging needs 16-byte aligned image rows (Wimg % 64 == 0 holds here) and one image below 2^31 elements
+    const bool vec = SUNET_PE_VEC && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && static_cast<int64_t>(img_chans) * Himg * Wimg < (1LL << 31);
+#define PE_MMA(EPL) if (img_fmt == IMG_U8_NHWC) PE_MMA_T(EPL, true, false) else if (vec) PE_MMA_T(EPL, false, true) else PE_MMA_T(EPL, false, false)
     switch (E / 32) {
       case 1: PE_MMA(1); break;
       case 2: PE_MMA(2); break;
@@ -604,8 +639,75 @@ __global__ void __launch_bounds__(256) upsample_combine_kernel(const __half* __r
   }
 }
 
+// The same arithmetic with the index decomposition taken from the launch geometry: grid = (pixel groups of an output row, output
+// row, image), block = (16-byte vectors of a pixel, pixels), R a compile-time constant.  The flat form above spends ~55% of its
+// instructions on five runtime divisions and 64-bit addresses and is issue-bound (75% of the issue slots busy at 2.6 TB/s, ncu r10).
+#ifndef SUNET_UPC_ROWS
+#define SUNET_UPC_ROWS 1   // 0: always the flat-index kernel (A/B runs)
+#endif
+template <int R>
+__global__ void __launch_bounds__(256) upsample_combine_rows_kernel(const __half* __restrict__ Yp, const __half* __restrict__ Z,
+                                                                    void* __restrict__ out, int out_f32, int H, int W, int Co) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int v8 = static_cast<int>(threadIdx.x) << 3;
+  const int X = blockIdx.x * blockDim.y + threadIdx.y;
+  const int OW = W * R, OH = H * R;
+  if (X >= OW) return;
+  const int Y = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int h = Y / R, ii = Y % R, w = X / R, jj = X % R;
+  const uint4 yp = __ldg(reinterpret_cast<const uint4*>(Yp + (((b * H + h) * W + w) * (R * R) + ii * R + jj) * Co + v8));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_tap(Y, R, H, y0, y1, ly);
+  bilinear_tap(X, R, W, x0, x1, lx);
+  const __half* zr0 = Z + (b * H + y0) * W * Co + v8;
+  const __half* zr1 = Z + (b * H + y1) * W * Co + v8;
+  const uint4 z00 = __ldg(reinterpret_cast<const uint4*>(zr0 + x0 * Co));
+  const uint4 z01 = __ldg(reinterpret_cast<const uint4*>(zr0 + x1 * Co));
+  const uint4 z10 = __ldg(reinterpret_cast<const uint4*>(zr1 + x0 * Co));
+  const uint4 z11 = __ldg(reinterpret_cast<const uint4*>(zr1 + x1 * Co));
+  const __half2 *p = reinterpret_cast<const __half2*>(&yp), *a = reinterpret_cast<const __half2*>(&z00),
+                *bq = reinterpret_cast<const __half2*>(&z01), *c = reinterpret_cast<const __half2*>(&z10),
+                *d = reinterpret_cast<const __half2*>(&z11);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fp = __half22float2(p[j]), fa = __half22float2(a[j]), fb = __half22float2(bq[j]), fc = __half22float2(c[j]),
+                 fd = __half22float2(d[j]);
+    // the flat kernel's expressions, term for term (bit-identical results)
+    const float tx = (fa.x * (1.f - ly) + fc.x * ly), ux = (fb.x * (1.f - ly) + fd.x * ly);
+    const float ty = (fa.y * (1.f - ly) + fc.y * ly), uy = (fb.y * (1.f - ly) + fd.y * ly);
+    f[2 * j] = fp.x + tx * (1.f - lx) + ux * lx;
+    f[2 * j + 1] = fp.y + ty * (1.f - lx) + uy * lx;
+  }
+  const int64_t o_off = ((b * OH + Y) * OW + X) * Co + v8;
+  if (out_f32) {
+    float* o = static_cast<float*>(out) + o_off;
+    *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(static_cast<__half*>(out) + o_off) = o;
+  }
+}
+
 int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, int B, int H, int W, int Co, int r, cudaStream_t s) {
   if (Co % 8) return fail(SUNET_E_SHAPE, "upsample: Co=%d must be a multiple of 8", Co);
+  const int nv = Co / 8;
+  if (SUNET_UPC_ROWS && (r == 2 || r == 4) && nv <= 256 && H * r <= 65535 && B <= 65535) {
+    int px = 1;   // pixels per block, a power of two (no ragged last block on the power-of-two SUNet rows); consecutive threads
+    while (2 * px * nv <= 256) px *= 2;   // cover consecutive 16-byte vectors of the output row
+    const dim3 block(nv, px), grid((W * r + px - 1) / px, H * r, B);
+    if (r == 2) SUNET_CUDA(launch_pdl(upsample_combine_rows_kernel<2>, grid, block, 0, s, Yp, Z, out, out_f32, H, W, Co));
+    else SUNET_CUDA(launch_pdl(upsample_combine_rows_kernel<4>, grid, block, 0, s, Yp, Z, out, out_f32, H, W, Co));
+    SUNET_CHECK_LAUNCH();
+    return 0;
+  }
   const int64_t total = static_cast<int64_t>(B) * H * r * W * r * (Co / 8);
   if (total < (static_cast<int64_t>(1) << 31))
     SUNET_CUDA(launch_pdl(upsample_combine_kernel<unsigned>, dim3(blocks_for(total, 256)), dim3(256), 0, s, Yp, Z, out, out_f32, H, W, Co, r, total));

@@ -521,6 +521,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 // parts the tile can reach: the last / first sub-pixel row of the tokens above / below, the halo columns of the tokens left / right),
 // token stride 100 words so that the 8 tokens of a pixel row hit 8 different bank groups.  The sum order is fixed (deterministic).
 // MODE 0: fp32 NCHW; 1: 8-bit NHWC, rint(clamp(v, 0, 1) * 255); 2: fp32 NCHW + validation epilogue (EvalEpilogue), as tail_stencil.
+#ifndef SUNET_TF_STAGE_FLAT
+#define SUNET_TF_STAGE_FLAT 0   // 1: the flat-index staging loop of tail_finish_kernel (A/B runs)
+#endif
 constexpr int TF_T8 = 8;        // tokens per tile side
 constexpr int TF_N = TF_T8 + 2; // staged tokens per side
 constexpr int TF_STRIDE = 100;  // words per staged token: 4 sub-pixel rows x [3][8] + 4 pad
@@ -536,6 +539,7 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
   const int trem = blockIdx.x % (tiles_x * tiles_y);
   const int th0 = (trem / tiles_x) * TF_T8, tw0 = (trem % tiles_x) * TF_T8;
   const int tid = threadIdx.x;
+#if SUNET_TF_STAGE_FLAT
   {
     constexpr int TOTAL = TF_N * TF_N * 24, BATCH = 5;   // 16-byte vectors: [token][sub-pixel row][6]
 #pragma unroll 1
@@ -566,6 +570,34 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
       }
     }
   }
+#else
+  // Staging with the index decomposition hoisted: thread = (staged token column tc, 16-byte vector r of a token's 24), the loop walks
+  // the 10 staged token rows - everything but the row test and one address is loop-invariant.  (The flat form above decomposed
+  // i -> (token, sub-pixel row, vector) with three divisions per vector, 57% of the kernel's instructions at 78% issue-slot use: ncu r09.)
+  if (tid < TF_N * 24) {
+    const int tc = tid / 24, r = tid - tc * 24;
+    const int sy = r / 6, v = r - sy * 6;
+    const int tx = tw0 - 1 + tc;
+    const bool col_ok = tx >= 0 && tx < W && (tc != 0 || (v & 1) == 1) && (tc != TF_N - 1 || (v & 1) == 0);
+    float* dst = sS + tc * TF_STRIDE + r * 4;
+#pragma unroll
+    for (int h0 = 0; h0 < TF_N; h0 += 5) {
+      float4 q[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {   // all loads of a batch are in flight before the first shared-memory store
+        const int tr = h0 + k, ty = th0 - 1 + tr;
+        const bool need = col_ok && ty >= 0 && ty < H && (tr != 0 || sy == 3) && (tr != TF_N - 1 || sy == 0);
+        q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (need) {
+          const int64_t tok = (b * H + ty) * W + tx;
+          q[k] = __ldg(reinterpret_cast<const float4*>(S + (((tok >> 5) * 4 + sy) * 32 + (tok & 31)) * 24) + v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(dst + (h0 + k) * TF_N * TF_STRIDE) = q[k];
+    }
+  }
+#endif
   __syncthreads();
   double part[4] = {0.0, 0.0, 0.0, 0.0};
   const int lx_ = tid & 31;
