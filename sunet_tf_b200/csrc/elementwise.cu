@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   }
 }
 
+#ifndef SUNET_LN_THIRDS
+#define SUNET_LN_THIRDS 1   // 0: only the power-of-two lane / vector table (A/B runs)
+#endif
 template <bool MERGE>
 static int launch_ln(const __half* in, int64_t ld_in, __half* out, int64_t ld_out, const float* gamma, const float* beta, int64_t M,
                      int C, int H, int W, int Csrc, cudaStream_t s) {
@@ -154,6 +157,24 @@ static int launch_ln(const __half* in, int64_t ld_in, __half* out, int64_t ld_ou
       (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
     return fail(SUNET_E_ALIGN, "layernorm: 16-byte aligned rows / affine vectors required");
   const int nvec = C / 8;
+  // Row widths of 3 * 2^k vectors (C = 96, 192, 384, 768 and the 4C rows of PatchMerging) take three (six) vectors per lane on 2^k
+  // lanes: every lane is active (the power-of-two table below leaves a quarter of them idle), the reductions are two steps shorter
+  // and each thread has three independent 16-byte loads in flight.
+#define LN_CASE(LPR, MAXV)                                                                                                          \
+  SUNET_CUDA(launch_pdl(layernorm_kernel<LPR, MAXV, MERGE>, dim3(blocks_for(M * LPR, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, \
+                        M, C, H, W, Csrc))
+  if (SUNET_LN_THIRDS && (nvec == 12 || nvec == 24 || nvec == 48 || nvec == 96 || nvec == 192)) {
+    switch (nvec) {
+      case 12: LN_CASE(4, 3); break;
+      case 24: LN_CASE(8, 3); break;
+      case 48: LN_CASE(16, 3); break;
+      case 96: LN_CASE(32, 3); break;
+      default: LN_CASE(32, 6); break;
+    }
+    SUNET_CHECK_LAUNCH();
+    return 0;
+  }
+#undef LN_CASE
   if (nvec <= 16) {
     SUNET_CUDA(launch_pdl(layernorm_kernel<16, 1, MERGE>, dim3(blocks_for(M * 16, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, M, C, H, W, Csrc));
   } else if (nvec <= 32) {
