@@ -157,19 +157,19 @@ static int launch_ln(const __half* in, int64_t ld_in, __half* out, int64_t ld_ou
       (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
     return fail(SUNET_E_ALIGN, "layernorm: 16-byte aligned rows / affine vectors required");
   const int nvec = C / 8;
-  // Row widths of 3 * 2^k vectors (C = 96, 192, 384, 768 and the 4C rows of PatchMerging) take three (six) vectors per lane on 2^k
+  // Row widths of 3 * 2^k vectors (C = 96, 192, 384, 768 and the 4C rows of PatchMerging) take three vectors per lane on 2^k
   // lanes: every lane is active (the power-of-two table below leaves a quarter of them idle), the reductions are two steps shorter
   // and each thread has three independent 16-byte loads in flight.
 #define LN_CASE(LPR, MAXV)                                                                                                          \
   SUNET_CUDA(launch_pdl(layernorm_kernel<LPR, MAXV, MERGE>, dim3(blocks_for(M * LPR, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, gamma, beta, \
                         M, C, H, W, Csrc))
-  if (SUNET_LN_THIRDS && (nvec == 12 || nvec == 24 || nvec == 48 || nvec == 96 || nvec == 192)) {
+  // (192 vectors - the stage-2 merge, 4096 rows - stay on <32, 8>: six vectors per lane measured 18.9 against 16.9 us there)
+  if (SUNET_LN_THIRDS && (nvec == 12 || nvec == 24 || nvec == 48 || nvec == 96)) {
     switch (nvec) {
       case 12: LN_CASE(4, 3); break;
       case 24: LN_CASE(8, 3); break;
       case 48: LN_CASE(16, 3); break;
-      case 96: LN_CASE(32, 3); break;
-      default: LN_CASE(32, 6); break;
+      default: LN_CASE(32, 3); break;
     }
     SUNET_CHECK_LAUNCH();
     return 0;
