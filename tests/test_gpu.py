@@ -323,6 +323,19 @@ def test_grey_input_and_batch_invariance(dev, model_init):
     assert torch.equal(y_full[0], y_full[3]) and torch.equal(y_full[1], y_full[2])
 
 
+def test_unaligned_input_takes_the_scalar_staging_path_with_identical_results(dev, model_init):
+    """patch_embed stages its image tile in 16-byte cp.async chunks when the image pointer is 16-byte aligned and falls back to the
+    4-byte per-pixel form otherwise: an input view that starts 4 bytes into its storage must give the same bits."""
+    noisy, _ = Wt.awgn_input(2, seed=3)
+    x = noisy.to(dev)
+    y_aligned = model_init(x).clone()
+    buf = torch.empty(x.numel() + 1, device=dev, dtype=torch.float32)
+    xu = buf[1:].view_as(x)
+    xu.copy_(x)
+    assert xu.data_ptr() % 16 == 4 and xu.is_contiguous()
+    assert torch.equal(model_init(xu), y_aligned)
+
+
 def test_fused_tail_agrees_with_gemm_stencil_path(dev, monkeypatch):
     """The x4 tail as tail_up_fused + tail_finish (per-token strips of partial output sums, bilinear branch added on the SM; the
     [tokens * 16][16] tap tensor never reaches HBM) against the pre-fusion sequence - two GEMMs, the tap tensor, the 9-tap tail_stencil

@@ -17,7 +17,8 @@ fi
 if [ "$what" != launches ]; then
   for k in ${KERNELS:-attn_fused_kernel:attn96:0 attn_fused_kernel:attn192:8 attn_fused_kernel:attn384:16 mlp_proj_fused_kernel:mlp96:0 \
            mlp_proj_fused_kernel:mlp192:8 patch_embed_mma:patchembed:1 \
-           tail_finish:tailfinish:1 tail_up_fused:tailup:1 attn_core_tc:attntc:8 mlp_row_kernel:mlprow:16 gemm_tn_f16_kernel:gemm:40}; do
+           tail_finish:tailfinish:1 tail_up_fused:tailup:1 attn_core_tc:attntc:8 mlp_row_kernel:mlprow:16 gemm_tn_f16_kernel:gemm:40 \
+           upsample_combine:upcombine:2 layernorm_kernel:mergeln:0 layernorm_kernel:normup:20}; do
     IFS=: read -r name short skip <<< "$k"
     ncu --set full --clock-control none --import-source on -k regex:"$name" -s $skip -c 1 \
         -o gpurun_out/prof_${tag}_$short -f python tools/one_forward.py > gpurun_out/ncu_${tag}_$short.log 2>&1
