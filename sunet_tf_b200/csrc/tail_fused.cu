@@ -524,6 +524,10 @@ __global__ void __launch_bounds__(THREADS, 1)
 #ifndef SUNET_TF_STAGE_FLAT
 #define SUNET_TF_STAGE_FLAT 0   // 1: the flat-index staging loop of tail_finish_kernel (A/B runs)
 #endif
+#ifndef SUNET_TF_BATCH
+#define SUNET_TF_BATCH 10       // staged loads in flight per thread of tail_finish_kernel: all 10 token rows at once (5: 45.4 us, 10: 37.4 us; the long-scoreboard wait on these loads was the top stall)
+#endif
+constexpr int TF_BATCH = SUNET_TF_BATCH;
 constexpr int TF_T8 = 8;        // tokens per tile side
 constexpr int TF_N = TF_T8 + 2; // staged tokens per side
 constexpr int TF_STRIDE = 100;  // words per staged token: 4 sub-pixel rows x [3][8] + 4 pad
@@ -581,10 +585,10 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
     const bool col_ok = tx >= 0 && tx < W && (tc != 0 || (v & 1) == 1) && (tc != TF_N - 1 || (v & 1) == 0);
     float* dst = sS + tc * TF_STRIDE + r * 4;
 #pragma unroll
-    for (int h0 = 0; h0 < TF_N; h0 += 5) {
-      float4 q[5];
+    for (int h0 = 0; h0 < TF_N; h0 += TF_BATCH) {
+      float4 q[TF_BATCH];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {   // all loads of a batch are in flight before the first shared-memory store
+      for (int k = 0; k < TF_BATCH; ++k) {   // all loads of a batch are in flight before the first shared-memory store
         const int tr = h0 + k, ty = th0 - 1 + tr;
         const bool need = col_ok && ty >= 0 && ty < H && (tr != 0 || sy == 3) && (tr != TF_N - 1 || sy == 0);
         q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
         }
       }
 #pragma unroll
-      for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(dst + (h0 + k) * TF_N * TF_STRIDE) = q[k];
+      for (int k = 0; k < TF_BATCH; ++k) *reinterpret_cast<float4*>(dst + (h0 + k) * TF_N * TF_STRIDE) = q[k];
     }
   }
 #endif
