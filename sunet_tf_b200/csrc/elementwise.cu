@@ -717,9 +717,99 @@ __global__ void __launch_bounds__(256) upsample_combine_rows_kernel(const __half
   }
 }
 
+// r = 2, one thread per (low-res pixel, 16-byte vector): its 2 x 2 output pixels share the 3 x 3 neighbourhood of Z, so the nine
+// vectors are loaded and converted once (the per-output kernels above load 16 and convert 16 for the same four outputs) and the six
+// vertical interpolations are shared by the two output columns: ~100 instead of ~240 instructions per output vector in a kernel that is
+// issue-bound (83% of the issue slots, ncu r10).  Per output the expressions are those of the kernels above, term for term, with the
+// same operands: for output row 2h the taps are rows (h - 1, h) with weight 0.75 - or, at h = 0, rows (0, 1) with weight 0 - and for
+// row 2h + 1 rows (h, min(h + 1, H - 1)) with weight 0.25 (bilinear_tap); columns alike.
+#ifndef SUNET_UPC_QUAD
+#define SUNET_UPC_QUAD 1   // 0: upsample_combine_rows_kernel also for r = 2 (A/B runs)
+#endif
+__device__ __forceinline__ void upc_unpack(const uint4& u, float (&f)[8]) {
+  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h2[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+__global__ void __launch_bounds__(256) upsample_combine_quad_kernel(const __half* __restrict__ Yp, const __half* __restrict__ Z,
+                                                                    void* __restrict__ out, int out_f32, int H, int W, int Co) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int v8 = static_cast<int>(threadIdx.x) << 3;
+  const int w = blockIdx.x * blockDim.y + threadIdx.y;
+  if (w >= W) return;
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int OW = 2 * W, OH = 2 * H;
+  int ya0, ya1, yb0, yb1, xa0, xa1, xb0, xb1;
+  float lya, lyb, lxa, lxb;
+  bilinear_tap(2 * h, 2, H, ya0, ya1, lya);
+  bilinear_tap(2 * h + 1, 2, H, yb0, yb1, lyb);
+  bilinear_tap(2 * w, 2, W, xa0, xa1, lxa);
+  bilinear_tap(2 * w + 1, 2, W, xb0, xb1, lxb);
+  // rows ya0 <= ya1' <= yb1 with ya1' = yb0 = h: the three distinct rows / columns of the neighbourhood
+  const int rr[3] = {ya0, h, yb1}, cc[3] = {xa0, w, xb1};
+  const bool top = ya1 != h, left = xa1 != w;   // h = 0 / w = 0: the second tap of the even output row / column is row / column 1 (weight 0)
+  const __half* zb = Z + b * H * W * Co + v8;
+  // vertical interpolation per neighbourhood column: V[ii][c] = Z[y0(ii)][c] (1 - ly(ii)) + Z[y1(ii)][c] ly(ii)
+  float V[2][3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float z0[8], z1[8], z2[8];
+    upc_unpack(__ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(rr[0]) * W + cc[c]) * Co)), z0);
+    upc_unpack(__ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(rr[1]) * W + cc[c]) * Co)), z1);
+    upc_unpack(__ldg(reinterpret_cast<const uint4*>(zb + (static_cast<int64_t>(rr[2]) * W + cc[c]) * Co)), z2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a1 = top ? z2[e] : z1[e];
+      V[0][c][e] = z0[e] * (1.f - lya) + a1 * lya;
+      V[1][c][e] = z1[e] * (1.f - lyb) + z2[e] * lyb;
+    }
+  }
+  const __half* yrow = Yp + ((b * H + h) * W + w) * 4 * Co + v8;
+#pragma unroll
+  for (int ii = 0; ii < 2; ++ii) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      float fp[8], f[8];
+      upc_unpack(__ldg(reinterpret_cast<const uint4*>(yrow + (ii * 2 + jj) * Co)), fp);
+      const float lx = jj ? lxb : lxa;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float tx = jj ? V[ii][1][e] : V[ii][0][e];
+        const float ux = jj ? V[ii][2][e] : (left ? V[ii][2][e] : V[ii][1][e]);
+        f[e] = fp[e] + tx * (1.f - lx) + ux * lx;
+      }
+      const int64_t o_off = ((b * OH + 2 * h + ii) * OW + 2 * w + jj) * Co + v8;
+      if (out_f32) {
+        float* o = static_cast<float*>(out) + o_off;
+        *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(static_cast<__half*>(out) + o_off) = o;
+      }
+    }
+  }
+}
+
 int upsample_combine(const __half* Yp, const __half* Z, void* out, int out_f32, int B, int H, int W, int Co, int r, cudaStream_t s) {
   if (Co % 8) return fail(SUNET_E_SHAPE, "upsample: Co=%d must be a multiple of 8", Co);
   const int nv = Co / 8;
+  if (SUNET_UPC_QUAD && r == 2 && nv <= 256 && H <= 65535 && B <= 65535) {
+    int px = 1;
+    while (2 * px * nv <= 256 && 2 * px <= W) px *= 2;
+    const dim3 block(nv, px), grid((W + px - 1) / px, H, B);
+    SUNET_CUDA(launch_pdl(upsample_combine_quad_kernel, grid, block, 0, s, Yp, Z, out, out_f32, H, W, Co));
+    SUNET_CHECK_LAUNCH();
+    return 0;
+  }
   if (SUNET_UPC_ROWS && (r == 2 || r == 4) && nv <= 256 && H * r <= 65535 && B <= 65535) {
     int px = 1;   // pixels per block, a power of two (no ragged last block on the power-of-two SUNet rows); consecutive threads
     while (2 * px * nv <= 256) px *= 2;   // cover consecutive 16-byte vectors of the output row
